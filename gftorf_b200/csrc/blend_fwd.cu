@@ -1,0 +1,222 @@
+// blend_fwd.cu — per-tile front-to-back blend of RGB, 7-channel ToF phasor/quads, depth,
+// accumulation, depth distortion and first-hit distribution, one pass, for sm_100a.
+//
+// Replaces renderCUDA<3,7,2,1> (cuda_rasterizer/forward.cu:424-676).
+//
+// What is different from the reference kernel, and why the results are still the same:
+//   - every per-Gaussian quantity (xy, conic+opacity, rgb, 7 phasor channels, dist, ndc) is
+//     staged in shared memory from ONE 80-byte record per Gaussian; the reference stages 7 floats
+//     and re-gathers 12 more from global memory for every contributing (pixel, Gaussian) pair
+//     (forward.cu:551-572).
+//   - a 16x16 tile is covered by 8 warps of 8x4 pixels.  Each warp tests, 32 Gaussians at a time,
+//     whether a Gaussian's conservative alpha>=1/255 box reaches its 8x4 patch and only walks the
+//     survivors.  A culled pair would have hit `continue` in the reference before touching any
+//     state (forward.cu:528-537), so skipping it is exact.
+//   - the alpha chain (power, expf, min, the two thresholds, T update) is evaluated with the
+//     exact operation order of the reference binary, so `done`, n_contrib and pixels are
+//     bit-identical.
+//   - `pixels` (one global float atomic per contributing pair in the reference, forward.cu:629)
+//     is counted with a warp ballot, accumulated per tile in shared memory and flushed with one
+//     atomic per (tile, Gaussian); the counts are integers < 2^24, so any order is exact.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gft {
+
+namespace {
+
+constexpr int BATCH = 256;
+
+struct FwdSmem {
+  float4 r0[BATCH];  // x y ex ey
+  float4 r1[BATCH];  // conA conB conC opacity
+  float4 r2[BATCH];  // r g b dist
+  float4 r3[BATCH];  // ph0..ph3
+  float4 r4[BATCH];  // ph4 ph5 ph6 ndc
+  int id[BATCH];
+  int cnt[BATCH];
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(GFT_BLOCK)
+blend_fwd_kernel(BlendFwdParams p) {
+  __shared__ FwdSmem s;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
+  // warp patch: 8 wide x 4 high
+  const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
+  const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
+  const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
+  const bool inside = pix_x < (uint32_t)p.W && pix_y < (uint32_t)p.H;
+  const uint32_t pix_id = (uint32_t)p.W * pix_y + pix_x;
+  const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+  const float patch_x0 = (float)px0, patch_x1 = (float)(px0 + 7u);
+  const float patch_y0 = (float)py0, patch_y1 = (float)(py0 + 3u);
+
+  const uint2 range = p.ranges[tile];
+  const int n = (int)(range.y - range.x);
+
+  bool done = !inside;
+  bool warp_done = __all_sync(0xffffffffu, done);
+  float T = 1.0f;
+  uint32_t last_contributor = 0;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, P4 = 0.f, P5 = 0.f, P6 = 0.f;
+  float D = 0.f, A = 0.f, DD = 0.f, DD_D = 0.f, DD_D2 = 0.f;
+  float WD0 = 0.f, WD1 = 0.f, WD2 = 0.f;
+  bool first_hit = true;
+
+  for (int base = 0; base < n; base += BATCH) {
+    // End if the entire block votes that it is done (forward.cu:500-502)
+    if (__syncthreads_and(done)) break;
+
+    const int m = min(BATCH, n - base);
+    if ((int)tid < m) {
+      const int g = (int)__ldg(p.point_list + range.x + base + tid);
+      const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
+      s.id[tid] = g;
+      s.cnt[tid] = 0;
+      s.r0[tid] = __ldg(r + 0);
+      s.r1[tid] = __ldg(r + 1);
+      s.r2[tid] = __ldg(r + 2);
+      s.r3[tid] = __ldg(r + 3);
+      s.r4[tid] = __ldg(r + 4);
+    }
+    __syncthreads();
+
+    if (!warp_done) {
+      for (int c = 0; c < m; c += 32) {
+        const int jj = c + (int)lane;
+        bool hit = false;
+        if (jj < m) {
+          const float4 g0 = s.r0[jj];
+          // written so that NaN extents mean "not culled"
+          hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
+                  g0.y - g0.w > patch_y1);
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        int mycnt = 0;
+        while (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int k = c + b;
+          const float4 g0 = s.r0[k];
+          const float4 g1 = s.r1[k];
+          const float dx = __fsub_rn(g0.x, pixfx);
+          const float dy = __fsub_rn(g0.y, pixfy);
+          const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
+          bool contrib = !done && !(power > 0.0f);
+          float alpha = 0.f, test_T = 0.f;
+          if (contrib) {
+            alpha = fminf(0.99f, __fmul_rn(g1.w, expf(power)));
+            contrib = !(alpha < 1.0f / 255.0f);
+            if (contrib) {
+              test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+              if (test_T < 0.0001f) {
+                done = true;
+                contrib = false;
+              }
+            }
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
+          if ((int)lane == b) mycnt = __popc(bal);
+          if (contrib) {
+            const float4 g2 = s.r2[k];
+            const float4 g3 = s.r3[k];
+            const float4 g4 = s.r4[k];
+            const float w = __fmul_rn(T, alpha);
+            const float wp = __fmul_rn(T, w);
+            C0 = __fmaf_rn(w, g2.x, C0);
+            C1 = __fmaf_rn(w, g2.y, C1);
+            C2 = __fmaf_rn(w, g2.z, C2);
+            P0 = __fmaf_rn(wp, g3.x, P0);
+            P1 = __fmaf_rn(wp, g3.y, P1);
+            P2 = __fmaf_rn(wp, g3.z, P2);
+            P3 = __fmaf_rn(wp, g3.w, P3);
+            P4 = __fmaf_rn(wp, g4.x, P4);
+            P5 = __fmaf_rn(wp, g4.y, P5);
+            P6 = __fmaf_rn(wp, g4.z, P6);
+            if (first_hit) {  // first applied Gaussian (forward.cu:561-567)
+              WD0 = alpha;
+              WD1 = g2.w;
+              WD2 = g3.z;
+              first_hit = false;
+            }
+            // depth distortion, forward.cu:572-578 in the reference's evaluation order
+            const float z = g4.w;
+            const float z2 = __fmul_rn(z, z);
+            const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
+            float t2 = __fmaf_rn(A, z2, -t1);
+            const float wz = __fmul_rn(w, z);
+            t2 = __fadd_rn(DD_D2, t2);
+            DD_D = __fadd_rn(DD_D, wz);
+            DD_D2 = __fmaf_rn(z, wz, DD_D2);
+            D = __fmaf_rn(w, g2.w, D);
+            DD = __fmaf_rn(w, t2, DD);
+            A = __fadd_rn(A, w);
+            T = test_T;
+            last_contributor = (uint32_t)(base + k + 1);
+          }
+        }
+        if (mycnt) atomicAdd(&s.cnt[jj], mycnt);
+        if (__all_sync(0xffffffffu, done)) {
+          warp_done = true;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if ((int)tid < m) {
+      const int cnt = s.cnt[tid];
+      if (cnt) atomicAdd(p.pixels + s.id[tid], (float)cnt);
+    }
+  }
+
+  if (inside) {
+    const size_t HW = (size_t)p.H * (size_t)p.W;
+    p.img_state[pix_id] = make_float4(T, DD_D, DD_D2, __uint_as_float(last_contributor));
+    float bgv[7];
+    if (p.bg_mode == 0) {
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch * HW + pix_id);
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
+    }
+    // colour reads bg planes 0..2, phasor planes 0..6, both weighted by T (forward.cu:644,649)
+    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C0);
+    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C1);
+    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2);
+    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P0);
+    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P1);
+    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P2);
+    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P3);
+    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P4);
+    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P5);
+    p.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
+    p.out_depth[pix_id] = D;
+    p.out_acc[pix_id] = A;
+    p.out_depth_distortion[pix_id] = DD;
+    p.out_distribution[0 * HW + pix_id] = WD0;
+    p.out_distribution[1 * HW + pix_id] = WD1;
+    p.out_distribution[2 * HW + pix_id] = WD2;
+    // outputs the reference allocates but never writes (forward.cu:655-667): defined as 0
+    if (p.out_normal) {
+      p.out_normal[0 * HW + pix_id] = 0.f;
+      p.out_normal[1 * HW + pix_id] = 0.f;
+      p.out_normal[2 * HW + pix_id] = 0.f;
+    }
+    if (p.out_entropy) p.out_entropy[pix_id] = 0.f;
+    if (p.out_amp_distortion) p.out_amp_distortion[pix_id] = 0.f;
+  }
+}
+
+void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
+  const int tiles = p.grid_x * p.grid_y;
+  if (tiles <= 0) return;
+  blend_fwd_kernel<<<tiles, GFT_BLOCK, 0, stream>>>(p);
+}
+
+}  // namespace gft

@@ -1,0 +1,195 @@
+// common.cuh — shared device helpers for the sm_100a RGB+ToF Gaussian rasterizer.
+//
+// Everything that decides an INTEGER result of the pipeline (radii, tile rectangles, the depth
+// bits of the sort keys, n_contrib, pixels) is written with explicit-rounding intrinsics
+// (__fmul_rn / __fadd_rn / __fmaf_rn / __fdiv_rn / __frcp_rn / __fsqrt_rn).  The operation order
+// reproduces the dataflow nvcc 12.9 + ptxas generate for the reference expressions
+// (cuda_rasterizer/forward.cu:128-206,281-342,524-543 and auxiliary.h:44-80 of
+// submodules/diff-gaussian-rasterization-w-tof); intrinsics are never re-associated or
+// contracted, so the result does not depend on how the surrounding code is compiled.
+//
+// Contraction rule that the reference binary follows (SASS-verified):
+//   p1 + p2 + p3 (+ c)  ->  fma(p3, fma(p1, mul(p2))) (+ c as a separate add)
+//   a*c - b*b           ->  fma(a, c, -mul(b,b))
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GFT_BLOCK 256
+#define GFT_TILE_X 16
+#define GFT_TILE_Y 16
+#define GFT_REC_FLOATS 20   // blend record: 5 x float4 per Gaussian
+#define GFT_GRAD_FLOATS 20  // blend-gradient record: 5 x float4 per Gaussian
+
+namespace gft {
+
+// Spherical-harmonics constants, auxiliary.h:23-40 (constexpr scalars -> immediates in SASS)
+constexpr float kSH_C0 = 0.28209479177387814f;
+constexpr float kSH_C1 = 0.4886025119029199f;
+constexpr float kSH_C2_0 = 1.0925484305920792f;
+constexpr float kSH_C2_1 = -1.0925484305920792f;
+constexpr float kSH_C2_2 = 0.31539156525252005f;
+constexpr float kSH_C2_3 = -1.0925484305920792f;
+constexpr float kSH_C2_4 = 0.5462742152960396f;
+constexpr float kSH_C3_0 = -0.5900435899266435f;
+constexpr float kSH_C3_1 = 2.890611442640554f;
+constexpr float kSH_C3_2 = -0.4570457994644658f;
+constexpr float kSH_C3_3 = 0.3731763325901154f;
+constexpr float kSH_C3_4 = -0.4570457994644658f;
+constexpr float kSH_C3_5 = 1.445305721320277f;
+constexpr float kSH_C3_6 = -0.5900435899266435f;
+
+#define GFT_PI_F 3.14159265358979323846f  // auxiliary.h:42
+
+// a*b + c*d + e*f in the reference's contracted form: fma(e,f, fma(a,b, mul(c,d)))
+__device__ __forceinline__ float dot3c(float a, float b, float c, float d, float e, float f) {
+  return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+
+// Column-major 4x4 applied to a point: m[0]x + m[4]y + m[8]z + m[12]  (auxiliary.h:61-80)
+__device__ __forceinline__ float xform_row(const float* __restrict__ m, int r, float x, float y,
+                                           float z) {
+  return __fadd_rn(dot3c(x, m[r], y, m[r + 4], z, m[r + 8]), m[r + 12]);
+}
+
+struct Cov3 {
+  float c0, c1, c2, c3, c4, c5;
+};
+
+// computeCov3D, forward.cu:172-206 (quaternion NOT normalised; (r,x,y,z) = (q0..q3)).
+// For finite inputs the structural zeros of S drop out exactly: M[c][r] = fl(s_r * R[c][r]).
+__device__ __forceinline__ Cov3 cov3d_from_scale_rot(float sx0, float sy0, float sz0, float mod,
+                                                     float r, float x, float y, float z) {
+  const float sx = __fmul_rn(mod, sx0), sy = __fmul_rn(mod, sy0), sz = __fmul_rn(mod, sz0);
+  const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+  const float xy = __fmul_rn(x, y), rz = __fmul_rn(r, z);
+  const float xz = __fmul_rn(x, z), ry = __fmul_rn(r, y);
+  const float yz = __fmul_rn(y, z), rx = __fmul_rn(r, x);
+  const float xx_zz = __fmaf_rn(x, x, zz);
+  const float xx_yy = __fmaf_rn(x, x, yy);
+  const float yy_zz = __fadd_rn(yy, zz);
+  // glm::mat3 R (column-major fill): R[0]=(R00,R01,R02) ...
+  const float R00 = __fsub_rn(1.f, __fadd_rn(yy_zz, yy_zz));
+  const float R01 = __fadd_rn(__fsub_rn(xy, rz), __fsub_rn(xy, rz));
+  const float R02 = __fadd_rn(__fadd_rn(ry, xz), __fadd_rn(ry, xz));
+  const float R10 = __fadd_rn(__fadd_rn(xy, rz), __fadd_rn(xy, rz));
+  const float R11 = __fsub_rn(1.f, __fadd_rn(xx_zz, xx_zz));
+  const float R12 = __fadd_rn(__fsub_rn(yz, rx), __fsub_rn(yz, rx));
+  const float R20 = __fadd_rn(__fsub_rn(xz, ry), __fsub_rn(xz, ry));
+  const float R21 = __fadd_rn(__fadd_rn(rx, yz), __fadd_rn(rx, yz));
+  const float R22 = __fsub_rn(1.f, __fadd_rn(xx_yy, xx_yy));
+  // M = S * R
+  const float M00 = __fmul_rn(sx, R00), M01 = __fmul_rn(sy, R01), M02 = __fmul_rn(sz, R02);
+  const float M10 = __fmul_rn(sx, R10), M11 = __fmul_rn(sy, R11), M12 = __fmul_rn(sz, R12);
+  const float M20 = __fmul_rn(sx, R20), M21 = __fmul_rn(sy, R21), M22 = __fmul_rn(sz, R22);
+  // Sigma = transpose(M) * M, glm product order (type_mat3x3.inl:510-518)
+  Cov3 c;
+  c.c0 = dot3c(M00, M00, M01, M01, M02, M02);
+  c.c1 = dot3c(M10, M00, M11, M01, M12, M02);
+  c.c2 = dot3c(M20, M00, M21, M01, M22, M02);
+  c.c3 = dot3c(M10, M10, M11, M11, M12, M12);
+  c.c4 = dot3c(M20, M10, M21, M11, M22, M12);
+  c.c5 = dot3c(M20, M20, M21, M21, M22, M22);
+  return c;
+}
+
+// The 2x3 non-zero part of T = W * J used by computeCov2D (forward.cu:128-167,
+// backward.cu:287-313).  T0* = T[0][*], T1* = T[1][*] in glm indexing.
+struct Tmat {
+  float T00, T01, T02, T10, T11, T12;
+};
+
+__device__ __forceinline__ Tmat ewa_T(const float* __restrict__ V, float tx, float ty, float tz,
+                                      float focal_x, float focal_y, float tan_fovx,
+                                      float tan_fovy, float* cx_out = nullptr,
+                                      float* cy_out = nullptr, float* txtz_out = nullptr,
+                                      float* tytz_out = nullptr) {
+  const float limx = __fmul_rn(tan_fovx, 1.3f);
+  const float limy = __fmul_rn(tan_fovy, 1.3f);
+  const float txtz = __fdiv_rn(tx, tz);
+  const float tytz = __fdiv_rn(ty, tz);
+  const float cx = fminf(limx, fmaxf(-limx, txtz));
+  const float cy = fminf(limy, fmaxf(-limy, tytz));
+  if (cx_out) *cx_out = cx;
+  if (cy_out) *cy_out = cy;
+  if (txtz_out) *txtz_out = txtz;
+  if (tytz_out) *tytz_out = tytz;
+  const float tz2 = __fmul_rn(tz, tz);
+  const float J00 = __fdiv_rn(focal_x, tz);
+  const float J02 = __fdiv_rn(__fmul_rn(focal_x, __fmul_rn(cx, -tz)), tz2);
+  const float J11 = __fdiv_rn(focal_y, tz);
+  const float J12 = __fdiv_rn(__fmul_rn(focal_y, __fmul_rn(cy, -tz)), tz2);
+  Tmat t;
+  t.T00 = __fmaf_rn(V[2], J02, __fmul_rn(V[0], J00));
+  t.T01 = __fmaf_rn(V[6], J02, __fmul_rn(V[4], J00));
+  t.T02 = __fmaf_rn(V[10], J02, __fmul_rn(V[8], J00));
+  t.T10 = __fmaf_rn(V[2], J12, __fmul_rn(J11, V[1]));
+  t.T11 = __fmaf_rn(V[6], J12, __fmul_rn(J11, V[5]));
+  t.T12 = __fmaf_rn(V[10], J12, __fmul_rn(J11, V[9]));
+  return t;
+}
+
+// cov = transpose(T) * transpose(Vrk) * T, returns (cov[0][0]+0.3, cov[0][1], cov[1][1]+0.3)
+__device__ __forceinline__ float3 ewa_cov2d(const Tmat& t, const Cov3& v) {
+  const float B00 = dot3c(t.T00, v.c0, t.T01, v.c1, t.T02, v.c2);
+  const float B01 = dot3c(t.T10, v.c0, t.T11, v.c1, t.T12, v.c2);
+  const float B10 = dot3c(t.T00, v.c1, t.T01, v.c3, t.T02, v.c4);
+  const float B11 = dot3c(t.T10, v.c1, t.T11, v.c3, t.T12, v.c4);
+  const float B20 = dot3c(t.T00, v.c2, t.T01, v.c4, t.T02, v.c5);
+  const float B21 = dot3c(t.T10, v.c2, t.T11, v.c4, t.T12, v.c5);
+  float3 c;
+  c.x = __fadd_rn(dot3c(t.T00, B00, t.T01, B10, t.T02, B20), 0.3f);
+  c.y = dot3c(t.T00, B01, t.T01, B11, t.T02, B21);
+  c.z = __fadd_rn(dot3c(t.T10, B01, t.T11, B11, t.T12, B21), 0.3f);
+  return c;
+}
+
+// ndc2Pix, auxiliary.h:44-47 — evaluated in double with a double FMA, rounded once to float.
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+  return __double2float_rn(
+      __dmul_rn(__fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0), 0.5));
+}
+
+// getRect, auxiliary.h:49-59.  `radius` is the int-converted radius; grid in tiles.
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy,
+                                          uint32_t& x0, uint32_t& y0, uint32_t& x1, uint32_t& y1) {
+  const float rf = (float)radius;
+  x0 = min((uint32_t)gx, (uint32_t)max(0, (int)__fmul_rn(__fsub_rn(px, rf), 0.0625f)));
+  y0 = min((uint32_t)gy, (uint32_t)max(0, (int)__fmul_rn(__fsub_rn(py, rf), 0.0625f)));
+  x1 = min((uint32_t)gx,
+           (uint32_t)max(0, (int)__fmul_rn(
+                                __fadd_rn(__fadd_rn(__fadd_rn(px, rf), 16.f), -1.f), 0.0625f)));
+  y1 = min((uint32_t)gy,
+           (uint32_t)max(0, (int)__fmul_rn(
+                                __fadd_rn(__fadd_rn(__fadd_rn(py, rf), 16.f), -1.f), 0.0625f)));
+}
+
+// Gaussian falloff exponent of one (pixel, Gaussian) pair, forward.cu:524-527 as compiled:
+//   u = dy*(dy*C); v = dy*(dx*B); q = fma(dx, dx*A, u); power = fma(q, -0.5, -v)
+__device__ __forceinline__ float pair_power(float dx, float dy, float A, float B, float C) {
+  const float u = __fmul_rn(dy, __fmul_rn(dy, C));
+  const float v = __fmul_rn(dy, __fmul_rn(dx, B));
+  const float q = __fmaf_rn(dx, __fmul_rn(dx, A), u);
+  return __fmaf_rn(q, -0.5f, -v);
+}
+
+// ---- warp helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Relaxed/acquire 64-bit accesses for the decoupled look-back scan.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+}  // namespace gft

@@ -1,0 +1,417 @@
+// preprocess.cu — per-Gaussian forward preprocessing for sm_100a, fused with the tile-count scan.
+//
+// Replaces, in ONE kernel:
+//   - preprocessCUDA<3,7,2>   (cuda_rasterizer/forward.cu:251-419)  frustum-z cull, projection,
+//     cov3D, EWA cov2D (+0.3), conic, radius, tile rectangle, SH->RGB, SH->(phase, amp),
+//     phasor/quad synthesis with 1/d^2 falloff, distance-to-light, ndc distance;
+//   - cub::DeviceScan::InclusiveSum over tiles_touched (rasterizer_impl.cu:307) — done here as a
+//     single-pass chained scan with decoupled look-back, so point_offsets and num_rendered come
+//     out of the same launch;
+//   - the zero-fill of `pixels` and of the tile ranges (rasterize_points.cu:83,
+//     rasterizer_impl.cu:341).
+//
+// Data layout written (HBM): one 80-byte "blend record" per Gaussian
+//     x y ex ey | conA conB conC opacity | r g b dist | ph0 ph1 ph2 ph3 | ph4 ph5 ph6 ndc
+// so the blend kernels fetch a Gaussian with five 16-byte loads from one place instead of seven
+// scattered arrays; (ex, ey) are conservative half-extents of the region where the Gaussian can
+// reach alpha >= 1/255, used for exact sub-tile culling.
+#include <cstdio>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gft {
+
+namespace {
+
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
+  // Basis values multiplying sh[1..15], in the association of forward.cu:37-59 (SH_Ck * poly).
+  if (deg > 0) {
+    b[1] = -kSH_C1 * y;
+    b[2] = kSH_C1 * z;
+    b[3] = -kSH_C1 * x;
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z;
+      const float xy = x * y, yz = y * z, xz = x * z;
+      b[4] = kSH_C2_0 * xy;
+      b[5] = kSH_C2_1 * yz;
+      b[6] = kSH_C2_2 * (2.0f * zz - xx - yy);
+      b[7] = kSH_C2_3 * xz;
+      b[8] = kSH_C2_4 * (xx - yy);
+      if (deg > 2) {
+        b[9] = kSH_C3_0 * y * (3.0f * xx - yy);
+        b[10] = kSH_C3_1 * xy * z;
+        b[11] = kSH_C3_2 * y * (4.0f * zz - xx - yy);
+        b[12] = kSH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+        b[13] = kSH_C3_4 * x * (4.0f * zz - xx - yy);
+        b[14] = kSH_C3_5 * z * (xx - yy);
+        b[15] = kSH_C3_6 * x * (xx - 3.0f * yy);
+      }
+    }
+  }
+}
+
+// Load n floats of one SH row; 16-byte vector loads when the row is 16-byte aligned.
+template <int MAXN>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int n, float* dst) {
+  if ((((uintptr_t)row) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = n >> 2;
+#pragma unroll
+    for (int i = 0; i < MAXN / 4; ++i) {
+      if (i < n4) {
+        const float4 v = __ldg(r4 + i);
+        dst[4 * i + 0] = v.x;
+        dst[4 * i + 1] = v.y;
+        dst[4 * i + 2] = v.z;
+        dst[4 * i + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = 4 * n4 + i;
+      if (k < n) dst[k] = __ldg(row + k);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i)
+      if (i < n) dst[i] = __ldg(row + i);
+  }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(GFT_BLOCK)
+preprocess_fwd_kernel(PreprocessParams p) {
+  __shared__ uint32_t s_vbid;
+  __shared__ uint32_t s_warp_tot[GFT_BLOCK / 32];
+  __shared__ uint32_t s_prefix;
+
+  // Dynamic block id: a block only ever waits on blocks that already hold a ticket, so the
+  // look-back below cannot deadlock whatever order the hardware schedules blocks in.
+  if (threadIdx.x == 0) s_vbid = atomicAdd(p.scan_ticket, 1u);
+  __syncthreads();
+  const uint32_t vb = s_vbid;
+  const int idx = (int)(vb * GFT_BLOCK + threadIdx.x);
+
+  // Zero tile ranges (empty tiles must read (0,0), rasterizer_impl.cu:341).
+  for (int t = idx; t < p.num_tiles; t += gridDim.x * GFT_BLOCK) p.ranges[t] = make_uint2(0u, 0u);
+
+  uint32_t tiles = 0;
+  if (idx < p.P) {
+    int radius_i = 0;
+    uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+    p.pixels[idx] = 0.f;
+
+    const float* __restrict__ V = p.viewmatrix;
+    const float* __restrict__ PM = p.projmatrix;
+    const float px = __ldg(p.means3D + 3 * idx + 0);
+    const float py = __ldg(p.means3D + 3 * idx + 1);
+    const float pz = __ldg(p.means3D + 3 * idx + 2);
+
+    // in_frustum, auxiliary.h:152-179: z-only test (NaN passes, as in the reference).
+    const float vz = xform_row(V, 2, px, py, pz);
+    bool alive = !(vz < p.near_n || vz > p.far_n);
+    if (!alive && p.prefiltered) {
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+
+    float vx = 0.f, vy = 0.f, pix_x = 0.f, pix_y = 0.f;
+    float3 cov = make_float3(0.f, 0.f, 0.f);
+    float det = 0.f;
+    Cov3 c3;
+    if (alive) {
+      vx = xform_row(V, 0, px, py, pz);
+      vy = xform_row(V, 1, px, py, pz);
+      const float hx = xform_row(PM, 0, px, py, pz);
+      const float hy = xform_row(PM, 1, px, py, pz);
+      const float hw = xform_row(PM, 3, px, py, pz);
+      const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
+      const float projx = __fmul_rn(hx, p_w);
+      const float projy = __fmul_rn(hy, p_w);
+
+      if (p.cov3D_precomp != nullptr) {
+        const float* c = p.cov3D_precomp + 6 * (size_t)idx;
+        c3.c0 = __ldg(c + 0); c3.c1 = __ldg(c + 1); c3.c2 = __ldg(c + 2);
+        c3.c3 = __ldg(c + 3); c3.c4 = __ldg(c + 4); c3.c5 = __ldg(c + 5);
+      } else {
+        const float* s = p.scales + 3 * (size_t)idx;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+        c3 = cov3d_from_scale_rot(__ldg(s), __ldg(s + 1), __ldg(s + 2), p.scale_modifier, q.x, q.y,
+                                  q.z, q.w);
+        // cov3D is saved for the backward pass (rasterizer_impl.cu:471)
+        float2* dst = reinterpret_cast<float2*>(p.cov3D + 6 * (size_t)idx);
+        dst[0] = make_float2(c3.c0, c3.c1);
+        dst[1] = make_float2(c3.c2, c3.c3);
+        dst[2] = make_float2(c3.c4, c3.c5);
+      }
+
+      const Tmat T = ewa_T(V, vx, vy, vz, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy);
+      cov = ewa_cov2d(T, c3);
+      det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
+      alive = !(det == 0.0f);  // forward.cu:325
+      if (alive) {
+        const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
+        const float disc = fmaxf(__fmaf_rn(mid, mid, -det), 0.1f);
+        const float s = __fsqrt_rn(disc);
+        const float lam = fmaxf(__fadd_rn(mid, s), __fsub_rn(mid, s));
+        const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(lam), 3.f));
+        radius_i = (int)my_radius;
+        pix_x = ndc2pix(projx, p.W);
+        pix_y = ndc2pix(projy, p.H);
+        tile_rect(pix_x, pix_y, radius_i, p.grid_x, p.grid_y, rx0, ry0, rx1, ry1);
+        tiles = (rx1 - rx0) * (ry1 - ry0);
+        alive = tiles != 0;
+      }
+    }
+
+    if (alive) {
+      const float det_inv = __frcp_rn(det);
+      const float conA = __fmul_rn(cov.z, det_inv);
+      const float conB = __fmul_rn(cov.y, -det_inv);
+      const float conC = __fmul_rn(cov.x, det_inv);
+      const float opacity = __ldg(p.opacities + idx);
+
+      // ---- view direction and SH basis (forward.cu:25-27,74-76) ------------------------
+      float basis[16];
+      float dirx = 0.f, diry = 0.f, dirz = 0.f;
+      if (p.shs != nullptr || p.shs_p != nullptr) {
+        const float cxw = __ldg(p.campos + 0), cyw = __ldg(p.campos + 1), czw = __ldg(p.campos + 2);
+        dirx = px - cxw;
+        diry = py - cyw;
+        dirz = pz - czw;
+        const float len = sqrtf(dirx * dirx + diry * diry + dirz * dirz);
+        dirx = dirx / len;
+        diry = diry / len;
+        dirz = dirz / len;
+        sh_basis(p.D, dirx, diry, dirz, basis);
+      }
+      const int ncoef = (p.D + 1) * (p.D + 1);
+
+      // ---- colour (forward.cu:346-359) ---------------------------------------------------
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+      uint32_t clamp_bits = 0;
+      if (p.colors_precomp != nullptr) {
+        cr = __ldg(p.colors_precomp + 3 * (size_t)idx + 0);
+        cg = __ldg(p.colors_precomp + 3 * (size_t)idx + 1);
+        cb = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
+      }
+      if (p.shs != nullptr) {
+        float sh[48];
+        const int n = min(ncoef, p.M);
+        load_row<48>(p.shs + (size_t)idx * p.M * 3, 3 * n, sh);
+        float r0 = kSH_C0 * sh[0], r1 = kSH_C0 * sh[1], r2 = kSH_C0 * sh[2];
+        if (p.D > 0) {
+          // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3   (basis carries the sign)
+#pragma unroll
+          for (int k = 1; k < 4; ++k) {
+            r0 += basis[k] * sh[3 * k + 0];
+            r1 += basis[k] * sh[3 * k + 1];
+            r2 += basis[k] * sh[3 * k + 2];
+          }
+          if (p.D > 1) {
+#pragma unroll
+            for (int k = 4; k < 9; ++k) {
+              r0 += basis[k] * sh[3 * k + 0];
+              r1 += basis[k] * sh[3 * k + 1];
+              r2 += basis[k] * sh[3 * k + 2];
+            }
+            if (p.D > 2) {
+#pragma unroll
+              for (int k = 9; k < 16; ++k) {
+                r0 += basis[k] * sh[3 * k + 0];
+                r1 += basis[k] * sh[3 * k + 1];
+                r2 += basis[k] * sh[3 * k + 2];
+              }
+            }
+          }
+        }
+        r0 += 0.5f; r1 += 0.5f; r2 += 0.5f;
+        clamp_bits |= (r0 < 0.f) ? 1u : 0u;
+        clamp_bits |= (r1 < 0.f) ? (1u << 8) : 0u;
+        clamp_bits |= (r2 < 0.f) ? (1u << 16) : 0u;
+        cr = fmaxf(r0, 0.f); cg = fmaxf(r1, 0.f); cb = fmaxf(r2, 0.f);
+      }
+
+      // ---- distance to light, falloff (forward.cu:361-363) -------------------------------
+      const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
+      const float ndc = p.far_n / (p.far_n - p.near_n) * (1 - p.near_n / dist);
+      const float factor = 1.0f / (dist * dist);
+
+      // ---- phasor (forward.cu:365-407) ----------------------------------------------------
+      // With neither shs_p nor phasors_precomp the reference leaves real_img_amp uninitialised
+      // (SURVEY A.7-7); we define those features as 0.
+      float ph[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float pa0 = 0.f, pa1 = 0.f;
+      bool have_ph = false;
+      float phase = 0.f, amp = 0.f;
+      if (p.phasors_precomp != nullptr) {
+        phase = dist * p.dist2phase;
+        pa0 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 0);
+        pa1 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 1);
+        if (p.use_view_dependent_phase) phase += pa0;
+        amp = pa1;
+        have_ph = true;
+      }
+      if (p.shs_p != nullptr) {
+        float sp[32];
+        const int n = min(ncoef, p.M_p);
+        load_row<32>(p.shs_p + (size_t)idx * p.M_p * 2, 2 * n, sp);
+        float q0 = kSH_C0 * sp[0], q1 = kSH_C0 * sp[1];
+        if (p.D > 0) {
+#pragma unroll
+          for (int k = 1; k < 4; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
+          if (p.D > 1) {
+#pragma unroll
+            for (int k = 4; k < 9; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
+            if (p.D > 2) {
+#pragma unroll
+              for (int k = 9; k < 16; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
+            }
+          }
+        }
+        q0 += 0.5f; q1 += 0.5f;
+        q0 = q0 - 0.5f - kSH_C0 * sp[0];  // remove phase DC (forward.cu:115)
+        if (q1 < 0.f) { clamp_bits |= (1u << 24); q1 = 0.f; }
+        pa0 = q0; pa1 = q1;
+        phase = dist * p.dist2phase + p.phase_offset;
+        if (p.use_view_dependent_phase) phase += q0;
+        amp = q1;
+        have_ph = true;
+      }
+      if (have_ph) {
+        float sn, cs;
+        sincosf(phase, &sn, &cs);
+        ph[0] = cs * amp * factor;
+        ph[1] = sn * amp * factor;
+        ph[2] = amp * factor;
+        ph[3] = (cs + p.dc_offset) * amp * factor;
+        ph[4] = (-cs + p.dc_offset) * amp * factor;
+        ph[5] = (sn + p.dc_offset) * amp * factor;
+        ph[6] = (-sn + p.dc_offset) * amp * factor;
+      }
+
+      // ---- conservative contribution extents for sub-tile culling -----------------------
+      // A pixel can pass the alpha test only if opacity*exp(power) >= 1/255, i.e.
+      // d^T Q d <= 2 ln(255*opacity).  The rounding error of the float `power` chain is bounded
+      // by 2k*cond(Sigma)*q (k = 4e-7), so inflating the threshold by 1/(1-4k*cond) keeps the box
+      // a superset of what the reference's arithmetic can accept.  Anything doubtful -> no cull.
+      float ex = __int_as_float(0x7f800000), ey = __int_as_float(0x7f800000);  // +inf
+      if (!p.subtile_cull) {
+        // keep +inf: no culling
+      } else if (opacity < (1.0f / 255.0f)) {
+        ex = ey = -__int_as_float(0x7f800000);  // alpha <= opacity < 1/255: can never contribute
+      } else {
+        const double dA = (double)conA, dB = (double)conB, dC = (double)conC;
+        const double dq = dA * dC - dB * dB;
+        const float mid = 0.5f * (cov.x + cov.z);
+        const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lmax = mid + sq, lmin = mid - sq;
+        const float cond = lmax / lmin;
+        if (dq > 0.0 && dA > 0.0 && dC > 0.0 && lmin > 0.f && cond < 2.0e5f && cond == cond) {
+          const float t2 = (2.0f * __logf(255.0f * opacity) + 0.04f) / (1.0f - 1.6e-6f * cond);
+          const float sxx = (float)(dC / dq), syy = (float)(dA / dq);
+          ex = sqrtf(t2 * sxx) * 1.0001f + 0.02f;
+          ey = sqrtf(t2 * syy) * 1.0001f + 0.02f;
+        }
+      }
+
+      float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS);
+      rec[0] = make_float4(pix_x, pix_y, ex, ey);
+      rec[1] = make_float4(conA, conB, conC, opacity);
+      rec[2] = make_float4(cr, cg, cb, dist);
+      rec[3] = make_float4(ph[0], ph[1], ph[2], ph[3]);
+      rec[4] = make_float4(ph[4], ph[5], ph[6], ndc);
+      p.depths[idx] = vz;
+      p.clamped[idx] = clamp_bits;
+      reinterpret_cast<float2*>(p.pa)[idx] = make_float2(pa0, pa1);
+      reinterpret_cast<uint2*>(p.rect)[idx] =
+          make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
+    } else {
+      tiles = 0;
+      radius_i = 0;
+    }
+    p.radii[idx] = alive ? radius_i : 0;
+    p.tiles_touched[idx] = tiles;
+  }
+
+  // ---- block-wide inclusive scan of `tiles` ------------------------------------------------
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += n;
+  }
+  if (lane == 31) s_warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t warp_base = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < GFT_BLOCK / 32; ++w) {
+    const uint32_t t = s_warp_tot[w];
+    if ((uint32_t)w < warp) warp_base += t;
+    block_total += t;
+  }
+  incl += warp_base;
+
+  // ---- chained scan across blocks: status word = flag<<32 | value --------------------------
+  // flag 1 = block aggregate available, 2 = inclusive prefix available.
+  if (warp == 0) {
+    unsigned long long* st = p.scan_state;
+    uint32_t excl = 0;
+    if (vb == 0) {
+      if (lane == 0) st_release_u64(st, (2ull << 32) | block_total);
+    } else {
+      if (lane == 0) st_release_u64(st + vb, (1ull << 32) | block_total);
+      int base = (int)vb - 1;
+      while (true) {
+        const int j = base - (int)lane;
+        unsigned long long s = 0;
+        if (j >= 0) {
+          do { s = ld_acquire_u64(st + j); } while ((s >> 32) == 0ull);
+        }
+        const uint32_t flag = j >= 0 ? (uint32_t)(s >> 32) : 2u;  // virtual prefix 0 before block 0
+        const uint32_t val = j >= 0 ? (uint32_t)s : 0u;
+        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
+        // sum values of lanes up to and including the first (nearest) lane holding a prefix
+        const int first = pmask ? (__ffs(pmask) - 1) : 31;
+        uint32_t v = (lane <= (uint32_t)first) ? val : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (pmask) break;
+        base -= 32;
+      }
+      if (lane == 0) st_release_u64(st + vb, (2ull << 32) | (unsigned long long)(excl + block_total));
+    }
+    if (lane == 0) {
+      s_prefix = excl;
+      if (vb == gridDim.x - 1) *p.num_rendered = excl + block_total;
+    }
+  }
+  __syncthreads();
+  if (idx < p.P) p.point_offsets[idx] = s_prefix + incl;
+}
+
+// markVisible / checkFrustum, rasterizer_impl.cu:54-68
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ V, uint8_t* __restrict__ present,
+                                    float near_n, float far_n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float vz = xform_row(V, 2, __ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1),
+                             __ldg(means3D + 3 * idx + 2));
+  present[idx] = !(vz < near_n || vz > far_n);
+}
+
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
+  const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
+  preprocess_fwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present,
+                         float near_n, float far_n, cudaStream_t stream) {
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, V, present, near_n, far_n);
+}
+
+}  // namespace gft

@@ -1,0 +1,435 @@
+// preprocess_bwd.cu — per-Gaussian backward of the preprocessing, ONE kernel for sm_100a.
+//
+// Replaces computeCov2DCUDA (cuda_rasterizer/backward.cu:265-395) and preprocessCUDA<3,7,2>
+// (backward.cu:467-606) with their helpers computeColorFromSH (:20-139), computePhasorFromSH
+// (:143-260) and computeCov3D (:399-462).  The reference runs two kernels that communicate through
+// dL_dmeans / dL_dcov3D in global memory and relies on 15 zero-filled tensors
+// (rasterize_points.cu:222-236); here everything for one Gaussian stays in registers, every output
+// row is written exactly once (zeros for culled Gaussians and for SH coefficients above the active
+// degree), and the two scalar gradients (phase_offset, dc_offset), which the reference accumulates
+// with one global atomic per Gaussian on a single address (backward.cu:556,567), are block-reduced
+// first: one atomic per 256 Gaussians.
+//
+// Input: the 20-float gradient record per Gaussian produced by blend_bwd.cu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gft {
+
+namespace {
+
+struct V3 { float x, y, z; };
+
+// dnormvdv(float3, float3), auxiliary.h:102-113
+__device__ __forceinline__ V3 dnormvdv3(V3 v, V3 dv) {
+  const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+  V3 o;
+  o.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+  o.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+  o.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+  return o;
+}
+
+// SH backward shared by colour (NC=3) and phasor (NC=2): writes dL_dsh rows [0, ncoef) and zero
+// rows [ncoef, M); returns dL/ddir (before the normalisation Jacobian).
+template <int NC>
+__device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, float z,
+                                          const float* __restrict__ sh, const float* g,
+                                          float* __restrict__ dsh) {
+  float dx[NC], dy[NC], dz[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { dx[c] = 0.f; dy[c] = 0.f; dz[c] = 0.f; }
+  auto put = [&](int k, float basis) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = basis * g[c];
+  };
+  put(0, kSH_C0);
+  if (deg > 0) {
+    put(1, -kSH_C1 * y);
+    put(2, kSH_C1 * z);
+    put(3, -kSH_C1 * x);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      dx[c] = -kSH_C1 * sh[3 * NC + c];
+      dy[c] = -kSH_C1 * sh[1 * NC + c];
+      dz[c] = kSH_C1 * sh[2 * NC + c];
+    }
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z;
+      const float xy = x * y, yz = y * z, xz = x * z;
+      put(4, kSH_C2_0 * xy);
+      put(5, kSH_C2_1 * yz);
+      put(6, kSH_C2_2 * (2.f * zz - xx - yy));
+      put(7, kSH_C2_3 * xz);
+      put(8, kSH_C2_4 * (xx - yy));
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float s4 = sh[4 * NC + c], s5 = sh[5 * NC + c], s6 = sh[6 * NC + c],
+                    s7 = sh[7 * NC + c], s8 = sh[8 * NC + c];
+        dx[c] += kSH_C2_0 * y * s4 + kSH_C2_2 * 2.f * -x * s6 + kSH_C2_3 * z * s7 +
+                 kSH_C2_4 * 2.f * x * s8;
+        dy[c] += kSH_C2_0 * x * s4 + kSH_C2_1 * z * s5 + kSH_C2_2 * 2.f * -y * s6 +
+                 kSH_C2_4 * 2.f * -y * s8;
+        dz[c] += kSH_C2_1 * y * s5 + kSH_C2_2 * 2.f * 2.f * z * s6 + kSH_C2_3 * x * s7;
+      }
+      if (deg > 2) {
+        put(9, kSH_C3_0 * y * (3.f * xx - yy));
+        put(10, kSH_C3_1 * xy * z);
+        put(11, kSH_C3_2 * y * (4.f * zz - xx - yy));
+        put(12, kSH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
+        put(13, kSH_C3_4 * x * (4.f * zz - xx - yy));
+        put(14, kSH_C3_5 * z * (xx - yy));
+        put(15, kSH_C3_6 * x * (xx - 3.f * yy));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float s9 = sh[9 * NC + c], s10 = sh[10 * NC + c], s11 = sh[11 * NC + c],
+                      s12 = sh[12 * NC + c], s13 = sh[13 * NC + c], s14 = sh[14 * NC + c],
+                      s15 = sh[15 * NC + c];
+          dx[c] += (kSH_C3_0 * s9 * 3.f * 2.f * xy + kSH_C3_1 * s10 * yz +
+                    kSH_C3_2 * s11 * -2.f * xy + kSH_C3_3 * s12 * -3.f * 2.f * xz +
+                    kSH_C3_4 * s13 * (-3.f * xx + 4.f * zz - yy) + kSH_C3_5 * s14 * 2.f * xz +
+                    kSH_C3_6 * s15 * 3.f * (xx - yy));
+          dy[c] += (kSH_C3_0 * s9 * 3.f * (xx - yy) + kSH_C3_1 * s10 * xz +
+                    kSH_C3_2 * s11 * (-3.f * yy + 4.f * zz - xx) +
+                    kSH_C3_3 * s12 * -3.f * 2.f * yz + kSH_C3_4 * s13 * -2.f * xy +
+                    kSH_C3_5 * s14 * -2.f * yz + kSH_C3_6 * s15 * -3.f * 2.f * xy);
+          dz[c] += (kSH_C3_1 * s10 * xy + kSH_C3_2 * s11 * 4.f * 2.f * yz +
+                    kSH_C3_3 * s12 * 3.f * (2.f * zz - xx - yy) +
+                    kSH_C3_4 * s13 * 4.f * 2.f * xz + kSH_C3_5 * s14 * (xx - yy));
+        }
+      }
+    }
+  }
+  const int ncoef = (deg + 1) * (deg + 1);
+  for (int k = ncoef; k < M; ++k) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = 0.f;
+  }
+  V3 d = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {  // glm::dot(dXdx, dL_dX)
+    d.x += dx[c] * g[c];
+    d.y += dy[c] * g[c];
+    d.z += dz[c] * g[c];
+  }
+  return d;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    t = lane < GFT_BLOCK / 32 ? s_red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(GFT_BLOCK)
+preprocess_bwd_kernel(PreprocessBwdParams p) {
+  __shared__ float s_red[GFT_BLOCK / 32];
+  const int idx = blockIdx.x * GFT_BLOCK + threadIdx.x;
+  const bool in_range = idx < p.P;
+  const bool vis = in_range && (__ldg(p.radii + idx) > 0);
+
+  float part_phase = 0.f, part_dc = 0.f;
+
+  if (in_range && !vis) {
+    // culled: every output row is zero (the reference leaves its zero-filled tensors untouched)
+    p.dL_dmeans2D[3 * (size_t)idx + 0] = 0.f;
+    p.dL_dmeans2D[3 * (size_t)idx + 1] = 0.f;
+    p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+    p.dL_dopacity[idx] = 0.f;
+    p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
+    p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
+    p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
+    if (p.dL_dsh) for (int k = 0; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * 3 * p.M + k] = 0.f;
+    if (p.dL_dsh_p) for (int k = 0; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * 2 * p.M_p + k] = 0.f;
+    if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
+    if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
+    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = 0.f;
+    if (p.dL_dphasors) for (int k = 0; k < 7; ++k) p.dL_dphasors[7 * (size_t)idx + k] = 0.f;
+    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
+    if (p.dL_dconic) for (int k = 0; k < 4; ++k) p.dL_dconic[4 * (size_t)idx + k] = 0.f;
+    if (p.dL_ddist) p.dL_ddist[idx] = 0.f;
+    if (p.dL_dndc) p.dL_dndc[idx] = 0.f;
+  }
+
+  if (vis) {
+    const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * GFT_GRAD_FLOATS);
+    const float4 a0 = __ldg(gr + 0), a1 = __ldg(gr + 1), a2 = __ldg(gr + 2), a3 = __ldg(gr + 3),
+                 a4 = __ldg(gr + 4);
+    const float dm2x = a0.x, dm2y = a0.y;
+    const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
+    const float dopac = a1.y;
+    const float dcol[3] = {a1.z, a1.w, a2.x};
+    const float ddist_rec = a2.y, dndc_rec = a2.z;
+    const float dph[7] = {a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y};
+
+    const float* __restrict__ V = p.viewmatrix;
+    const float* __restrict__ proj = p.projmatrix;
+    const float mx = __ldg(p.means3D + 3 * (size_t)idx + 0);
+    const float my = __ldg(p.means3D + 3 * (size_t)idx + 1);
+    const float mz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+
+    // pass-through outputs
+    p.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
+    p.dL_dmeans2D[3 * (size_t)idx + 1] = dm2y;
+    p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+    p.dL_dopacity[idx] = dopac;
+    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol[k];
+    if (p.dL_dphasors) for (int k = 0; k < 7; ++k) p.dL_dphasors[7 * (size_t)idx + k] = dph[k];
+    if (p.dL_dconic) {
+      reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+    }
+    if (p.dL_ddist) p.dL_ddist[idx] = ddist_rec;
+    if (p.dL_dndc) p.dL_dndc[idx] = dndc_rec;
+
+    // ---------------- cov2D backward (backward.cu:276-394) -----------------------------------
+    const float* c3 = p.cov3D + 6 * (size_t)idx;
+    const float v0 = __ldg(c3 + 0), v1 = __ldg(c3 + 1), v2 = __ldg(c3 + 2), v3 = __ldg(c3 + 3),
+                v4 = __ldg(c3 + 4), v5 = __ldg(c3 + 5);
+    float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+    float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+    const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+    const float m_view_x = tx, m_view_y = ty, m_view_z = tz;
+    const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+    const float txtz = tx / tz, tytz = ty / tz;
+    tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    const float h_x = p.focal_x, h_y = p.focal_y;
+    const float J00 = h_x / tz, J02 = -(h_x * tx) / (tz * tz);
+    const float J11 = h_y / tz, J12 = -(h_y * ty) / (tz * tz);
+    // T = W * J in glm indexing (T[c][r]): T0r = W[0][r]*J00 + W[2][r]*J02 with W[c][r] = V[4r + c]
+    const float T00 = V[0] * J00 + V[2] * J02;
+    const float T01 = V[4] * J00 + V[6] * J02;
+    const float T02 = V[8] * J00 + V[10] * J02;
+    const float T10 = V[1] * J11 + V[2] * J12;
+    const float T11 = V[5] * J11 + V[6] * J12;
+    const float T12 = V[9] * J11 + V[10] * J12;
+    // cov2D = T^T * Vrk^T * T, upper 2x2
+    const float B00 = T00 * v0 + T01 * v1 + T02 * v2;  // (Vrk * T[0]) rows
+    const float B01 = T00 * v1 + T01 * v3 + T02 * v4;
+    const float B02 = T00 * v2 + T01 * v4 + T02 * v5;
+    const float B10 = T10 * v0 + T11 * v1 + T12 * v2;
+    const float B11 = T10 * v1 + T11 * v3 + T12 * v4;
+    const float B12 = T10 * v2 + T11 * v4 + T12 * v5;
+    const float a = T00 * B00 + T01 * B01 + T02 * B02 + 0.3f;
+    const float b = T00 * B10 + T01 * B11 + T02 * B12;
+    const float c = T10 * B10 + T11 * B11 + T12 * B12 + 0.3f;
+
+    const float denom = a * c - b * b;
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (denom2inv != 0) {
+      dL_da = denom2inv * (-c * c * dcon_x + 2 * b * c * dcon_y + (denom - a * c) * dcon_w);
+      dL_dc = denom2inv * (-a * a * dcon_w + 2 * a * b * dcon_y + (denom - a * c) * dcon_x);
+      dL_db = denom2inv * 2 * (b * c * dcon_x - (denom + 2 * b * b) * dcon_y + a * b * dcon_w);
+      dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+      dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+      dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+      dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+      dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+      dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+    }
+    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+
+    // dL/dT (backward.cu:358-369): B0* = T[0]-row products with Vrk, B1* likewise
+    const float dL_dT00 = 2 * B00 * dL_da + B10 * dL_db;
+    const float dL_dT01 = 2 * B01 * dL_da + B11 * dL_db;
+    const float dL_dT02 = 2 * B02 * dL_da + B12 * dL_db;
+    const float dL_dT10 = 2 * B10 * dL_dc + B00 * dL_db;
+    const float dL_dT11 = 2 * B11 * dL_dc + B01 * dL_db;
+    const float dL_dT12 = 2 * B12 * dL_dc + B02 * dL_db;
+    // dL/dJ (backward.cu:373-376): W[c][r] = V[4r + c]
+    const float dL_dJ00 = V[0] * dL_dT00 + V[4] * dL_dT01 + V[8] * dL_dT02;
+    const float dL_dJ02 = V[2] * dL_dT00 + V[6] * dL_dT01 + V[10] * dL_dT02;
+    const float dL_dJ11 = V[1] * dL_dT10 + V[5] * dL_dT11 + V[9] * dL_dT12;
+    const float dL_dJ12 = V[2] * dL_dT10 + V[6] * dL_dT11 + V[10] * dL_dT12;
+    const float itz = 1.f / tz;
+    const float itz2 = itz * itz;
+    const float itz3 = itz2 * itz;
+    const float dL_dtx = x_grad_mul * -h_x * itz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -h_y * itz2 * dL_dJ12;
+    const float dL_dtz = -h_x * itz2 * dL_dJ00 - h_y * itz2 * dL_dJ11 +
+                         (2 * h_x * tx) * itz3 * dL_dJ02 + (2 * h_y * ty) * itz3 * dL_dJ12;
+    // transformVec4x3Transpose (auxiliary.h:91-100)
+    float dmx = V[0] * dL_dtx + V[1] * dL_dty + V[2] * dL_dtz;
+    float dmy = V[4] * dL_dtx + V[5] * dL_dty + V[6] * dL_dtz;
+    float dmz = V[8] * dL_dtx + V[9] * dL_dty + V[10] * dL_dtz;
+
+    // ---------------- mean2D -> mean3D (backward.cu:498-519) ---------------------------------
+    {
+      const float m_hom_w = proj[3] * mx + proj[7] * my + proj[11] * mz + proj[15];
+      const float m_w = 1.0f / (m_hom_w + 0.0000001f);
+      const float mul1 = (proj[0] * mx + proj[4] * my + proj[8] * mz + proj[12]) * m_w * m_w;
+      const float mul2 = (proj[1] * mx + proj[5] * my + proj[9] * mz + proj[13]) * m_w * m_w;
+      dmx += (proj[0] * m_w - proj[3] * mul1) * dm2x + (proj[1] * m_w - proj[3] * mul2) * dm2y;
+      dmy += (proj[4] * m_w - proj[7] * mul1) * dm2x + (proj[5] * m_w - proj[7] * mul2) * dm2y;
+      dmz += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
+    }
+
+    // ---------------- view direction ---------------------------------------------------------
+    V3 dir_orig = {0.f, 0.f, 0.f};
+    float dirx = 0.f, diry = 0.f, dirz = 0.f;
+    if (p.shs != nullptr || p.shs_p != nullptr) {
+      dir_orig.x = mx - __ldg(p.campos + 0);
+      dir_orig.y = my - __ldg(p.campos + 1);
+      dir_orig.z = mz - __ldg(p.campos + 2);
+      const float len =
+          sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+      dirx = dir_orig.x / len;
+      diry = dir_orig.y / len;
+      dirz = dir_orig.z / len;
+    }
+    const uint32_t clamp_bits = __ldg(p.clamped + idx);
+
+    // ---------------- SH colour backward (backward.cu:20-139) --------------------------------
+    if (p.shs != nullptr) {
+      float g[3] = {dcol[0], dcol[1], dcol[2]};
+      g[0] *= (clamp_bits & 0x1u) ? 0.f : 1.f;
+      g[1] *= (clamp_bits & 0x100u) ? 0.f : 1.f;
+      g[2] *= (clamp_bits & 0x10000u) ? 0.f : 1.f;
+      const float* sh = p.shs + (size_t)idx * p.M * 3;
+      float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
+      const V3 dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, sh, g, dsh);
+      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
+      dmx += dm.x; dmy += dm.y; dmz += dm.z;
+    }
+
+    // ---------------- phasor backward (backward.cu:525-587) ----------------------------------
+    const float dist = __ldg(p.rec + (size_t)idx * GFT_REC_FLOATS + 11);
+    if (p.shs_p != nullptr) {
+      const float2 pa = __ldg(reinterpret_cast<const float2*>(p.pa) + idx);
+      float phase = dist * p.dist2phase + p.phase_offset;
+      if (p.use_view_dependent_phase) phase += pa.x;
+      const float amplitude = pa.y;
+      const float factor = 1.0f / (dist * dist);
+      const float dL_dR = dph[0], dL_dI = dph[1], dL_dA = dph[2];
+      const float dq1 = dph[3], dq2 = dph[4], dq3 = dph[5], dq4 = dph[6];
+      float sin_p, cos_p;
+      sincosf(phase, &sin_p, &cos_p);
+      const float dc = p.dc_offset;
+      const float dphase_sum = dL_dR * -sin_p + dL_dI * cos_p + dq1 * -sin_p + dq2 * sin_p +
+                               dq3 * cos_p + dq4 * -cos_p;
+      float gpa[2] = {0.f, 0.f};
+      if (p.use_view_dependent_phase) gpa[0] = dphase_sum * amplitude * factor;
+      part_phase = dphase_sum * amplitude * factor;
+      gpa[1] = (dL_dR * cos_p + dL_dI * sin_p + dL_dA + dq1 * (cos_p + dc) + dq2 * (-cos_p + dc) +
+                dq3 * (sin_p + dc) + dq4 * (-sin_p + dc)) * factor;
+      part_dc = (dq1 + dq2 + dq3 + dq4) * amplitude * factor;
+      const float coeff =
+          dphase_sum * p.dist2phase * amplitude * factor / dist +
+          (dL_dR * -cos_p + dL_dI * -sin_p - dL_dA + dq1 * -(cos_p + dc) + dq2 * (cos_p - dc) +
+           dq3 * -(sin_p + dc) + dq4 * (sin_p - dc)) * 2.0f * amplitude * factor * factor;
+      const float dxv = m_view_x * coeff, dyv = m_view_y * coeff, dzv = m_view_z * coeff;
+      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
+      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
+      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
+
+      // computePhasorFromSH backward (no special case for the removed phase DC: SURVEY A.5)
+      gpa[1] *= (clamp_bits & 0x1000000u) ? 0.f : 1.f;
+      const float* shp = p.shs_p + (size_t)idx * p.M_p * 2;
+      float* dshp = p.dL_dsh_p + (size_t)idx * p.M_p * 2;
+      const V3 dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, shp, gpa, dshp);
+      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
+      dmx += dm.x; dmy += dm.y; dmz += dm.z;
+    }
+
+    // ---------------- depth / ndc -> mean (backward.cu:589-601) ------------------------------
+    {
+      const float dndc_ddist = (p.far_n * p.near_n) / ((p.far_n - p.near_n) * dist * dist);
+      const float dL_ddist = dndc_rec * dndc_ddist + ddist_rec;
+      const float dxv = dL_ddist * m_view_x / dist;
+      const float dyv = dL_ddist * m_view_y / dist;
+      const float dzv = dL_ddist * m_view_z / dist;
+      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
+      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
+      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
+    }
+    p.dL_dmeans3D[3 * (size_t)idx + 0] = dmx;
+    p.dL_dmeans3D[3 * (size_t)idx + 1] = dmy;
+    p.dL_dmeans3D[3 * (size_t)idx + 2] = dmz;
+
+    // ---------------- cov3D -> scale, rotation (backward.cu:399-462) -------------------------
+    if (p.scales != nullptr) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      const float sx = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 0);
+      const float sy = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 1);
+      const float sz = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 2);
+      // R[c][r] as filled column by column by glm::mat3(...)
+      const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
+      const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
+      const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
+      // M = S * R : M[c][r] = s_r * R[c][r]
+      const float M00 = sx * R00, M01 = sy * R01, M02 = sz * R02;
+      const float M10 = sx * R10, M11 = sy * R11, M12 = sz * R12;
+      const float M20 = sx * R20, M21 = sy * R21, M22 = sz * R22;
+      // dL_dSigma (symmetric), columns
+      const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2];
+      const float S11 = dcov[3], S12 = 0.5f * dcov[4], S22 = dcov[5];
+      // dL_dM = 2 * M * dL_dSigma ; (A*B)[c][r] = sum_k A[k][r] * B[c][k]
+      const float D00 = 2.f * (M00 * S00 + M10 * S01 + M20 * S02);
+      const float D01 = 2.f * (M01 * S00 + M11 * S01 + M21 * S02);
+      const float D02 = 2.f * (M02 * S00 + M12 * S01 + M22 * S02);
+      const float D10 = 2.f * (M00 * S01 + M10 * S11 + M20 * S12);
+      const float D11 = 2.f * (M01 * S01 + M11 * S11 + M21 * S12);
+      const float D12 = 2.f * (M02 * S01 + M12 * S11 + M22 * S12);
+      const float D20 = 2.f * (M00 * S02 + M10 * S12 + M20 * S22);
+      const float D21 = 2.f * (M01 * S02 + M11 * S12 + M21 * S22);
+      const float D22 = 2.f * (M02 * S02 + M12 * S12 + M22 * S22);
+      // Rt[i] = (R[0][i], R[1][i], R[2][i]); dL_dMt[i] = (D[0][i], D[1][i], D[2][i])
+      const float ds_x = R00 * D00 + R10 * D10 + R20 * D20;
+      const float ds_y = R01 * D01 + R11 * D11 + R21 * D21;
+      const float ds_z = R02 * D02 + R12 * D12 + R22 * D22;
+      p.dL_dscales[3 * (size_t)idx + 0] = ds_x;
+      p.dL_dscales[3 * (size_t)idx + 1] = ds_y;
+      p.dL_dscales[3 * (size_t)idx + 2] = ds_z;
+      // dL_dMt[i] *= s_i ; Mt[i][j] = D[j][i] * s_i
+      const float t00 = D00 * sx, t01 = D10 * sx, t02 = D20 * sx;
+      const float t10 = D01 * sy, t11 = D11 * sy, t12 = D21 * sy;
+      const float t20 = D02 * sz, t21 = D12 * sz, t22 = D22 * sz;
+      float4 dq;
+      dq.x = 2 * z * (t01 - t10) + 2 * y * (t20 - t02) + 2 * x * (t12 - t21);
+      dq.y = 2 * y * (t10 + t01) + 2 * z * (t20 + t02) + 2 * r * (t12 - t21) - 4 * x * (t22 + t11);
+      dq.z = 2 * x * (t10 + t01) + 2 * r * (t20 - t02) + 2 * z * (t12 + t21) - 4 * y * (t22 + t00);
+      dq.w = 2 * r * (t01 - t10) + 2 * x * (t20 + t02) + 2 * y * (t12 + t21) - 4 * z * (t11 + t00);
+      reinterpret_cast<float4*>(p.dL_drotations)[idx] = dq;
+    }
+  }
+
+  // ---- the two scalar gradients: block reduction, one atomic per block ----------------------
+  if (p.shs_p != nullptr) {
+    const float sp = block_sum(part_phase, s_red);
+    const float sd = block_sum(part_dc, s_red);
+    if (threadIdx.x == 0) {
+      if (sp != 0.f) atomicAdd(p.dL_dphase_offset, sp);
+      if (sd != 0.f) atomicAdd(p.dL_ddc_offset, sd);
+    }
+  }
+}
+
+__global__ void zero_scalars_kernel(float* a, float* b) {
+  if (a) *a = 0.f;
+  if (b) *b = 0.f;
+}
+
+void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
+  zero_scalars_kernel<<<1, 1, 0, stream>>>(p.dL_dphase_offset, p.dL_ddc_offset);
+  if (p.P <= 0) return;
+  const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
+  preprocess_bwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+}
+
+}  // namespace gft

@@ -1,0 +1,265 @@
+// radix_sort_own.cu — hand-written stable LSD radix sort for (u64 key, u32 value) pairs, sm_100a.
+//
+// Shape: 8-bit digits; ONE histogram kernel reads the keys once and builds the digit histograms
+// of every pass; each pass is then ONE "onesweep" kernel: a tile of TILE_ITEMS consecutive pairs
+// is ranked inside the block (warp match_any ranking, stable), the tile's digit counts are
+// chained to the preceding tiles with a decoupled look-back (so the global digit offsets never
+// need a separate scan kernel or a second read of the keys), pairs are reordered by digit in
+// shared memory and written out in runs so that stores coalesce.
+//
+// HBM traffic: 8 B/pair for the histogram + (12 B read + 12 B write)/pair/pass — the same
+// algorithmic traffic as cub's onesweep; what it saves against the reference's call is the
+// temp-buffer copy of the non-double-buffered CUB API and the separate upsweep launches.
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace gft {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                         // pairs per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 pairs per tile
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PRE = 2u << 30;
+constexpr uint32_t VAL_MASK = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// hist[pass][bin] over all keys; one read of the keys for all passes.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_histogram_kernel(const uint64_t* __restrict__ keys, int R, int npass, int end_bit,
+                    uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_BINS];
+  for (int i = threadIdx.x; i < npass * RS_BINS; i += RS_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  const int stride = gridDim.x * RS_THREADS;
+  for (int i = blockIdx.x * RS_THREADS + threadIdx.x; i < R; i += stride) {
+    const uint64_t k = __ldg(keys + i);
+    for (int p = 0; p < npass; ++p) {
+      const int shift = 8 * p;
+      const int nb = min(8, end_bit - shift);
+      const uint32_t d = (uint32_t)(k >> shift) & ((1u << nb) - 1u);
+      atomicAdd(&s_hist[p * RS_BINS + d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * RS_BINS; i += RS_THREADS) {
+    const uint32_t v = s_hist[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// In-place exclusive scan of each pass's 256 bins: hist -> global digit base.
+__global__ void __launch_bounds__(RS_BINS) rs_scan_bins_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_w[RS_BINS / 32];
+  uint32_t* h = hist + blockIdx.x * RS_BINS;
+  const uint32_t v = h[threadIdx.x];
+  uint32_t incl = v;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += n;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t w = 0; w < warp; ++w) base += s_w[w];
+  h[threadIdx.x] = base + incl - v;
+}
+
+struct RsSmem {
+  uint64_t keys[RS_TILE];
+  uint32_t vals[RS_TILE];
+  uint32_t warp_hist[RS_WARPS][RS_BINS];  // per-warp digit counts -> exclusive warp prefixes
+  uint32_t tile_excl[RS_BINS];            // exclusive prefix of digit counts inside the tile
+  uint32_t gbase[RS_BINS];                // global output position of the tile's first digit-d pair
+  uint32_t tile_id;
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int R,
+                   int shift, int nbits, const uint32_t* __restrict__ digit_base,
+                   uint32_t* __restrict__ ticket, uint32_t* __restrict__ state) {
+  extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+  RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
+  for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s.tile_id;
+  const uint32_t tile_base = tile * RS_TILE;
+  const uint32_t dmask = (1u << nbits) - 1u;
+
+  // ---- load (warp-striped: warp w owns RS_ITEMS*32 consecutive pairs) and rank -------------
+  uint64_t key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  uint32_t rnk[RS_ITEMS];  // rank among the warp's pairs with the same digit
+  const uint32_t wbase = tile_base + warp * (RS_ITEMS * 32);
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t g = wbase + i * 32 + lane;
+    const bool ok = g < (uint32_t)R;
+    key[i] = ok ? __ldg(keys_in + g) : ~0ull;
+    val[i] = ok ? __ldg(vals_in + g) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t g = wbase + i * 32 + lane;
+    const bool ok = g < (uint32_t)R;
+    const uint32_t d = ok ? ((uint32_t)(key[i] >> shift) & dmask) : 256u;  // 256 = padding
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader && ok) {
+      old = s.warp_hist[warp][d];
+      s.warp_hist[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rnk[i] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per-digit: prefix over warps, tile count, look-back, in-tile exclusive scan ---------
+  {
+    const uint32_t d = tid;  // RS_THREADS == RS_BINS
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = s.warp_hist[w][d];
+      s.warp_hist[w][d] = run;
+      run += c;
+    }
+    const uint32_t count = run;
+    uint32_t* st = state + (size_t)tile * RS_BINS + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_release_u32(st, FLAG_PRE | count);
+    } else {
+      st_release_u32(st, FLAG_AGG | count);
+      const uint32_t* pv = st - RS_BINS;
+      while (true) {
+        uint32_t v;
+        do { v = ld_acquire_u32(pv); } while ((v & ~VAL_MASK) == 0u);
+        excl += v & VAL_MASK;
+        if (v & FLAG_PRE) break;
+        pv -= RS_BINS;
+      }
+      st_release_u32(st, FLAG_PRE | (excl + count));
+    }
+    // exclusive scan of `count` over the 256 digits
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += n;
+    }
+    __shared__ uint32_t s_wtot[RS_WARPS];
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t w = 0; w < warp; ++w) wb += s_wtot[w];
+    const uint32_t texcl = wb + incl - count;
+    s.tile_excl[d] = texcl;
+    // global position of local slot i (digit d): gbase[d] + i, with gbase = base + excl - texcl
+    s.gbase[d] = __ldg(digit_base + d) + excl - texcl;
+  }
+  __syncthreads();
+
+  // ---- reorder by digit in shared memory ---------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t g = wbase + i * 32 + lane;
+    if (g < (uint32_t)R) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+      const uint32_t slot = s.tile_excl[d] + s.warp_hist[warp][d] + rnk[i];
+      s.keys[slot] = key[i];
+      s.vals[slot] = val[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- coalesced write-out -----------------------------------------------------------------
+  const uint32_t n_valid = min((uint32_t)RS_TILE, (uint32_t)R - tile_base);
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const uint32_t slot = i * RS_THREADS + tid;
+    if (slot < n_valid) {
+      const uint64_t k = s.keys[slot];
+      const uint32_t d = (uint32_t)(k >> shift) & dmask;
+      const uint32_t pos = s.gbase[d] + slot;
+      keys_out[pos] = k;
+      vals_out[pos] = s.vals[slot];
+    }
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+int radix_sort_passes(int end_bit) { return (end_bit + 7) / 8; }
+
+size_t own_sort_temp_bytes(int R) {
+  const size_t tiles = ((size_t)max(R, 1) + RS_TILE - 1) / RS_TILE;
+  // hist[8][256] + ticket[8] + state[passes][tiles][256]
+  return align_up(RS_MAX_PASSES * RS_BINS * 4 + RS_MAX_PASSES * 4, 256) +
+         RS_MAX_PASSES * tiles * RS_BINS * 4;
+}
+
+// Sorts on bits [0,end_bit).  Ping-pongs between (a) and (b) starting from a; the result lands in
+// b when the pass count is odd and in a when it is even.  Returns the pass count, <0 on error.
+int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, uint64_t* keys_b,
+                   const uint32_t* vals_a_c, uint32_t* vals_b, int R, int end_bit,
+                   cudaStream_t stream) {
+  if (R <= 0) return 0;
+  if (end_bit > 64 || end_bit <= 0) return -1;
+  if (temp_bytes < own_sort_temp_bytes(R)) return -2;
+  uint64_t* keys_a = const_cast<uint64_t*>(keys_a_c);
+  uint32_t* vals_a = const_cast<uint32_t*>(vals_a_c);
+  const int npass = radix_sort_passes(end_bit);
+  const int tiles = (R + RS_TILE - 1) / RS_TILE;
+  const size_t head = align_up(RS_MAX_PASSES * RS_BINS * 4 + RS_MAX_PASSES * 4, 256);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
+  uint32_t* ticket = hist + RS_MAX_PASSES * RS_BINS;
+  uint32_t* state = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_temp) + head);
+  cudaMemsetAsync(d_temp, 0, head + (size_t)npass * tiles * RS_BINS * 4, stream);
+
+  int hblocks = (R + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
+  hblocks = max(1, min(hblocks, 148 * 8));
+  rs_histogram_kernel<<<hblocks, RS_THREADS, 0, stream>>>(keys_a, R, npass, end_bit, hist);
+  rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
+
+  // per-device attribute; cheap enough to set on every call (keeps the library state-free)
+  cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(RsSmem));
+  uint64_t* kin = keys_a; uint64_t* kout = keys_b;
+  uint32_t* vin = vals_a; uint32_t* vout = vals_b;
+  for (int p = 0; p < npass; ++p) {
+    const int shift = 8 * p;
+    const int nb = min(8, end_bit - shift);
+    rs_onesweep_kernel<<<tiles, RS_THREADS, sizeof(RsSmem), stream>>>(
+        kin, kout, vin, vout, R, shift, nb, hist + p * RS_BINS, ticket + p,
+        state + (size_t)p * tiles * RS_BINS);
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return npass;
+}
+
+}  // namespace gft
