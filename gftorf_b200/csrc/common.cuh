@@ -61,22 +61,25 @@ struct Cov3 {
 __device__ __forceinline__ Cov3 cov3d_from_scale_rot(float sx0, float sy0, float sz0, float mod,
                                                      float r, float x, float y, float z) {
   const float sx = __fmul_rn(mod, sx0), sy = __fmul_rn(mod, sy0), sz = __fmul_rn(mod, sz0);
+  // Dataflow of the reference binary (SASS of preprocessCUDA, sm_100a): x*z, r*x, r*z, y*y, z*z are
+  // rounded products; the other product of each sum/difference is fused into an FMA.
   const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
-  const float xy = __fmul_rn(x, y), rz = __fmul_rn(r, z);
-  const float xz = __fmul_rn(x, z), ry = __fmul_rn(r, y);
-  const float yz = __fmul_rn(y, z), rx = __fmul_rn(r, x);
+  const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+  const float xz_p_ry = __fmaf_rn(r, y, xz), xz_m_ry = __fmaf_rn(-r, y, xz);
+  const float yz_m_rx = __fmaf_rn(y, z, -rx), yz_p_rx = __fmaf_rn(y, z, rx);
+  const float xy_m_rz = __fmaf_rn(x, y, -rz), xy_p_rz = __fmaf_rn(x, y, rz);
   const float xx_zz = __fmaf_rn(x, x, zz);
   const float xx_yy = __fmaf_rn(x, x, yy);
   const float yy_zz = __fadd_rn(yy, zz);
   // glm::mat3 R (column-major fill): R[0]=(R00,R01,R02) ...
   const float R00 = __fsub_rn(1.f, __fadd_rn(yy_zz, yy_zz));
-  const float R01 = __fadd_rn(__fsub_rn(xy, rz), __fsub_rn(xy, rz));
-  const float R02 = __fadd_rn(__fadd_rn(ry, xz), __fadd_rn(ry, xz));
-  const float R10 = __fadd_rn(__fadd_rn(xy, rz), __fadd_rn(xy, rz));
+  const float R01 = __fadd_rn(xy_m_rz, xy_m_rz);
+  const float R02 = __fadd_rn(xz_p_ry, xz_p_ry);
+  const float R10 = __fadd_rn(xy_p_rz, xy_p_rz);
   const float R11 = __fsub_rn(1.f, __fadd_rn(xx_zz, xx_zz));
-  const float R12 = __fadd_rn(__fsub_rn(yz, rx), __fsub_rn(yz, rx));
-  const float R20 = __fadd_rn(__fsub_rn(xz, ry), __fsub_rn(xz, ry));
-  const float R21 = __fadd_rn(__fadd_rn(rx, yz), __fadd_rn(rx, yz));
+  const float R12 = __fadd_rn(yz_m_rx, yz_m_rx);
+  const float R20 = __fadd_rn(xz_m_ry, xz_m_ry);
+  const float R21 = __fadd_rn(yz_p_rx, yz_p_rx);
   const float R22 = __fsub_rn(1.f, __fadd_rn(xx_yy, xx_yy));
   // M = S * R
   const float M00 = __fmul_rn(sx, R00), M01 = __fmul_rn(sy, R01), M02 = __fmul_rn(sz, R02);

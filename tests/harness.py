@@ -24,9 +24,12 @@ GRAD_REL_L2 = 1e-4
 
 def build_inputs(P, W, H, kind="trained", seed=0, pose="identity", device="cuda", sh_degree=3,
                  depth_range=15.0, bg_hw=None, view_dependent_phase=False, phase_offset=0.0,
-                 dc_offset=0.0, sigma_px=1.5):
+                 dc_offset=0.0, sigma_px=1.5, zero_shp_rest=False):
     cam = scenes.make_camera(W, H, depth_range=depth_range, pose=pose, seed=seed)
     cloud = scenes.make_cloud(P, cam, kind=kind, seed=seed, sigma_px=sigma_px)
+    if zero_shp_rest:
+        # keeps the reference's undefined dL_dPA (defect D1) out of dL_dmeans3D
+        cloud["shs_p"][:, 1:, :] = 0.0
     bh, bw = bg_hw if bg_hw else (H, W)
     bg = scenes.make_background(bh, bw, seed=seed)
     grads = scenes.make_pixel_grads(H, W, seed=seed)

@@ -24,6 +24,8 @@ CASES = {
     "small": dict(P=2000, W=160, H=120, kind="trained", seed=1, pose="orbit"),
     "init_small": dict(P=2000, W=160, H=120, kind="init", seed=2),
     "c1": dict(P=20000, W=320, H=240, kind="trained", seed=0),
+    "c1_r0": dict(P=20000, W=320, H=240, kind="trained", seed=0, zero_shp_rest=True),
+    "c2_r0": dict(P=300000, W=640, H=480, kind="trained", seed=0, zero_shp_rest=True),
     "c1_init": dict(P=20000, W=320, H=240, kind="init", seed=0),
     "c2": dict(P=300000, W=640, H=480, kind="trained", seed=0),
     "c2_orbit_vdp": dict(P=300000, W=640, H=480, kind="trained", seed=3, pose="orbit",
@@ -68,6 +70,8 @@ def main():
         rb = harness.call_backward(ref_driver.RefModule, inp, ref)
         torch.cuda.synchronize()
         brep = harness.compare_backward(ob, rb)
+        if ob[7].numel():
+            brep["sh_p_row0"] = harness.rel_l2(ob[7][0], rb[7][0])
         rep["bwd"] = brep
         if args.time:
             rep["ms"] = dict(
