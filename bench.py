@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py — measures the hot path BASELINE.json names: the RGB+ToF Gaussian rasterizer's
+forward+backward inside a training iteration, on synthetic F-TöRF-shaped scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu] [--workload c2]
+
+A STEP is one training iteration's worth of rasterizer work for one camera pair, exactly the call
+pattern of gaussian_renderer/__init__.py:107-128 + train.py:279: forward of the colour view,
+forward of the ToF view, backward of both (every output computed, all five consumed output
+gradients dense).  At N > 1 every rank does one such step on its own views (weak scaling) and the
+step ends with the NCCL sum-allreduce of the flat per-Gaussian gradient bucket.
+
+  value  : Mpix/s of pixels taken through forward+backward, whole job, inputs resident in HBM,
+           called through the C-ABI entry points (gftorf_b200.rasterizer._C);
+           ms_per_step is BASELINE's "fwd+bwd ms/iter".
+  e2e    : the same metric through the public autograd surface (GaussianRasterizer + backward())
+           with HOST buffers: pinned-host -> device copies of all Gaussian parameters, cameras,
+           background and pixel gradients, and device -> host reads of the parameter gradients
+           and the rendered images, all inside the timed region.
+  --impl reference : the UNMODIFIED reference kernels (oracle/_ref/libgftorf_ref.so, built from
+           /root/reference by oracle/Makefile) driven the way the reference's torch binding drives
+           them (oracle/ref_driver.py) — same workload, same metric, on the GPU.  The reference has
+           no CPU implementation, so its "own implementation of the path" is this.
+           Falls back to the CPU port (oracle/gft_oracle.cpp) only if that library is absent.
+  --impl cpu : the CPU port on the host cores (the cpu_baseline, as a full line).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from gftorf_b200 import scenes  # noqa: E402
+
+WORKLOADS = {
+    # configs[1] of BASELINE.json: F-TöRF synthetic-shaped scene, 300k Gaussians, 640x480 RGB + ToF
+    "c2": dict(P=300000, color=(640, 480), tof=(640, 480), depth_range=15.0, kind="trained",
+               desc="BASELINE configs[1]: 300k Gaussians, 640x480 RGB view + 640x480 ToF view, SH degree 3"),
+    # configs[0]: the CPU-runnable case
+    "c1": dict(P=20000, color=(320, 240), tof=(320, 240), depth_range=15.0, kind="trained",
+               desc="BASELINE configs[0]: 20k Gaussians, 320x240"),
+    # configs[2] shape (TöRF real-shaped): 500k Gaussians, ToF 320x240 + colour 640x480
+    "c3": dict(P=500000, color=(640, 480), tof=(320, 240), depth_range=10.0, kind="trained",
+               desc="BASELINE configs[2] shape: 500k Gaussians, 640x480 colour + 320x240 ToF"),
+    # configs[3] per-view shape: 2M Gaussians, 1080p RGB + 640x480 ToF
+    "c4": dict(P=2000000, color=(1920, 1080), tof=(640, 480), depth_range=15.0, kind="trained",
+               desc="BASELINE configs[3] per-view shape: 2M Gaussians, 1080p colour + 640x480 ToF"),
+}
+
+
+# --------------------------------------------------------------------------------------------
+def make_view(P, wh, depth_range, kind, seed, device, cloud=None, bg_hw=None):
+    W, H = wh
+    cam = scenes.make_camera(W, H, depth_range=depth_range, seed=seed)
+    if cloud is None:
+        cloud = scenes.make_cloud(P, cam, kind=kind, seed=seed)
+    bh, bw = bg_hw if bg_hw else (H, W)
+    bg = scenes.make_background(bh, bw, seed=seed)
+    grads = scenes.make_pixel_grads(H, W, seed=seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    view = dict(W=W, H=H, viewmatrix=t(cam["viewmatrix"]), projmatrix=t(cam["projmatrix"]),
+                campos=t(cam["campos"]), tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+                near_n=cam["znear"], far_n=cam["zfar"], depth_range=cam["depth_range"], bg=t(bg),
+                grads={k: t(v) for k, v in grads.items()})
+    return view, cloud
+
+
+def build_scene(wl, seed, device):
+    color, cloud = make_view(wl["P"], wl["color"], wl["depth_range"], wl["kind"], seed, device)
+    # the bg map is sized from the colour camera and reused for the ToF view (train.py:121-128)
+    tof, _ = make_view(wl["P"], wl["tof"], wl["depth_range"], wl["kind"], seed, device, cloud=cloud,
+                       bg_hw=(wl["color"][1], wl["color"][0]))
+    tof["bg"] = color["bg"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    params = {k: t(cloud[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p")}
+    return params, [color, tof]
+
+
+def fwd_args(params, v, empty):
+    return (v["bg"], params["means3D"], empty, empty, params["opacities"], params["scales"],
+            params["rotations"], 1.0, empty, v["viewmatrix"], v["projmatrix"], v["tanfovx"],
+            v["tanfovy"], v["H"], v["W"], params["shs"], params["shs_p"], 3, v["campos"], False,
+            False, v["near_n"], v["far_n"], v["depth_range"], False, 0.0, 0.0)
+
+
+def bwd_args(params, v, f, empty, zero3, zero1):
+    g = v["grads"]
+    return (v["bg"], params["means3D"], f[11], empty, empty, params["scales"], params["rotations"],
+            1.0, empty, v["viewmatrix"], v["projmatrix"], v["tanfovx"], v["tanfovy"], g["color"],
+            g["phasor"], g["depth"], zero3, g["acc"], zero1, g["depth_distortion"], zero1,
+            params["shs"], params["shs_p"], 3, v["campos"], f[12], f[0], f[13], f[14], False,
+            v["near_n"], v["far_n"], v["depth_range"], False, 0.0, 0.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def stage_bytes(stage, P, V, R, N, T):
+    """Algorithmic bytes per launch of each stage (SURVEY §8d split per kernel)."""
+    return {
+        "preprocess_fwd": 24 * P + 464 * V,
+        "duplicate_keys": 12 * R,
+        "radix_sort": 24 * R,
+        "identify_ranges": 8 * R + 8 * T,
+        "blend_fwd": 76 * R + 128 * N,
+        "zero_grad_records": 80 * P,
+        "blend_bwd": 76 * R + 96 * N + 80 * V,
+        "preprocess_bwd": 388 * P + 472 * V,
+    }.get(stage, 0)
+
+
+# --------------------------------------------------------------------------------------------
+def run_gpu(args, impl):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gftorf_b200 import rasterizer, _capi, parallel
+    if impl == "ours":
+        mod = rasterizer._C
+    else:
+        from oracle import ref_driver
+        mod = ref_driver.RefModule
+
+    wl = WORKLOADS[args.workload]
+    params, views = build_scene(wl, seed=rank, device=dev)   # each rank: its own views of the batch
+    empty = torch.Tensor([])
+    zero3 = {id(v): torch.zeros_like(v["grads"]["color"]) for v in views}
+    zero1 = {id(v): torch.zeros_like(v["grads"]["depth"]) for v in views}
+    P = wl["P"]
+    npix = sum(v["W"] * v["H"] for v in views)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    bucket_flat = torch.zeros(P * parallel.FLOATS_PER_GAUSSIAN + 4, dtype=torch.float32, device=dev)
+
+    def accumulate(b):
+        # gradients of the two views add (autograd's AccumulateGrad in the reference's training loop)
+        o = 0
+        for t in (b[4], b[6], b[7], b[3], b[8], b[9]):
+            n = t.numel()
+            bucket_flat[o:o + n] += t.reshape(-1)
+            o += n
+
+    def step_resident():
+        bucket_flat.zero_()
+        stats = []
+        for v in views:
+            f = mod.rasterize_gaussians(*fwd_args(params, v, empty))
+            b = mod.rasterize_gaussians_backward(*bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]))
+            accumulate(b)
+            stats.append((f[0], f[11]))
+        if world > 1:
+            dist.all_reduce(bucket_flat)
+        return stats
+
+    # ---- e2e: public autograd surface, host buffers --------------------------------------------
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+    host_params = {k: params[k].cpu().pin_memory() for k in names}
+    host_views = []
+    for v in views:
+        hv = {k: v[k].cpu().pin_memory() for k in ("viewmatrix", "projmatrix", "campos")}
+        hv["grads"] = {k: g.cpu().pin_memory() for k, g in v["grads"].items()}
+        host_views.append(hv)
+    host_bg = views[0]["bg"].cpu().pin_memory()
+    host_out_grads = {k: torch.empty_like(host_params[k]).pin_memory() for k in names}
+    host_imgs = [torch.empty((11, v["H"], v["W"]), dtype=torch.float32).pin_memory() for v in views]
+    h2d_bytes = sum(t.numel() * 4 for t in host_params.values()) + host_bg.numel() * 4 + sum(
+        sum(t.numel() * 4 for t in (hv["viewmatrix"], hv["projmatrix"], hv["campos"])) +
+        sum(g.numel() * 4 for g in hv["grads"].values()) for hv in host_views)
+    d2h_bytes = sum(t.numel() * 4 for t in host_out_grads.values()) + sum(t.numel() * 4 for t in host_imgs)
+
+    if impl == "ours":
+        Settings, Raster = rasterizer.GaussianRasterizationSettings, rasterizer.GaussianRasterizer
+    else:
+        # the reference's own autograd Function would sit here; its binding is restated by
+        # ref_driver, so the e2e arm drives forward/backward explicitly with the same copies
+        Settings = Raster = None
+
+    def step_e2e():
+        dp = {k: host_params[k].to(dev, non_blocking=True) for k in names}
+        bg = host_bg.to(dev, non_blocking=True)
+        acc = None
+        for v, hv, himg in zip(views, host_views, host_imgs):
+            vm = hv["viewmatrix"].to(dev, non_blocking=True)
+            pm = hv["projmatrix"].to(dev, non_blocking=True)
+            cp = hv["campos"].to(dev, non_blocking=True)
+            g = {k: t.to(dev, non_blocking=True) for k, t in hv["grads"].items()}
+            if impl == "ours":
+                leaves = {k: dp[k].requires_grad_(True) for k in names}
+                m2d = torch.zeros_like(dp["means3D"], requires_grad=True)
+                s = Settings(image_height=v["H"], image_width=v["W"], tanfovx=v["tanfovx"],
+                             tanfovy=v["tanfovy"], bg=bg, scale_modifier=1.0, viewmatrix=vm,
+                             projmatrix=pm, sh_degree=3, campos=cp, prefiltered=False, debug=False,
+                             near_n=v["near_n"], far_n=v["far_n"], depth_range=v["depth_range"])
+                out = Raster(s)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                shs=leaves["shs"], shs_p=leaves["shs_p"], scales=leaves["scales"],
+                                rotations=leaves["rotations"])
+                torch.autograd.backward(
+                    [out[0], out[1], out[2], out[4], out[6]],
+                    [g["color"], g["phasor"], g["depth"], g["acc"], g["depth_distortion"]])
+                himg[0:3].copy_(out[0], non_blocking=True)
+                himg[3:10].copy_(out[1], non_blocking=True)
+                himg[10:11].copy_(out[2], non_blocking=True)
+            else:
+                vv = dict(v, viewmatrix=vm, projmatrix=pm, campos=cp, bg=bg, grads=g)
+                f = mod.rasterize_gaussians(*fwd_args(dp, vv, empty))
+                b = mod.rasterize_gaussians_backward(*bwd_args(dp, vv, f, empty, zero3[id(v)], zero1[id(v)]))
+                grads_now = dict(means3D=b[4], opacities=b[3], shs=b[6], shs_p=b[7], scales=b[8], rotations=b[9])
+                acc = grads_now if acc is None else {k: acc[k] + grads_now[k] for k in names}
+                himg[0:3].copy_(f[1], non_blocking=True)
+                himg[3:10].copy_(f[2], non_blocking=True)
+                himg[10:11].copy_(f[3], non_blocking=True)
+        for k in names:
+            gsrc = dp[k].grad if impl == "ours" else acc[k]
+            host_out_grads[k].copy_(gsrc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, K, W, profile=False):
+        for _ in range(W):
+            step_fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        if profile and impl == "ours":
+            _capi.profile_read(4096)
+            _capi.profile_enable(True)
+        n0 = _capi.launch_count() if impl == "ours" else 0
+        t0 = time.perf_counter()
+        stats = None
+        for i in range(K):
+            flush.zero_()                      # L2 flush (256 MiB > 126 MB L2), untimed
+            evs[i][0].record()
+            stats = step_fn()
+            evs[i][1].record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        launches = (_capi.launch_count() - n0) if impl == "ours" else None
+        stages = []
+        if profile and impl == "ours":
+            stages = _capi.profile_read(4096)
+            _capi.profile_enable(False)
+        ms = [a.elapsed_time(b) for a, b in evs]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()), wall, launches, stages, stats
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, wall_ms, launches, stages, stats = timed(step_resident, K, W, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _, _, _, _ = timed(step_e2e, K, W)
+
+    # render-only throughput (forward only, all outputs) — BASELINE's second metric
+    def step_render():
+        for v in views:
+            mod.rasterize_gaussians(*fwd_args(params, v, empty))
+    render_ms, _, _, _, _ = timed(step_render, K, W)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    mpix = npix * world / 1e6
+    value = mpix * K / (total_ms / 1e3)
+    line = {
+        "metric": "rasterizer fwd+bwd throughput (RGB+ToF+depth)", "value": round(value, 3),
+        "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}; trained-like cloud (SURVEY §8d), "
+                               "one camera pair per rank per step, fwd colour + fwd ToF + bwd both"
+                               + ("; + NCCL allreduce of the [P,91] gradient bucket" if world > 1 else ""),
+                   "P": P, "views_per_step_per_rank": len(views),
+                   "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
+                   "timing": "sum of per-step CUDA-event durations, max over ranks"},
+        "fwd_bwd_ms_per_iter": round(total_ms / K, 4),
+        "wall_ms_total_incl_flush": round(wall_ms, 2),
+        "render_mpix_s": round(mpix * K / (render_ms / 1e3), 3),
+        "render_ms_per_step": round(render_ms / K, 4),
+        "e2e": {"value": round(mpix * K / (e2e_ms / 1e3), 3), "unit": "Mpix/s",
+                "ms_per_step": round(e2e_ms / K, 4), "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes),
+                "api": "GaussianRasterizer(...) + torch.autograd.backward" if impl == "ours"
+                       else "reference kernels via oracle/ref_driver.py (binding restated)"},
+        "clocks": clocks,
+    }
+    if impl == "ours":
+        line["gpu_launches"] = int(launches)
+        # roofline of the dominant kernel, from the per-stage CUDA events of the timed region
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per = {}
+        for name, ms in stages:
+            per.setdefault(name, []).append(ms)
+        mean_ms = {k: float(np.mean(v)) for k, v in per.items()}
+        calls_per_step = {k: len(v) / K for k, v in per.items()}
+        step_share = {k: mean_ms[k] * calls_per_step[k] for k in mean_ms}
+        dom = max(step_share, key=step_share.get) if step_share else None
+        if dom:
+            # V, R of the view with the larger share are close; use the mean over the step's views
+            Vs = [int((s[1] > 0).sum().item()) for s in stats]
+            Rs = [int(s[0]) for s in stats]
+            Ns = [v["W"] * v["H"] for v in views]
+            Ts = [((v["W"] + 15) // 16) * ((v["H"] + 15) // 16) for v in views]
+            byts = float(np.mean([stage_bytes(dom, P, Vs[i], Rs[i], Ns[i], Ts[i]) for i in range(len(views))]))
+            ach = byts / (mean_ms[dom] * 1e-3) / 1e9
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            except Exception:
+                pass
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 2),
+                                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                                "traffic": traffic,
+                                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
+                                "algorithmic_bytes_per_launch": int(byts),
+                                "kernel_ms_per_launch": round(mean_ms[dom], 4),
+                                "note": "the blend kernels are issue/latency bound by construction "
+                                        "(per-pair ALU + MUFU + shuffles), so their HBM fraction is small; "
+                                        "see profiles/ for issue-slot utilisation"}
+            total_bytes = sum(504 * P + 936 * Vs[i] + 188 * Rs[i] + 224 * Ns[i] + 8 * Ts[i] for i in range(len(views)))
+            line["step_roofline"] = {"algorithmic_bytes_per_step": int(total_bytes),
+                                     "achieved_gbs": round(total_bytes / (total_ms / K * 1e-3) / 1e9, 2),
+                                     "frac": round(total_bytes / (total_ms / K * 1e-3) / 1e9 / peak, 5),
+                                     "V": Vs, "R": Rs}
+            line["stage_ms_per_step"] = {k: round(v, 4) for k, v in sorted(step_share.items(), key=lambda kv: -kv[1])}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, wl, bound_s=20.0)
+    else:
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": "Mpix/s", "cores": 0, "kind": "reference",
+                                "sample": "full workload; the reference's own implementation of this path is "
+                                          "CUDA-only (no CPU rasterizer exists, SURVEY §8c), so this arm runs its "
+                                          "unmodified kernels (oracle/_ref) on the same GPU"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(args, wl, bound_s=20.0):
+    """The CPU port (oracle/gft_oracle.cpp, OpenMP over all host cores) on a bounded sample of the
+    workload: the colour view's forward+backward, repeated until ~bound_s seconds are spent."""
+    try:
+        from oracle import cpu_oracle
+        if not cpu_oracle.available():
+            return {"value": None, "unit": "Mpix/s", "cores": 0, "kind": "port",
+                    "sample": "oracle/libgft_oracle.so not built"}
+        params, views = build_scene(wl, seed=0, device="cpu")
+        v = views[0]
+        empty = torch.Tensor([])
+        z3, z1 = torch.zeros_like(v["grads"]["color"]), torch.zeros_like(v["grads"]["depth"])
+        times = []
+        t_start = time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            f = cpu_oracle.rasterize_gaussians(*fwd_args(params, v, empty))
+            cpu_oracle.rasterize_gaussians_backward(*bwd_args(params, v, f, empty, z3, z1))
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > bound_s or len(times) >= 10:
+                break
+        best = float(np.median(times))
+        return {"value": round(v["W"] * v["H"] / 1e6 / best, 4), "unit": "Mpix/s",
+                "cores": cpu_oracle.num_threads(), "kind": "port",
+                "ms_per_view_fwd_bwd": round(best * 1e3, 1),
+                "sample": f"colour view only ({v['W']}x{v['H']}, P={wl['P']}), fwd+bwd, "
+                          f"median of {len(times)} runs, OpenMP threads = host cores"}
+    except Exception as ex:  # never take the GPU line down with the baseline
+        return {"value": None, "unit": "Mpix/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+
+def run_cpu(args):
+    wl = WORKLOADS[args.workload]
+    cb = cpu_baseline(args, wl, bound_s=30.0)
+    line = {"metric": "rasterizer fwd+bwd throughput (RGB+ToF+depth)", "value": cb["value"],
+            "unit": "Mpix/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb.get("ms_per_view_fwd_bwd"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.workload}: {wl['desc']} (CPU port, bounded sample)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "cpu":
+        if rank == 0:
+            run_cpu(args)
+        return
+    if args.impl == "reference":
+        from oracle import ref_driver
+        if not ref_driver.available():
+            if rank == 0:
+                run_cpu(args)     # the oracle always exists: CPU port as the reference arm
+            return
+    run_gpu(args, args.impl)
+
+
+if __name__ == "__main__":
+    main()

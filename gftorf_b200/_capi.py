@@ -80,7 +80,7 @@ EXPORTS = (
     "gft_forward", "gft_geom_bytes", "gft_img_bytes", "gft_binning_bytes",
     "gft_backward_scratch_bytes", "gft_backward", "gft_mark_visible",
     "gft_dist2_workspace_bytes", "gft_dist2", "gft_workspace_layout", "gft_last_error",
-    "gft_abi_version",
+    "gft_abi_version", "gft_profile_enable", "gft_profile_read", "gft_launch_count",
 )
 
 
@@ -116,6 +116,12 @@ def declare(lib, prefix="gft_"):
         lib.gft_workspace_layout.restype = None
         lib.gft_abi_version.argtypes = []
         lib.gft_abi_version.restype = C.c_int
+        lib.gft_profile_enable.argtypes = [C.c_int]
+        lib.gft_profile_enable.restype = None
+        lib.gft_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]
+        lib.gft_profile_read.restype = C.c_int
+        lib.gft_launch_count.argtypes = []
+        lib.gft_launch_count.restype = C.c_ulonglong
     return lib
 
 
@@ -133,3 +139,19 @@ def lib():
         if _lib.gft_abi_version() != 1:
             raise ImportError("libgftorf_b200.so ABI version mismatch")
     return _lib
+
+
+def profile_enable(on=True):
+    lib().gft_profile_enable(1 if on else 0)
+
+
+def profile_read(cap=64):
+    """[(stage name, milliseconds)] of the calls made since the last read, in launch order."""
+    ms = (C.c_float * cap)()
+    names = (C.c_char_p * cap)()
+    n = lib().gft_profile_read(ms, names, cap)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def launch_count():
+    return int(lib().gft_launch_count())

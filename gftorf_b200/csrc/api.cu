@@ -24,9 +24,45 @@
 #include "kernels.h"
 #include "radix_sort.cuh"
 
+#include <atomic>
+#include <vector>
+
+namespace gft {
+static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace gft
+
 namespace {
 
 thread_local std::string g_err;
+
+// Optional per-stage timing with CUDA events on the caller's stream (gft_profile_* in the ABI).
+struct StageRec { const char* name; cudaEvent_t e0, e1; };
+struct Profile {
+  bool on = false;
+  std::vector<StageRec> pool;   // events are created once and reused
+  int used = 0;
+  void reset() { used = 0; }
+  StageRec* next(const char* name) {
+    if (used == (int)pool.size()) {
+      StageRec r; r.name = name;
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      pool.push_back(r);
+    }
+    pool[used].name = name;
+    return &pool[used++];
+  }
+};
+thread_local Profile g_prof;
+
+struct Stage {
+  StageRec* r = nullptr;
+  cudaStream_t s;
+  Stage(const char* name, cudaStream_t stream) : s(stream) {
+    if (g_prof.on) { r = g_prof.next(name); cudaEventRecord(r->e0, s); }
+  }
+  ~Stage() { if (r) cudaEventRecord(r->e1, s); }
+};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -117,6 +153,23 @@ BinWs bin_layout(int R) {
 extern "C" {
 
 const char* gft_last_error(void) { return g_err.c_str(); }
+
+unsigned long long gft_launch_count(void) { return gft::g_launches.load(); }
+void gft_profile_enable(int on) { g_prof.on = on != 0; g_prof.reset(); }
+int gft_profile_read(float* ms, const char** names, int cap) {
+  int n = 0;
+  for (int i = 0; i < g_prof.used && n < cap; ++i) {
+    StageRec& r = g_prof.pool[i];
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) break;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) break;
+    ms[n] = t;
+    if (names) names[n] = r.name;
+    ++n;
+  }
+  g_prof.reset();
+  return n;
+}
 int gft_abi_version(void) { return GFT_ABI_VERSION; }
 
 size_t gft_geom_bytes(int P) { return geom_layout(P).total; }
@@ -231,7 +284,7 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   pp.scan_state = reinterpret_cast<unsigned long long*>(hdr + 4);
   const char* nocull = std::getenv("GFT_NO_CULL");
   pp.subtile_cull = !(nocull && nocull[0] == '1');
-  gft::launch_preprocess_fwd(pp, stream);
+  { Stage st("preprocess_fwd", stream); gft::launch_preprocess_fwd(pp, stream); }
   GFT_CUDA_OK("preprocess");
 
   // R sizes the binning workspace, so it has to reach the host (rasterizer_impl.cu:310-315)
@@ -253,16 +306,19 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   const uint64_t* keys_sorted = keys_a;
   const uint32_t* point_list = vals_a;
   if (R > 0) {
-    gft::launch_duplicate_keys(P, a->radii, pp.rect, pp.depths, pp.point_offsets, keys_a, vals_a,
-                               gx, stream);
+    { Stage st("duplicate_keys", stream);
+      gft::launch_duplicate_keys(P, a->radii, pp.rect, pp.depths, pp.point_offsets, keys_a, vals_a,
+                                 gx, stream); }
     GFT_CUDA_OK("duplicate_keys");
     const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
-    const int rc = gft::sort_pairs(bin + bl.temp, bl.temp_bytes, keys_a, keys_b, vals_a, vals_b, R,
-                                   end_bit, stream);
+    int rc;
+    { Stage st("radix_sort", stream);
+      rc = gft::sort_pairs(bin + bl.temp, bl.temp_bytes, keys_a, keys_b, vals_a, vals_b, R, end_bit,
+                           stream); }
     if (rc < 0) return fail(-2, "gft_forward: radix sort failed");
     GFT_CUDA_OK("sort");
     if (gft::sort_result_in_out(end_bit)) { keys_sorted = keys_b; point_list = vals_b; }
-    gft::launch_identify_ranges(R, keys_sorted, pp.ranges, stream);
+    { Stage st("identify_ranges", stream); gft::launch_identify_ranges(R, keys_sorted, pp.ranges, stream); }
     GFT_CUDA_OK("identify_ranges");
   }
 
@@ -278,7 +334,7 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   bp.out_depth_distortion = a->out_depth_distortion;
   bp.out_amp_distortion = a->out_amp_distortion; bp.out_distribution = a->out_distribution;
   bp.pixels = a->pixels;
-  gft::launch_blend_fwd(bp, stream);
+  { Stage st("blend_fwd", stream); gft::launch_blend_fwd(bp, stream); }
   GFT_CUDA_OK("blend_fwd");
   return R;
 }
@@ -318,7 +374,8 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   const char* img = a->img_buffer;
   const char* bin = a->binning_buffer;
 
-  cudaMemsetAsync(a->scratch, 0, (size_t)P * GFT_GRAD_FLOATS * 4, stream);
+  { Stage st("zero_grad_records", stream);
+    cudaMemsetAsync(a->scratch, 0, (size_t)P * GFT_GRAD_FLOATS * 4, stream); }
 
   if (a->R > 0) {
     const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
@@ -335,7 +392,7 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
     bp.dL_ddepth = a->dL_dout_depth; bp.dL_dacc = a->dL_dout_acc;
     bp.dL_ddd = a->dL_dout_depth_distortion;
     bp.grad_rec = a->scratch;
-    gft::launch_blend_bwd(bp, stream);
+    { Stage st("blend_bwd", stream); gft::launch_blend_bwd(bp, stream); }
     GFT_CUDA_OK("blend_bwd");
   }
 
@@ -364,7 +421,7 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   pb.dL_dphase_offset = a->dL_dphase_offset; pb.dL_ddc_offset = a->dL_ddc_offset;
   pb.dL_dcolors = a->dL_dcolors; pb.dL_dphasors = a->dL_dphasors; pb.dL_dcov3D = a->dL_dcov3D;
   pb.dL_dconic = a->dL_dconic; pb.dL_ddist = a->dL_ddist; pb.dL_dndc = a->dL_dndc;
-  gft::launch_preprocess_bwd(pb, stream);
+  { Stage st("preprocess_bwd", stream); gft::launch_preprocess_bwd(pb, stream); }
   GFT_CUDA_OK("preprocess_bwd");
   return 0;
 }

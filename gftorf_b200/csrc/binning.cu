@@ -73,11 +73,13 @@ void launch_duplicate_keys(int P, const int* /*radii*/, const uint16_t* rect, co
   const int blocks = (P + GFT_BLOCK - 1) / GFT_BLOCK;
   duplicate_keys_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(P, rect, depths, point_offsets, keys,
                                                           values, grid_x);
+  note_launches(1);
 }
 
 void launch_identify_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream) {
   if (R <= 0) return;
   identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, keys, ranges);
+  note_launches(1);
 }
 
 bool sort_result_in_out(int end_bit) { return sort_lands_in_out(end_bit); }

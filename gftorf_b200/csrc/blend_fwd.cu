@@ -217,6 +217,7 @@ void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
   blend_fwd_kernel<<<tiles, GFT_BLOCK, 0, stream>>>(p);
+  note_launches(1);
 }
 
 }  // namespace gft

@@ -6,6 +6,9 @@
 
 namespace gft {
 
+// process-wide count of kernels launched by this library (gft_launch_count in the C ABI)
+void note_launches(int n);
+
 struct PreprocessParams {
   int P, D, M, M_p;
   int W, H, grid_x, grid_y, num_tiles;

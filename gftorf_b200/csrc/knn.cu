@@ -265,6 +265,7 @@ int knn_dist2(const float* points, int P, float* out, char* workspace, cudaStrea
   knn_gather_boxes_kernel<<<nboxes, KNN_BOX, 0, stream>>>(P, points, order, w.sorted, w.boxes);
   knn_search_kernel<<<(P + KNN_THREADS - 1) / KNN_THREADS, KNN_THREADS, 0, stream>>>(
       P, w.sorted, w.boxes, nboxes, out);
+  note_launches(5);
   return 0;
 }
 

@@ -407,11 +407,13 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   preprocess_fwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+  note_launches(1);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present,
                          float near_n, float far_n, cudaStream_t stream) {
   mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, V, present, near_n, far_n);
+  note_launches(1);
 }
 
 }  // namespace gft

@@ -427,9 +427,11 @@ __global__ void zero_scalars_kernel(float* a, float* b) {
 
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
   zero_scalars_kernel<<<1, 1, 0, stream>>>(p.dL_dphase_offset, p.dL_ddc_offset);
+  note_launches(1);
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   preprocess_bwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+  note_launches(1);
 }
 
 }  // namespace gft

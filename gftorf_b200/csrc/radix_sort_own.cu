@@ -12,6 +12,7 @@
 // temp-buffer copy of the non-double-buffered CUB API and the separate upsweep launches.
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "kernels.h"
 
 namespace gft {
 
@@ -244,6 +245,7 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
   hblocks = max(1, min(hblocks, 148 * 8));
   rs_histogram_kernel<<<hblocks, RS_THREADS, 0, stream>>>(keys_a, R, npass, end_bit, hist);
   rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
+  note_launches(2 + npass);
 
   // per-device attribute; cheap enough to set on every call (keeps the library state-free)
   cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,0 +1,125 @@
+"""Multi-GPU host logic: view-sharded data parallelism for training and frame sharding for
+render-only sweeps.
+
+The reference is single-process, single-GPU and renders one view per iteration (train.py:159,
+utils/general_utils.py:146); a rasterizer call is a pure function of (Gaussian parameters, one
+camera), and loss gradients of different views simply add.  So the path shards by VIEW with the
+Gaussian parameters replicated (364 B/Gaussian), and the only exchange step is one sum-allreduce of
+the per-Gaussian gradients per iteration, plus a tiny sum/max exchange of the densification
+statistics (scene/gaussian_model.py:648-654, train.py:443).  Render-only frames are independent:
+no collective at all.
+
+One process per GPU; torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+# parameter groups of scene/gaussian_model.py:247-272 as the rasterizer sees them, floats/Gaussian
+PARAM_LAYOUT = (("means3D", 3), ("shs", 48), ("shs_p", 32), ("opacities", 1), ("scales", 3),
+                ("rotations", 4))
+FLOATS_PER_GAUSSIAN = sum(n for _, n in PARAM_LAYOUT)  # 91 -> 364 B
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Views of a multi-camera batch owned by `rank`: contiguous blocks, sizes differing by <= 1."""
+    base, extra = divmod(n_views, world)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> List[int]:
+    """Frames of a render-only trajectory owned by `rank`: r, r+n, r+2n, ... (no collective)."""
+    return list(range(rank, n_frames, world))
+
+
+class GradBucket:
+    """One flat fp32 buffer holding the gradient of every Gaussian parameter (+ the two scalar ToF
+    offsets).  `attach()` makes each leaf's .grad a VIEW into the buffer, so autograd accumulates
+    the gradients of all local views in place and the collective runs on the buffer as it stands —
+    no pack or copy step between the last backward and the allreduce."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], scalars: Sequence[torch.Tensor] = ()):
+        self.names = [n for n, _ in PARAM_LAYOUT if n in params]
+        self.params = params
+        self.scalars = list(scalars)
+        ref = params[self.names[0]]
+        sizes = [params[n].numel() for n in self.names] + [s.numel() for s in self.scalars]
+        self.offsets, cur = [], 0
+        for n in sizes:
+            self.offsets.append(cur)
+            cur += (n + 3) // 4 * 4  # 16-byte aligned slices
+        self.flat = torch.zeros(cur, dtype=torch.float32, device=ref.device)
+        self.sizes = sizes
+
+    def views(self):
+        tensors = [self.params[n] for n in self.names] + self.scalars
+        return [self.flat[o:o + n].view_as(t) for o, n, t in zip(self.offsets, self.sizes, tensors)]
+
+    def attach(self):
+        tensors = [self.params[n] for n in self.names] + self.scalars
+        for t, v in zip(tensors, self.views()):
+            t.grad = v
+        return self
+
+    def zero(self):
+        self.flat.zero_()
+
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    def allreduce(self, group=None, average: bool = False, async_op: bool = False):
+        """Sum (or mean) over ranks.  No-op in a single process."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if average:
+            if async_op:
+                work.wait()
+                work = None
+            self.flat.div_(dist.get_world_size(group))
+        return work
+
+
+class DensifyStats:
+    """Per-Gaussian densification statistics (scene/gaussian_model.py:648-654, train.py:441-445).
+    The gradient NORM is taken per view, so each rank accumulates its own views and the ranks
+    exchange sums (accum, denom) and a max (max_radii2D)."""
+
+    def __init__(self, P: int, device):
+        self.sums = torch.zeros((P, 2), dtype=torch.float32, device=device)   # grad-norm*pixels, pixels
+        self.max_radii2D = torch.zeros((P,), dtype=torch.float32, device=device)
+
+    def update(self, viewspace_grad: torch.Tensor, radii: torch.Tensor, pixels: torch.Tensor):
+        vis = radii > 0
+        self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].float())
+        pix = pixels.view(-1)
+        norm = torch.norm(viewspace_grad[:, :2], dim=-1)
+        self.sums[:, 0] += torch.where(vis, norm * pix, torch.zeros_like(norm))
+        self.sums[:, 1] += torch.where(vis, pix, torch.zeros_like(pix))
+
+    def allreduce(self, group=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+def train_views(rasterize_view, views: Sequence, bucket: GradBucket, group=None,
+                stats: Optional[DensifyStats] = None):
+    """One data-parallel iteration over this rank's views.
+
+    `rasterize_view(view)` runs forward + loss + backward for one camera through the public
+    autograd surface and returns (viewspace_points, radii, pixels) for the densification
+    statistics; gradients land in the bucket through the attached .grad views.  Afterwards the
+    bucket (and the statistics) are reduced over the ranks."""
+    bucket.zero()
+    for v in views:
+        out = rasterize_view(v)
+        if stats is not None and out is not None:
+            vsp, radii, pixels = out
+            stats.update(vsp.grad, radii, pixels)
+    bucket.allreduce(group=group)
+    if stats is not None:
+        stats.allreduce(group=group)

@@ -223,6 +223,17 @@ typedef struct GftWorkspaceLayout {
 
 void gft_workspace_layout(int P, int R, int width, int height, GftWorkspaceLayout* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (no counterpart in the reference, which has no profiler hooks: SURVEY §5).
+ * gft_profile_enable(1) makes the calling thread's next gft_forward / gft_backward bracket every
+ * stage with CUDA events on the caller's stream; gft_profile_read() then waits for them and
+ * returns per-stage milliseconds (and static stage names) in launch order, at most `cap`.
+ * gft_launch_count() is the process-wide number of kernels this library has launched.
+ * ---------------------------------------------------------------------------------------- */
+void gft_profile_enable(int on);
+int gft_profile_read(float* ms, const char** names, int cap);
+unsigned long long gft_launch_count(void);
+
 const char* gft_last_error(void);
 int gft_abi_version(void);
 

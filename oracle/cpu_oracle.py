@@ -61,9 +61,12 @@ class Handle:
         return 1
 
     def __del__(self):
-        if self.ptr:
-            lib().orc_free(self.ptr)
-            self.ptr = None
+        try:
+            if self.ptr and _lib is not None:
+                _lib.orc_free(self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
 
 
 _DTYPES = {
@@ -87,9 +90,7 @@ def decode(handle):
             continue
         if n.value == 0:
             continue
-        nbytes = n.value * {1: 1, 4: 4, 8: 8}[np.dtype(dt).itemsize if np.dtype(dt).itemsize != 4 else 4]
-        if np.dtype(dt).itemsize == 8:
-            nbytes = n.value * 8
+        nbytes = n.value * np.dtype(dt).itemsize
         buf = (C.c_char * nbytes).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dt).copy()
         if name in _SHAPES:

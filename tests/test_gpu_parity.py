@@ -1,0 +1,498 @@
+"""GPU parity tests proper: the product library (through its C ABI, via the Python surface) against
+  (1) the UNMODIFIED reference kernels (oracle/_ref/libgftorf_ref.so) on the same GPU,
+  (2) the committed golden fixtures (reference outputs), and
+  (3) the CPU restatement (oracle/libgft_oracle.so) where the reference itself is undefined.
+Tolerances are north_star's: integers bit-exact, images <= 1e-5 abs, gradients <= 1e-4 rel-L2.
+"""
+import os
+
+import pytest
+import torch
+
+import golden_util
+import harness
+from gftorf_b200 import rasterizer, debug, distCUDA2
+from oracle import ref_driver, cpu_oracle
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not ref_driver.available(), reason="oracle/_ref not built")
+needs_oracle = pytest.mark.skipif(not cpu_oracle.available(), reason="CPU oracle not built")
+
+CASES = {
+    "tiny": dict(P=64, W=48, H=40, kind="trained", seed=0, sigma_px=4.0),
+    "ragged": dict(P=777, W=101, H=67, kind="trained", seed=5, sigma_px=3.0, pose="orbit"),
+    "small_orbit": dict(P=2000, W=160, H=120, kind="trained", seed=1, pose="orbit"),
+    "init_small": dict(P=2000, W=160, H=120, kind="init", seed=2),
+    "c1": dict(P=20000, W=320, H=240, kind="trained", seed=0),
+    "c1_init": dict(P=20000, W=320, H=240, kind="init", seed=1),
+    "c1_dense": dict(P=20000, W=320, H=240, kind="trained", seed=2, sigma_px=6.0),
+    "c2": dict(P=300000, W=640, H=480, kind="trained", seed=0),
+    "c2_vdp": dict(P=300000, W=640, H=480, kind="trained", seed=3, pose="orbit",
+                   view_dependent_phase=True, phase_offset=0.3, dc_offset=0.1),
+    "c3_tof": dict(P=500000, W=320, H=240, kind="trained", seed=4, depth_range=10.0,
+                   bg_hw=(480, 640)),
+}
+
+
+def run_both(spec, **fw):
+    inp = harness.build_inputs(device="cuda", **spec)
+    ours = harness.call_forward(rasterizer._C, inp, **fw)
+    ref = harness.call_forward(ref_driver.RefModule, inp, **fw)
+    torch.cuda.synchronize()
+    return inp, ours, ref
+
+
+def decoded(inp, ours, ref):
+    P, W, H = inp["P"], inp["W"], inp["H"]
+    od = debug.decode_buffers(ours[12], ours[13], ours[14], P, ours[0], W, H)
+    rd = ref_driver.decode_buffers(ref[12], ref[13], ref[14], P, ref[0], W, H)
+    return od, rd
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_vs_reference_kernels(name):
+    inp, ours, ref = run_both(CASES[name])
+    od, rd = decoded(inp, ours, ref)
+    rep = harness.compare_forward(ours, ref, od, rd)
+    harness.assert_forward_parity(rep)
+    assert rep["R_ours"] > 0 and rep["V"] > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["tiny", "ragged", "small_orbit", "init_small", "c1", "c1_dense",
+                                  "c2", "c2_vdp", "c3_tof"])
+def test_backward_vs_reference_kernels(name):
+    # zero higher-order phase/amp SH keeps the reference's undefined dL_dPA out of
+    # dL_dmeans3D; dL_dsh_p is compared on the one row the reference defines (Gaussian 0).
+    spec = dict(CASES[name], zero_shp_rest=True)
+    inp, ours, ref = run_both(spec)
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    torch.cuda.synchronize()
+    scale = float(rb[8].double().norm())
+    for i, k in enumerate(harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+            continue
+        if k == "sh_p":
+            assert harness.rel_l2(ob[i][0], rb[i][0]) <= harness.GRAD_REL_L2
+            continue
+        err = float((ob[i].double() - rb[i].double()).norm())
+        refn = float(rb[i].double().norm())
+        assert err <= harness.GRAD_REL_L2 * max(refn, 1e-3 * scale), (k, err, refn)
+
+
+@needs_ref
+def test_sh_p_gradient_rows_by_rotating_each_gaussian_to_index_zero():
+    """The reference defines dL_dsh_p only for Gaussian 0.  Swap Gaussian k with Gaussian 0, read
+    the reference's row 0, and compare with OUR row k of the unswapped scene."""
+    spec = dict(P=300, W=64, H=48, kind="trained", seed=7, sigma_px=3.0, view_dependent_phase=True,
+                phase_offset=0.2, dc_offset=0.05)
+    inp = harness.build_inputs(device="cuda", **spec)
+    ours = harness.call_forward(rasterizer._C, inp)
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    vis = (ours[11] > 0).nonzero().flatten().tolist()
+    checked = 0
+    for k in vis[:12]:
+        perm = torch.arange(inp["P"], device="cuda")
+        perm[0], perm[k] = k, 0
+        sw = dict(inp)
+        for name in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p"):
+            sw[name] = inp[name][perm].contiguous()
+        ref = harness.call_forward(ref_driver.RefModule, sw)
+        rb = harness.call_backward(ref_driver.RefModule, sw, ref)
+        torch.cuda.synchronize()
+        if float(rb[7][0].norm()) == 0.0:
+            continue
+        assert harness.rel_l2(ob[7][k], rb[7][0]) <= harness.GRAD_REL_L2, k
+        checked += 1
+    assert checked >= 6
+
+
+@needs_oracle
+@pytest.mark.parametrize("spec", [
+    dict(P=3000, W=128, H=96, kind="trained", seed=11, pose="orbit", view_dependent_phase=True,
+         phase_offset=0.3, dc_offset=0.1),
+    dict(P=1500, W=96, H=80, kind="init", seed=12),
+])
+def test_full_gradients_vs_cpu_oracle(spec):
+    """Every gradient, including all rows of dL_dsh_p and dL_dmeans3D with non-zero SH_p, against
+    the CPU restatement (which is pinned to the reference on everything the reference defines)."""
+    inp = harness.build_inputs(device="cuda", **spec)
+    ours = harness.call_forward(rasterizer._C, inp)
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    cin = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    cin["grads"] = {k: v.cpu() for k, v in inp["grads"].items()}
+    cf = harness.call_forward(cpu_oracle.OracleModule, cin)
+    cb = harness.call_backward(cpu_oracle.OracleModule, cin, cf)
+    assert ours[0] == cf[0]
+    assert torch.equal(ours[11].cpu(), cf[11])
+    if harness.nmismatch(ours[9].cpu(), cf[9]) == 0:  # no expf threshold flip on this scene
+        scale = float(cb[8].double().norm())
+        for i, k in enumerate(harness.BWD_NAMES):
+            if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+                continue
+            err = float((ob[i].cpu().double() - cb[i].double()).norm())
+            refn = float(cb[i].double().norm())
+            assert err <= harness.GRAD_REL_L2 * max(refn, 1e-3 * scale), (k, err, refn)
+
+
+@pytest.mark.parametrize("name", golden_util.CASES)
+def test_golden_fixtures(name):
+    """Product vs committed reference outputs (no reference library needed at run time)."""
+    inp, gold = golden_util.load(name, device="cuda")
+    f = harness.call_forward(rasterizer._C, inp)
+    b = harness.call_backward(rasterizer._C, inp, f)
+    torch.cuda.synchronize()
+    d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
+    assert f[0] == gold["R"]
+    assert torch.equal(f[11].cpu(), gold["f_radii"])
+    assert torch.equal(f[9].cpu(), gold["f_pixels"])
+    for k in ("tiles_touched", "point_offsets", "keys", "point_list", "ranges", "n_contrib"):
+        if "s_" + k in gold:
+            assert torch.equal(d[k].cpu(), gold["s_" + k]), k
+    for i, k in enumerate(harness.FWD_NAMES):
+        if i >= 1 and k not in ("pixels", "radii"):
+            assert (f[i].cpu() - gold["f_" + k]).abs().max() <= harness.IMG_ATOL, k
+    zero_rest = bool(gold["spec"].get("zero_shp_rest", False)) or gold["spec"]["kind"] == "init"
+    scale = float(gold["b_scales"].double().norm())
+    for i, k in enumerate(harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+            continue
+        if k == "sh_p":
+            assert harness.rel_l2(b[i][0].cpu(), gold["b_sh_p"][0]) <= harness.GRAD_REL_L2
+            continue
+        if k == "means3D" and not zero_rest:
+            continue
+        err = float((b[i].cpu().double() - gold["b_" + k].double()).norm())
+        refn = float(gold["b_" + k].double().norm())
+        assert err <= harness.GRAD_REL_L2 * max(refn, 1e-3 * scale), (k, err, refn)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases the reference's binding handles (rasterize_points.cu:104,238)
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+def test_no_gaussians():
+    inp = harness.build_inputs(device="cuda", P=0, W=40, H=24)
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    assert ours[0] == 0 == ref[0]
+    for i in range(1, 12):
+        assert ours[i].shape == ref[i].shape
+        assert torch.equal(ours[i], ref[i])  # all zeros, NOT T*bg (rasterize_points.cu:104)
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    for a, b in zip(ob, rb):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
+@needs_ref
+def test_everything_culled_renders_background():
+    inp = harness.build_inputs(device="cuda", P=500, W=40, H=24, seed=3)
+    inp["means3D"] = inp["means3D"] * torch.tensor([1.0, 1.0, -1.0], device="cuda")  # behind camera
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    assert ours[0] == 0 == ref[0]
+    assert int((ours[11] != 0).sum()) == 0
+    for i in range(1, 12):
+        assert torch.equal(ours[i], ref[i])
+    assert torch.equal(ours[1], inp["bg"][0:3])           # T = 1: colour = bg planes 0..2
+    assert torch.equal(ours[2], inp["bg"][0:7])
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    for g in ob:
+        assert float(g.abs().sum()) == 0.0
+
+
+@needs_ref
+def test_single_gaussian():
+    inp = harness.build_inputs(device="cuda", P=1, W=33, H=17, seed=9, sigma_px=6.0)
+    inp["means3D"] = torch.tensor([[0.02, -0.01, 2.0]], device="cuda")
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    od, rd = decoded(inp, ours, ref)
+    harness.assert_forward_parity(harness.compare_forward(ours, ref, od, rd))
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    # P = 1: index 0 is the only Gaussian, so even dL_dsh_p / dL_dmeans3D are defined in the reference
+    harness.assert_backward_parity(harness.compare_backward(ob, rb))
+
+
+@needs_ref
+def test_render_flow_path_precomputed_colours_no_phasor():
+    """gaussian_renderer/__init__.py:194-202: colors_precomp, no shs_p.  The reference blends
+    uninitialised phasor features there; only colour/depth/acc/dd/radii/pixels and
+    dL_dcolors are meaningful.  We define the phasor features as 0."""
+    inp = harness.build_inputs(device="cuda", P=4000, W=96, H=64, seed=4, sigma_px=3.0)
+    cp = torch.rand((4000, 3), device="cuda")
+    inp["bg"] = torch.zeros_like(inp["bg"])  # bg_map_flow is all zeros, train.py:128
+    ours = harness.call_forward(rasterizer._C, inp, colors_precomp=cp, use_shs_p=False)
+    ref = harness.call_forward(ref_driver.RefModule, inp, colors_precomp=cp, use_shs_p=False)
+    assert ours[0] == ref[0]
+    assert torch.equal(ours[11], ref[11]) and torch.equal(ours[9], ref[9])
+    for i in (1, 3, 5, 7):
+        assert torch.equal(ours[i], ref[i])
+    assert float(ours[2].abs().max()) == 0.0
+    inp["grads"]["phasor"] = torch.zeros_like(inp["grads"]["phasor"])
+    ob = harness.call_backward(rasterizer._C, inp, ours, colors_precomp=cp, use_shs_p=False)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref, colors_precomp=cp, use_shs_p=False)
+    for i in (0, 1, 3, 8, 9):  # means2D, colors_precomp, opacities, scales, rotations
+        assert harness.rel_l2(ob[i], rb[i]) <= harness.GRAD_REL_L2, harness.BWD_NAMES[i]
+
+
+@needs_ref
+def test_precomputed_covariance_path():
+    inp = harness.build_inputs(device="cuda", P=3000, W=96, H=64, seed=6, sigma_px=3.0,
+                               zero_shp_rest=True)
+    ours = harness.call_forward(rasterizer._C, inp)
+    od = debug.decode_buffers(ours[12], ours[13], ours[14], 3000, ours[0], 96, 64)
+    cov = od["cov3D"].clone()
+    cov[ours[11] <= 0] = 0
+    e = inp["empty"]
+
+    def fwd(mod):
+        return mod.rasterize_gaussians(
+            inp["bg"], inp["means3D"], e, e, inp["opacities"], e, e, 1.0, cov, inp["viewmatrix"],
+            inp["projmatrix"], inp["tanfovx"], inp["tanfovy"], 64, 96, inp["shs"], inp["shs_p"], 3,
+            inp["campos"], False, False, inp["near_n"], inp["far_n"], inp["depth_range"], False,
+            0.0, 0.0)
+    a, b = fwd(rasterizer._C), fwd(ref_driver.RefModule)
+    assert a[0] == b[0] and torch.equal(a[11], b[11])
+    for i in range(1, 11):
+        assert torch.equal(a[i], b[i])
+    g = inp["grads"]
+    z1 = torch.zeros_like(g["depth"])
+
+    def bwd(mod, f):
+        return mod.rasterize_gaussians_backward(
+            inp["bg"], inp["means3D"], f[11], e, e, e, e, 1.0, cov, inp["viewmatrix"],
+            inp["projmatrix"], inp["tanfovx"], inp["tanfovy"], g["color"], g["phasor"], g["depth"],
+            torch.zeros_like(g["color"]), g["acc"], z1, g["depth_distortion"], z1, inp["shs"],
+            inp["shs_p"], 3, inp["campos"], f[12], f[0], f[13], f[14], False, inp["near_n"],
+            inp["far_n"], inp["depth_range"], False, 0.0, 0.0)
+    ga, gb = bwd(rasterizer._C, a), bwd(ref_driver.RefModule, b)
+    assert harness.rel_l2(ga[5], gb[5]) <= harness.GRAD_REL_L2      # dL_dcov3D
+    assert harness.rel_l2(ga[4], gb[4]) <= harness.GRAD_REL_L2      # dL_dmeans3D
+    assert float(ga[8].abs().sum()) == 0.0 and float(gb[8].abs().sum()) == 0.0
+
+
+@needs_ref
+def test_constant_background_is_not_materialised_and_matches():
+    inp = harness.build_inputs(device="cuda", P=2000, W=80, H=48, seed=8, sigma_px=3.0)
+    const = torch.tensor([0.1, -0.2, 0.3, 0.4, -0.5, 0.6, 0.7], device="cuda")
+    inp["bg"] = const.view(7, 1, 1).expand(7, 48, 80)   # train.py:127
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    for i in range(1, 12):
+        assert torch.equal(ours[i], ref[i])
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    assert harness.rel_l2(ob[3], rb[3]) <= harness.GRAD_REL_L2
+
+
+@needs_ref
+def test_sort_backends_agree_bitwise():
+    spec = CASES["c1"]
+    inp = harness.build_inputs(device="cuda", **spec)
+    outs = {}
+    for backend in ("own", "cub"):
+        os.environ["GFT_SORT"] = backend
+        try:
+            f = harness.call_forward(rasterizer._C, inp)
+            d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
+            outs[backend] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone())
+        finally:
+            os.environ.pop("GFT_SORT", None)
+    for a, b in zip(outs["own"], outs["cub"]):
+        assert torch.equal(a, b)
+
+
+def test_subtile_culling_is_exact():
+    """The conservative per-warp culling must not change a single bit of the result."""
+    for name in ("c1", "c1_init", "c1_dense"):
+        inp = harness.build_inputs(device="cuda", **CASES[name])
+        a = harness.call_forward(rasterizer._C, inp)
+        os.environ["GFT_NO_CULL"] = "1"
+        try:
+            b = harness.call_forward(rasterizer._C, inp)
+        finally:
+            os.environ.pop("GFT_NO_CULL", None)
+        for i in range(1, 12):
+            assert torch.equal(a[i], b[i]), (name, harness.FWD_NAMES[i])
+        ga = harness.call_backward(rasterizer._C, inp, a)
+        gb = harness.call_backward(rasterizer._C, inp, b)
+        for x, y in zip(ga, gb):
+            assert harness.rel_l2(x, y) <= 1e-5
+
+
+def test_debug_mode_runs():
+    inp = harness.build_inputs(device="cuda", **CASES["tiny"])
+    e = inp["empty"]
+    out = rasterizer._C.rasterize_gaussians(
+        inp["bg"], inp["means3D"], e, e, inp["opacities"], inp["scales"], inp["rotations"], 1.0, e,
+        inp["viewmatrix"], inp["projmatrix"], inp["tanfovx"], inp["tanfovy"], inp["H"], inp["W"],
+        inp["shs"], inp["shs_p"], 3, inp["campos"], False, True, inp["near_n"], inp["far_n"],
+        inp["depth_range"], False, 0.0, 0.0)
+    assert out[0] > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+def test_full_size_c4_view_vs_reference():
+    """One 1080p view of config C4 (2M Gaussians): direct comparison still fits in seconds."""
+    spec = dict(P=2000000, W=1920, H=1080, kind="trained", seed=0, zero_shp_rest=True)
+    inp, ours, ref = run_both(spec)
+    od, rd = decoded(inp, ours, ref)
+    harness.assert_forward_parity(harness.compare_forward(ours, ref, od, rd))
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    for i, k in enumerate(harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp", "sh_p"):
+            continue
+        assert harness.rel_l2(ob[i], rb[i]) <= harness.GRAD_REL_L2, k
+
+
+def test_full_size_properties():
+    spec = dict(P=2000000, W=1920, H=1080, kind="trained", seed=1)
+    inp = harness.build_inputs(device="cuda", **spec)
+    f = harness.call_forward(rasterizer._C, inp)
+    P, W, H, R = inp["P"], inp["W"], inp["H"], f[0]
+    d = debug.decode_buffers(f[12], f[13], f[14], P, R, W, H)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    bits = 32 + T.bit_length()
+    keys = d["keys"] & ((1 << bits) - 1)
+    assert bool((keys[1:] >= keys[:-1]).all())                      # sortedness
+    tiles = (d["keys"] >> 32)
+    rng = d["ranges"].long()
+    lens = (rng[:, 1] - rng[:, 0])
+    assert int(lens.sum()) == R                                      # ranges partition [0, R)
+    nz = lens > 0
+    assert bool((tiles[rng[nz, 0]] == torch.arange(T, device="cuda")[nz]).all())
+    assert bool((tiles[rng[nz, 1] - 1] == torch.arange(T, device="cuda")[nz]).all())
+    assert int(d["tiles_touched"].long().sum()) == R
+    assert int(d["point_offsets"][-1]) == R
+    # stable sort: equal (tile, depth) keys keep ascending Gaussian index
+    same = keys[1:] == keys[:-1]
+    assert bool((d["point_list"][1:][same] > d["point_list"][:-1][same]).all())
+    # n_contrib never exceeds the tile list length of its pixel's tile
+    ncon = d["n_contrib"].view(H, W).long()
+    ty = torch.arange(H, device="cuda") // 16
+    tx = torch.arange(W, device="cuda") // 16
+    tl = lens.view((H + 15) // 16, (W + 15) // 16)[ty][:, tx]
+    assert bool((ncon <= tl).all())
+    # acc + final_T: 0 <= T <= 1, acc = sum of weights <= 1 - T (+ rounding)
+    Tf = d["final_T"].view(H, W)
+    assert bool(((Tf >= 0) & (Tf <= 1)).all())
+    assert float((f[5][0] + Tf - 1).abs().max()) < 1e-4
+    # determinism: forward twice, bit-identical everywhere
+    f2 = harness.call_forward(rasterizer._C, inp)
+    for i in range(1, 12):
+        assert torch.equal(f[i], f2[i])
+    # linearity of the backward in dL/dout
+    g1 = harness.call_backward(rasterizer._C, inp, f)
+    inp2 = dict(inp)
+    inp2["grads"] = {k: 2.0 * v for k, v in inp["grads"].items()}
+    g2 = harness.call_backward(rasterizer._C, inp2, f)
+    for a, b, k in zip(g1, g2, harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+            continue
+        assert harness.rel_l2(2.0 * a, b) <= harness.GRAD_REL_L2, k
+
+
+# ------------------------------------------------------------------------------------------------
+# distCUDA2 and markVisible
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 33, 1000, 1025, 20000, 300000])
+def test_dist2_bit_identical_to_reference(P):
+    g = torch.Generator().manual_seed(P)
+    pts = (torch.rand((P, 3), generator=g) * 4 - 2).cuda()
+    if P >= 33:
+        pts[7] = pts[3]
+        pts[8] = pts[3]
+    a, b = distCUDA2(pts), ref_driver.distCUDA2(pts)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
+@needs_ref
+def test_dist2_clustered_and_degenerate_clouds():
+    g = torch.Generator().manual_seed(5)
+    clustered = torch.cat([torch.randn((5000, 3), generator=g) * 0.01 + c
+                           for c in (torch.tensor([0., 0, 0]), torch.tensor([5., 5, 5]),
+                                     torch.tensor([-3., 2, 9]))]).cuda()
+    planar = torch.rand((8000, 3), generator=g).cuda()
+    planar[:, 2] = 1.0
+    same = torch.ones((100, 3)).cuda()
+    for pts in (clustered, planar, same):
+        a, b = distCUDA2(pts), ref_driver.distCUDA2(pts)
+        torch.cuda.synchronize()
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
+def test_dist2_golden():
+    k = golden_util.load_knn()
+    for name in [n for n in k if n.startswith("pts_")]:
+        out = distCUDA2(k[name].cuda()).cpu()
+        assert torch.equal(out.view(torch.int32), k["out_" + name[4:]].view(torch.int32)), name
+    assert distCUDA2(torch.zeros((0, 3), device="cuda")).shape == (0,)
+
+
+@needs_ref
+def test_mark_visible():
+    inp = harness.build_inputs(device="cuda", **CASES["c1"])
+    s = rasterizer.GaussianRasterizationSettings(
+        image_height=240, image_width=320, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"],
+        bg=inp["bg"], scale_modifier=1.0, viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+        sh_degree=3, campos=inp["campos"], prefiltered=False, debug=False, near_n=inp["near_n"],
+        far_n=inp["far_n"])
+    vis = rasterizer.GaussianRasterizer(s).markVisible(inp["means3D"])
+    ref = ref_driver.mark_visible(inp["means3D"], inp["viewmatrix"], inp["projmatrix"],
+                                  inp["near_n"], inp["far_n"])
+    assert vis.dtype == torch.bool and torch.equal(vis, ref)
+    assert 0 < int(vis.sum()) < inp["P"]
+
+
+# ------------------------------------------------------------------------------------------------
+# the public autograd surface, end to end
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+def test_autograd_surface_matches_reference_binding():
+    spec = dict(P=5000, W=128, H=96, kind="trained", seed=13, zero_shp_rest=True)
+    inp = harness.build_inputs(device="cuda", **spec)
+    phase = torch.nn.Parameter(torch.tensor([0.25], device="cuda"))
+    dc = torch.nn.Parameter(torch.tensor([0.05], device="cuda"))
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in names}
+    means2D = torch.zeros_like(inp["means3D"], requires_grad=True)
+    s = rasterizer.GaussianRasterizationSettings(
+        image_height=96, image_width=128, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"],
+        bg=inp["bg"], scale_modifier=1.0, viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+        sh_degree=3, campos=inp["campos"], prefiltered=False, debug=False, near_n=inp["near_n"],
+        far_n=inp["far_n"], depth_range=inp["depth_range"], use_view_dependent_phase=False,
+        optimize_phase_offset=True, optimize_dc_offset=True)
+    out = rasterizer.GaussianRasterizer(s)(
+        means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+        shs=leaves["shs"], shs_p=leaves["shs_p"], scales=leaves["scales"],
+        rotations=leaves["rotations"], phase_offset=phase, dc_offset=dc)
+    assert len(out) == 11 and out[10].dtype == torch.int32
+    g = inp["grads"]
+    loss = (out[0] * g["color"]).sum() + (out[1] * g["phasor"]).sum() + (out[2] * g["depth"]).sum() \
+        + (out[4] * g["acc"]).sum() + (out[6] * g["depth_distortion"]).sum()
+    loss.backward()
+    inp["phase_offset"], inp["dc_offset"] = 0.25, 0.05
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    for i in range(10):
+        assert torch.equal(out[i], ref[i + 1]), harness.FWD_NAMES[i + 1]
+    pairs = dict(means3D=rb[4], opacities=rb[3], shs=rb[6], scales=rb[8], rotations=rb[9])
+    for k, r in pairs.items():
+        assert harness.rel_l2(leaves[k].grad, r) <= harness.GRAD_REL_L2, k
+    assert harness.rel_l2(means2D.grad, rb[0]) <= harness.GRAD_REL_L2
+    assert harness.rel_l2(leaves["shs_p"].grad[0], rb[7][0]) <= harness.GRAD_REL_L2
+    assert harness.rel_l2(phase.grad, rb[10]) <= harness.GRAD_REL_L2
+    assert harness.rel_l2(dc.grad, rb[11]) <= harness.GRAD_REL_L2
+    assert float(means2D.grad[:, 2].abs().max()) == 0.0

@@ -1,0 +1,109 @@
+"""Host-side mirror of the reference's Python surface: names, validation errors, background
+handling, drop-in import paths, and the no-fallback rule.  Runs without a GPU."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import gftorf_b200  # noqa: E402
+from gftorf_b200 import rasterizer  # noqa: E402
+
+
+def _settings(**kw):
+    base = dict(image_height=32, image_width=32, tanfovx=0.5, tanfovy=0.5, bg=torch.zeros(7, 32, 32),
+                scale_modifier=1.0, viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0,
+                campos=torch.zeros(3), prefiltered=False, debug=False)
+    base.update(kw)
+    return rasterizer.GaussianRasterizationSettings(**base)
+
+
+def test_settings_fields_and_defaults_match_reference():
+    # diff_gaussian_rasterization_w_tof/__init__.py:22-40
+    s = _settings()
+    assert s._fields == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier",
+                         "viewmatrix", "projmatrix", "sh_degree", "campos", "prefiltered", "debug",
+                         "near_n", "far_n", "depth_range", "use_view_dependent_phase",
+                         "optimize_phase_offset", "optimize_dc_offset")
+    assert (s.near_n, s.far_n, s.depth_range) == (0.01, 100.0, 100.0)
+    assert (s.use_view_dependent_phase, s.optimize_phase_offset, s.optimize_dc_offset) == (False,) * 3
+
+
+def test_validation_errors_match_reference_messages():
+    # __init__.py:230-237
+    r = rasterizer.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(m, m, torch.zeros(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(m, m, torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), colors_precomp=torch.zeros(4, 3),
+          scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.zeros(4, 1), shs=torch.zeros(4, 1, 3))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), scales=torch.ones(4, 3),
+          rotations=torch.ones(4, 4), cov3D_precomp=torch.zeros(4, 6))
+
+
+def test_no_cpu_fallback():
+    r = rasterizer.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(m, m, torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), scales=torch.ones(4, 3),
+          rotations=torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gftorf_b200.distCUDA2(torch.zeros(4, 3))
+
+
+def test_means3d_shape_error_matches_reference():
+    # rasterize_points.cu:69-71
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):
+        rasterizer._native_forward(torch.zeros(7, 8, 8), torch.zeros(4, 2), *([torch.Tensor([])] * 2),
+                                   torch.zeros(4, 1), torch.ones(4, 3), torch.ones(4, 4), 1.0,
+                                   torch.Tensor([]), torch.eye(4), torch.eye(4), 0.5, 0.5, 8, 8,
+                                   torch.zeros(4, 1, 3), torch.Tensor([]), 0, torch.zeros(3), False,
+                                   False, 0.01, 100.0, 100.0, False, 0.0, 0.0)
+
+
+def test_background_modes():
+    H, W = 6, 5
+    const = torch.arange(7.0).view(7, 1, 1).expand(7, H, W)          # train.py:127
+    t, mode = rasterizer._prepare_bg(const, H, W)
+    assert mode == 1 and t.shape == (7,) and torch.equal(t, torch.arange(7.0))
+    full = torch.rand(7, H, W)
+    t, mode = rasterizer._prepare_bg(full, H, W)
+    assert mode == 0 and t.data_ptr() == full.data_ptr()
+    # colour-sized constant map reused for a smaller ToF view: the kernel's plane stride is the
+    # render's H*W, so the map has to be materialised to keep the wrapped indexing
+    big_const = torch.arange(7.0).view(7, 1, 1).expand(7, 2 * H, 2 * W)
+    t, mode = rasterizer._prepare_bg(big_const, H, W)
+    assert mode == 0 and t.is_contiguous() and t.numel() == 7 * 4 * H * W
+    with pytest.raises(RuntimeError, match="at least 7\\*H\\*W"):
+        rasterizer._prepare_bg(torch.zeros(3, H, W), H, W)
+
+
+def test_dropin_import_paths():
+    # gaussian_renderer/__init__.py:14 and scene/gaussian_model.py:20
+    sys.path.insert(0, os.path.join(ROOT, "gftorf_b200", "dropin"))
+    try:
+        from diff_gaussian_rasterization_w_tof import GaussianRasterizationSettings, GaussianRasterizer
+        from simple_knn._C import distCUDA2
+        assert GaussianRasterizer is rasterizer.GaussianRasterizer
+        assert GaussianRasterizationSettings is rasterizer.GaussianRasterizationSettings
+        assert distCUDA2 is gftorf_b200.distCUDA2
+    finally:
+        sys.path.pop(0)
+
+
+def test_autograd_function_signature():
+    import inspect
+    fwd = inspect.signature(rasterizer._RasterizeGaussians.forward)
+    assert list(fwd.parameters)[1:] == ["means3D", "means2D", "sh", "sh_p", "colors_precomp",
+                                        "phasors_precomp", "opacities", "scales", "rotations",
+                                        "cov3Ds_precomp", "phase_offset", "dc_offset", "raster_settings"]
+    gr = inspect.signature(rasterizer.GaussianRasterizer.forward)
+    assert list(gr.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "shs_p",
+                                       "colors_precomp", "phasors_precomp", "scales", "rotations",
+                                       "cov3D_precomp", "phase_offset", "dc_offset"]
