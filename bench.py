@@ -312,6 +312,13 @@ def run_gpu(args, impl):
         sampler.start()
     total_ms, wall_ms, launches, stages, stats = timed(step_resident, K, W, profile=True)
     clocks = sampler.stop() if rank == 0 else None
+    if args.resident_only:
+        if rank == 0:
+            print(json.dumps({"resident_only": True, "ms_per_step": total_ms / K,
+                              "gpu_launches": launches}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_ms, _, _, _, _ = timed(step_e2e, K, W)
 
     # render-only throughput (forward only, all outputs) — BASELINE's second metric
@@ -458,6 +465,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--resident-only", action="store_true",
+                    help="skip the e2e / render-only / cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "cpu":

@@ -322,8 +322,10 @@ def test_subtile_culling_is_exact():
             assert torch.equal(a[i], b[i]), (name, harness.FWD_NAMES[i])
         ga = harness.call_backward(rasterizer._C, inp, a)
         gb = harness.call_backward(rasterizer._C, inp, b)
+        scale = float(ga[8].double().norm())
         for x, y in zip(ga, gb):
-            assert harness.rel_l2(x, y) <= 1e-5
+            err = float((x.double() - y.double()).norm())
+            assert err <= 1e-5 * max(float(y.double().norm()), 1e-3 * scale)
 
 
 def test_debug_mode_runs():

@@ -1,0 +1,134 @@
+"""Self-consistency of the CPU oracle, independent of any GPU: its analytic backward against
+central finite differences of its own forward (pins the gradient formulas the reference's goldens
+cannot — all rows of dL_dsh_p and dL_dmeans3D with non-zero phase/amplitude SH),
+plus domain edge cases (empty input, everything culled, linearity of the backward)."""
+import numpy as np
+import pytest
+import torch
+
+import harness
+from oracle import cpu_oracle
+
+pytestmark = pytest.mark.skipif(not cpu_oracle.available(), reason="oracle/libgft_oracle.so not built")
+
+
+def _scene():
+    # few splats, each covering the whole 32x32 image with alpha well above 1/255 and total
+    # transmittance well above 1e-4: no (pixel, Gaussian) pair sits near a threshold, so the
+    # forward is smooth in every parameter over the finite-difference step
+    inp = harness.build_inputs(P=16, W=32, H=32, kind="trained", seed=3, device="cpu", sigma_px=40.0,
+                               view_dependent_phase=True, phase_offset=0.2, dc_offset=0.1)
+    g = torch.Generator().manual_seed(1)
+    z = inp["means3D"][:, 2:3].abs()
+    focal = 32 / (2 * inp["tanfovx"])
+    inp["scales"] = (z / focal) * 40.0 * (0.8 + 0.4 * torch.rand((16, 3), generator=g))
+    inp["opacities"] = 0.05 + 0.2 * torch.rand((16, 1), generator=g)
+    return inp
+
+
+def _loss(inp):
+    f = harness.call_forward(cpu_oracle.OracleModule, inp)
+    g = inp["grads"]
+    tot = (f[1].double() * g["color"].double()).sum() + (f[2].double() * g["phasor"].double()).sum() \
+        + (f[3].double() * g["depth"].double()).sum() + (f[5].double() * g["acc"].double()).sum() \
+        + (f[7].double() * g["depth_distortion"].double()).sum()
+    return float(tot), f
+
+
+@pytest.mark.parametrize("name,grad_index,eps", [
+    ("means3D", 4, 2e-3), ("opacities", 3, 2e-3), ("shs", 6, 5e-3), ("shs_p", 7, 5e-3),
+    ("scales", 8, 5e-3), ("rotations", 9, 5e-3),
+])
+def test_backward_matches_finite_differences(name, grad_index, eps):
+    inp = _scene()
+    _, f = _loss(inp)
+    b = harness.call_backward(cpu_oracle.OracleModule, inp, f)
+    grad = b[grad_index].double()
+    rng = np.random.default_rng(5)
+    agree = []
+    for _ in range(6):
+        d = torch.from_numpy(rng.normal(size=tuple(inp[name].shape))).double()
+        if name == "shs_p":
+            # the forward removes the phase DC term (forward.cu:115) but the reference backward still
+            # reports C0*dL_dphase for that coefficient (backward.cu:169) — restated as
+            # is, so that one coefficient is not a derivative of the forward
+            d[:, 0, 0] = 0.0
+        d /= d.norm()
+        base = inp[name].clone()
+        inp[name] = (base.double() + eps * d).float()
+        lp, fp = _loss(inp)
+        inp[name] = (base.double() - eps * d).float()
+        lm, fm = _loss(inp)
+        inp[name] = base
+        if not (torch.equal(fp[9], f[9]) and torch.equal(fm[9], f[9])):
+            continue  # a pixel crossed an alpha threshold inside the step: not differentiable there
+        fd = (lp - lm) / (2 * eps)
+        an = float((grad * d).sum())
+        agree.append((fd, an))
+    assert len(agree) >= 3
+    for fd, an in agree:
+        # error budget: 2% of the directional derivative + 0.2% of the gradient norm (float32 FD noise)
+        assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an)) + 2e-3 * float(grad.norm()) + 1e-3, (name, fd, an)
+
+
+def test_scalar_offset_gradients_match_finite_differences():
+    inp = _scene()
+    _, f = _loss(inp)
+    b = harness.call_backward(cpu_oracle.OracleModule, inp, f)
+    for key, idx in (("phase_offset", 10), ("dc_offset", 11)):
+        eps = 1e-3
+        base = inp[key]
+        inp[key] = base + eps
+        lp, _ = _loss(inp)
+        inp[key] = base - eps
+        lm, _ = _loss(inp)
+        inp[key] = base
+        fd = (lp - lm) / (2 * eps)
+        an = float(b[idx])
+        assert abs(fd - an) <= 2e-2 * max(abs(fd), abs(an)) + 1e-3, (key, fd, an)
+
+
+def test_backward_is_linear_in_pixel_gradients():
+    inp = _scene()
+    f = harness.call_forward(cpu_oracle.OracleModule, inp)
+    b1 = harness.call_backward(cpu_oracle.OracleModule, inp, f)
+    inp["grads"] = {k: 3.0 * v for k, v in inp["grads"].items()}
+    b3 = harness.call_backward(cpu_oracle.OracleModule, inp, f)
+    for a, c, k in zip(b1, b3, harness.BWD_NAMES):
+        if a.numel():
+            assert harness.rel_l2(3.0 * a, c) <= 1e-5, k
+
+
+def test_empty_and_fully_culled_inputs():
+    inp = harness.build_inputs(P=0, W=20, H=12, device="cpu")
+    f = harness.call_forward(cpu_oracle.OracleModule, inp)
+    assert f[0] == 0 and all(float(f[i].abs().sum()) == 0 for i in range(1, 11))
+    inp = harness.build_inputs(P=50, W=20, H=12, device="cpu", seed=2)
+    inp["means3D"] = inp["means3D"] * torch.tensor([1.0, 1.0, -1.0])
+    f = harness.call_forward(cpu_oracle.OracleModule, inp)
+    assert f[0] == 0 and int((f[11] != 0).sum()) == 0
+    assert torch.equal(f[1], inp["bg"][0:3]) and torch.equal(f[2], inp["bg"][0:7])  # T = 1
+    b = harness.call_backward(cpu_oracle.OracleModule, inp, f)
+    assert all(float(t.abs().sum()) == 0 for t in b)
+
+
+def test_binning_invariants():
+    inp = harness.build_inputs(P=3000, W=100, H=70, kind="trained", seed=8, device="cpu", sigma_px=3.0)
+    f = harness.call_forward(cpu_oracle.OracleModule, inp)
+    d = cpu_oracle.decode(f[12])
+    R = f[0]
+    keys = d["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())
+    same = keys[1:] == keys[:-1]
+    assert bool((d["point_list"][1:][same] > d["point_list"][:-1][same]).all())   # stable
+    lens = (d["ranges"][:, 1] - d["ranges"][:, 0]).long()
+    assert int(lens.sum()) == R == int(d["tiles_touched"].long().sum())
+    assert float(f[9].sum()) > 0
+    # pixels[i] counts contributing pixels: bounded by the tiles the Gaussian touches
+    assert bool((f[9].view(-1) <= d["tiles_touched"].float() * 256).all())
+    # knn: symmetric pair + order independence
+    pts = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3], [5, 5, 5]])
+    out = cpu_oracle.distCUDA2(pts)
+    assert abs(float(out[0]) - (1 + 4 + 9) / 3) < 1e-6
+    perm = torch.tensor([4, 2, 0, 3, 1])
+    assert torch.equal(cpu_oracle.distCUDA2(pts[perm]), out[perm])
