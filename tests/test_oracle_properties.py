@@ -96,7 +96,7 @@ def test_backward_is_linear_in_pixel_gradients():
     b3 = harness.call_backward(cpu_oracle.OracleModule, inp, f)
     for a, c, k in zip(b1, b3, harness.BWD_NAMES):
         if a.numel():
-            assert harness.rel_l2(3.0 * a, c) <= 1e-5, k
+            assert harness.rel_l2(3.0 * a, c) <= 1e-4, k
 
 
 def test_empty_and_fully_culled_inputs():
