@@ -362,6 +362,9 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
     return fail(-1, "gft_backward: incoming gradient pointer is null");
   if (!a->dL_dmeans2D || !a->dL_dopacity || !a->dL_dmeans3D || !a->scratch)
     return fail(-1, "gft_backward: required output pointer is null");
+  if (a->dL_dphasors)
+    return fail(-1, "gft_backward: dL_dphasors is a reference-only field (the 7 phasor gradients are "
+                    "reduced to the 4 combinations the phasor backward consumes); pass NULL");
   if ((a->shs && !a->dL_dsh) || (a->shs_p && !a->dL_dsh_p) ||
       (a->scales && (!a->dL_dscales || !a->dL_drotations)))
     return fail(-1, "gft_backward: missing gradient buffer for a provided input");
@@ -419,7 +422,7 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   pb.dL_dmeans3D = a->dL_dmeans3D; pb.dL_dsh = a->dL_dsh; pb.dL_dsh_p = a->dL_dsh_p;
   pb.dL_dscales = a->dL_dscales; pb.dL_drotations = a->dL_drotations;
   pb.dL_dphase_offset = a->dL_dphase_offset; pb.dL_ddc_offset = a->dL_ddc_offset;
-  pb.dL_dcolors = a->dL_dcolors; pb.dL_dphasors = a->dL_dphasors; pb.dL_dcov3D = a->dL_dcov3D;
+  pb.dL_dcolors = a->dL_dcolors; pb.dL_dcov3D = a->dL_dcov3D;
   pb.dL_dconic = a->dL_dconic; pb.dL_ddist = a->dL_ddist; pb.dL_dndc = a->dL_dndc;
   { Stage st("preprocess_bwd", stream); gft::launch_preprocess_bwd(pb, stream); }
   GFT_CUDA_OK("preprocess_bwd");

@@ -2,23 +2,35 @@
 //
 // Replaces renderCUDA<3,7> of the backward pass (cuda_rasterizer/backward.cu:609-889).
 //
-// The reference issues 18 scalar global atomicAdds for every contributing (pixel, Gaussian) pair
-// (backward.cu:788,802,812,832,876-877,881-883,886).  Here:
-//   - a 16x16 tile is walked by 8 warps of 8x4 pixels, 32 Gaussians at a time; a warp skips
-//     Gaussians whose conservative alpha>=1/255 box misses its patch (exact, see blend_fwd.cu);
-//   - the 18 per-pair partial gradients are summed over the warp's 32 pixels with a halving
-//     butterfly (20 -> 10 -> 5 values per lane, then a 3-step butterfly on the 5: 30 shuffles
-//     instead of 18*5 = 90), which leaves record floats [4g..4g+3] and [16+g] of the Gaussian's
-//     20-float gradient record complete in the lanes of lane-group g = lane>>3;
-//   - four lanes then issue one 16-byte vector reduction each (REDG.E.ADD.F32x4) plus two scalar
-//     ones: 6 reductions per (warp, Gaussian) instead of up to 32*18.
-//   - batches behind the furthest last-contributor of the tile are never loaded.
-// The per-pixel recurrences are the reference's, with `accum_rec` advanced at the end of an
-// iteration instead of the start of the next (same operations, same order, no last_color copy).
+// The reference keeps 13 per-channel back-to-front recurrences per pixel (accum_rec[3],
+// accum_rec_p[7], accum_rec_d, accum_rec_a, accum_rec_dd; backward.cu:673-683,780-833) and issues
+// 18 scalar global atomicAdds for every contributing (pixel, Gaussian) pair
+// (:788,802,812,832,876-877,881-883,886).  Here:
 //
-// Gradient record layout [P][20] (private; consumed by preprocess_bwd.cu):
-//   0 mean2D.x  1 mean2D.y  2 conic.x  3 conic.y | 4 conic.w  5 opacity  6 col.r  7 col.g |
-//   8 col.b  9 dist  10 ndc  11 ph0 | 12 ph1 13 ph2 14 ph3 15 ph4 | 16 ph5 17 ph6 18,19 unused
+//   * Scalar recurrences.  dL/dalpha only ever needs the recurrences CONTRACTED with the pixel's
+//     incoming gradients, and those contractions obey the same recurrences:
+//        weight alpha*T   family (colour, depth, acc, distortion):  X <- alpha*x + (1-alpha)*X,
+//            x = sum_c c*g_c + dist*g_d + dL_dw + g_a,      dL/dalpha += (x - X) * T
+//        weight alpha*T^2 family (7 phasor channels):            B <- alpha*pi + (1-alpha)^2*B,
+//            pi = sum_ch p_ch*g_ch,                          dL/dalpha += (pi - 2(1-alpha)B) * T^2
+//     Two scalar recurrences replace thirteen; same mathematics, a different (shorter) rounding path.
+//   * Per-Gaussian partials are sums over pixels of (per-pair scalar) x (per-pixel constant), and
+//     per-Gaussian factors are pulled out of the sums: the kernel accumulates
+//        S_x=sum h*dx  S_y=sum h*dy  S_xx=sum h*dx^2  S_xy=sum h*dx*dy  S_yy=sum h*dy^2   (h = o*G*dL/dalpha)
+//        sum G*dL/dalpha | sum w*g_c[3] | sum w*g_d | sum w*(2z*k2-k1) | sum wp*(gA,gB,gC,gS)
+//     where (gA,gB,gC,gS) are the four linear combinations of the 7 phasor pixel gradients that the
+//     phasor backward consumes (backward.cu:551-577).  15 values instead of 18.
+//   * Warp reduction with a halving butterfly: 16 -> 8 -> 4 -> 2 -> 1 values per lane (15 shuffles)
+//     plus one xor-1 step: 16 shuffles instead of 18*5 = 90.  Value i ends complete in lanes
+//     2i, 2i+1; the even lanes issue ONE reduction instruction onto the Gaussian's 64-byte record.
+//   * a 16x16 tile is walked by 8 warps of 8x4 pixels, 32 Gaussians at a time; a warp skips
+//     Gaussians whose conservative alpha>=1/255 box misses its patch (exact, see blend_fwd.cu);
+//     batches behind the tile's furthest last-contributor are never loaded; the next batch is
+//     gathered with cp.async into the other half of a double buffer while this one is processed.
+//
+// Gradient record [P][16] (private; consumed by preprocess_bwd.cu):
+//   0 S_x  1 S_y  2 S_xx  3 S_xy  4 S_yy  5 opacity  6 col.r  7 col.g  8 col.b  9 dist  10 ndc
+//   11 phA = dR+dq1-dq2   12 phB = dI+dq3-dq4   13 phC = dA   14 phS = dq1+dq2+dq3+dq4   15 unused
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,28 +40,30 @@ namespace {
 
 constexpr int BATCH = 256;
 
-struct BwdSmem {
+struct BwdBuf {
   float4 r0[BATCH];  // x y ex ey
   float4 r1[BATCH];  // conA conB conC opacity
   float4 r2[BATCH];  // r g b dist
   float4 r3[BATCH];  // ph0..ph3
   float4 r4[BATCH];  // ph4 ph5 ph6 ndc
   int id[BATCH];
-  uint32_t wmax[GFT_BLOCK / 32];
 };
 
-// Butterfly value index -> which quantity.  Lane-group g ends up owning values 5g..5g+4 which are
-// record floats 4g..4g+3 and 16+g.
-//   v[0..3]   = rec 0..3      v[4]  = rec 16
-//   v[5..8]   = rec 4..7      v[9]  = rec 17
-//   v[10..13] = rec 8..11     v[14] = rec 18 (pad)
-//   v[15..18] = rec 12..15    v[19] = rec 19 (pad)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 }  // namespace
 
-__global__ void __launch_bounds__(GFT_BLOCK, 2)
+__global__ void __launch_bounds__(GFT_BLOCK, 3)
 blend_bwd_kernel(BlendBwdParams p) {
-  __shared__ BwdSmem s;
+  extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
+  BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw);
+  __shared__ uint32_t s_wmax[GFT_BLOCK / 32];
+
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
@@ -66,18 +80,16 @@ blend_bwd_kernel(BlendBwdParams p) {
   const uint2 range = p.ranges[tile];
   const int n = (int)(range.y - range.x);
 
-  // per-pixel forward state and incoming gradients
-  float T_final = 0.f, w_z_total = 0.f, w_z2_total = 0.f;
+  // ---- per-pixel forward state, incoming gradients and the constants derived from them ----
+  float T_final = 0.f;
   uint32_t last_contributor = 0;
   float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
   float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f, gp3 = 0.f, gp4 = 0.f, gp5 = 0.f, gp6 = 0.f;
-  float gd = 0.f, ga = 0.f, gdd = 0.f;
-  float bgdot_c = 0.f, bgdot_p = 0.f;
+  float gd = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, bgdot = 0.f;
   if (inside) {
     const float4 st = __ldg(p.img_state + pix_id);
     T_final = st.x;
-    w_z_total = st.y;
-    w_z2_total = st.z;
+    const float w_z_total = st.y, w_z2_total = st.z;
     last_contributor = __float_as_uint(st.w);
     gc0 = __ldg(p.dL_dcolor + 0 * HW + pix_id);
     gc1 = __ldg(p.dL_dcolor + 1 * HW + pix_id);
@@ -90,8 +102,12 @@ blend_bwd_kernel(BlendBwdParams p) {
     gp5 = __ldg(p.dL_dphasor + 5 * HW + pix_id);
     gp6 = __ldg(p.dL_dphasor + 6 * HW + pix_id);
     gd = __ldg(p.dL_ddepth + pix_id);
-    ga = __ldg(p.dL_dacc + pix_id);
-    gdd = __ldg(p.dL_ddd + pix_id);
+    const float ga = __ldg(p.dL_dacc + pix_id);
+    const float gdd = __ldg(p.dL_ddd + pix_id);
+    // dL_dw + g_a = z^2*k2 - z*k1 + k0  (backward.cu:828 with the (1 - T_final) of quirk A.7-5)
+    k2 = gdd * (1.f - T_final);
+    k1 = 2.0f * gdd * w_z_total;
+    k0 = gdd * w_z2_total + ga;
     float bgv[7];
     if (p.bg_mode == 0) {
 #pragma unroll
@@ -100,50 +116,61 @@ blend_bwd_kernel(BlendBwdParams p) {
 #pragma unroll
       for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
     }
-    // backward.cu:850-857 (pixel constants; the reference recomputes them for every pair)
-    bgdot_c = bgv[0] * gc0 + bgv[1] * gc1 + bgv[2] * gc2;
-    bgdot_p = bgv[0] * gp0 + bgv[1] * gp1 + bgv[2] * gp2 + bgv[3] * gp3 + bgv[4] * gp4 +
-              bgv[5] * gp5 + bgv[6] * gp6;
+    // backward.cu:850-858: both background terms enter dL/dalpha with the factor -T_final/(1-alpha)
+    bgdot = bgv[0] * gc0 + bgv[1] * gc1 + bgv[2] * gc2 +
+            (bgv[0] * gp0 + bgv[1] * gp1 + bgv[2] * gp2 + bgv[3] * gp3 + bgv[4] * gp4 +
+             bgv[5] * gp5 + bgv[6] * gp6);
   }
+  // the four combinations of phasor pixel gradients the phasor backward needs
+  const float gA = gp0 + gp3 - gp4;
+  const float gB = gp1 + gp5 - gp6;
+  const float gS = (gp3 + gp4) + (gp5 + gp6);
 
   // furthest contributor of the warp / of the tile
   uint32_t wmax = last_contributor;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s.wmax[warp] = wmax;
+  if (lane == 0) s_wmax[warp] = wmax;
   __syncthreads();
   uint32_t bmax = 0;
 #pragma unroll
-  for (int w = 0; w < GFT_BLOCK / 32; ++w) bmax = max(bmax, s.wmax[w]);
-  const int n_eff = min(n, (int)bmax);  // Gaussians at tile-list positions >= bmax are skipped by every pixel
+  for (int w = 0; w < GFT_BLOCK / 32; ++w) bmax = max(bmax, s_wmax[w]);
+  const int n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
 
   float T = T_final;
-  float ar_c0 = 0.f, ar_c1 = 0.f, ar_c2 = 0.f;
-  float ar_p0 = 0.f, ar_p1 = 0.f, ar_p2 = 0.f, ar_p3 = 0.f, ar_p4 = 0.f, ar_p5 = 0.f, ar_p6 = 0.f;
-  float ar_d = 0.f, ar_a = 0.f, ar_dd = 0.f;
-  const float ddelx_dx = 0.5f * (float)p.W;
-  const float ddely_dy = 0.5f * (float)p.H;
-  const float one_m_Tf = 1.f - T_final;
+  float X = 0.f;     // contracted alpha*T-family recurrence
+  float Bp = 0.f;    // contracted alpha*T^2-family recurrence
 
   const int nb = (n_eff + BATCH - 1) / BATCH;
-  for (int b = nb - 1; b >= 0; --b) {
+
+  auto stage = [&](int b, int which) {
     const int base = b * BATCH;
     const int m = min(BATCH, n_eff - base);
-    __syncthreads();
     if ((int)tid < m) {
       const int g = (int)__ldg(p.point_list + range.x + base + tid);
       const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
-      s.id[tid] = g;
-      s.r0[tid] = __ldg(r + 0);
-      s.r1[tid] = __ldg(r + 1);
-      s.r2[tid] = __ldg(r + 2);
-      s.r3[tid] = __ldg(r + 3);
-      s.r4[tid] = __ldg(r + 4);
+      BwdBuf& d = buf[which];
+      d.id[tid] = g;
+      cp_async16(&d.r0[tid], r + 0);
+      cp_async16(&d.r1[tid], r + 1);
+      cp_async16(&d.r2[tid], r + 2);
+      cp_async16(&d.r3[tid], r + 3);
+      cp_async16(&d.r4[tid], r + 4);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
 
-    // positions >= wmax contribute nothing for this warp
-    const int m_w = min(m, (int)wmax - base);
+  int cur = 0;
+  if (nb > 0) stage(nb - 1, cur);
+  for (int b = nb - 1; b >= 0; --b) {
+    cp_async_wait_all();
+    __syncthreads();                       // batch b is in buf[cur]; everyone left buf[cur^1]
+    if (b > 0) stage(b - 1, cur ^ 1);      // gather the next (nearer) batch while this one is used
+    const BwdBuf& s = buf[cur];
+    const int base = b * BATCH;
+    const int m = min(BATCH, n_eff - base);
+
+    const int m_w = min(m, (int)wmax - base);  // positions >= wmax contribute nothing for this warp
     for (int c = ((m_w - 1) >> 5) << 5; c >= 0 && m_w > 0; c -= 32) {
       const int jj = c + (int)lane;
       bool hit = false;
@@ -162,7 +189,7 @@ blend_bwd_kernel(BlendBwdParams p) {
         const float dx = __fsub_rn(g0.x, pixfx);
         const float dy = __fsub_rn(g0.y, pixfy);
         const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
-        // backward.cu:739-754
+        // backward.cu:739-754 — the same alpha chain as the forward, so the same pairs are replayed
         bool contrib = ((uint32_t)(base + k) < last_contributor) && !(power > 0.0f);
         float G = 0.f, alpha = 0.f;
         if (contrib) {
@@ -172,130 +199,102 @@ blend_bwd_kernel(BlendBwdParams p) {
         }
         if (!__any_sync(0xffffffffu, contrib)) continue;
 
-        float v[20];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 20; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
         if (contrib) {
           const float4 g2 = s.r2[k];
           const float4 g3 = s.r3[k];
           const float4 g4 = s.r4[k];
           const float om = 1.f - alpha;
-          T = T / om;
-          const float w = alpha * T;      // dchannel_dcolor, dchannel_ddepth
-          const float wp = w * T;         // dchannel_dphasor = alpha * T * T
+          const float inv_om = 1.0f / om;
+          T = T * inv_om;                 // backward.cu:756
+          const float w = alpha * T;      // weight of the alpha*T family
+          const float wp = w * T;         // weight of the phasor family, alpha*T*T
 
-          // colour (backward.cu:776-790)
-          float dLa_c = (g2.x - ar_c0) * gc0 + (g2.y - ar_c1) * gc1 + (g2.z - ar_c2) * gc2;
-          dLa_c *= T;
-          // phasor (backward.cu:793-804)
-          const float two_om = 2.f * om;
-          float dLa_p = (g3.x - two_om * ar_p0) * gp0 + (g3.y - two_om * ar_p1) * gp1 +
-                        (g3.z - two_om * ar_p2) * gp2 + (g3.w - two_om * ar_p3) * gp3 +
-                        (g4.x - two_om * ar_p4) * gp4 + (g4.y - two_om * ar_p5) * gp5 +
-                        (g4.z - two_om * ar_p6) * gp6;
-          dLa_p *= T * T;
-          // depth (backward.cu:807-813)
-          const float dLa_d = (g2.w - ar_d) * gd * T;
-          // acc (backward.cu:816-818): accum_rec_a is advanced BEFORE use
-          const float dLa_a = (1.f - ar_a) * ga * T;
-          // depth distortion (backward.cu:825-833), uses (1 - T_final), quirk A.7-5
           const float z = g4.w;
-          const float dL_dw = gdd * (z * z * one_m_Tf - 2.0f * z * w_z_total + w_z2_total);
-          const float dLa_dd = (dL_dw - ar_dd) * T;
-          const float g_ndc = gdd * 2.0f * alpha * T * (z * one_m_Tf - w_z_total);
+          const float kappa = g2.x * gc0 + g2.y * gc1 + g2.z * gc2;
+          const float x_tot = kappa + g2.w * gd + (z * (z * k2 - k1) + k0);
+          const float pi = g3.x * gp0 + g3.y * gp1 + g3.z * gp2 + g3.w * gp3 + g4.x * gp4 +
+                           g4.y * gp5 + g4.z * gp6;
+          const float dL_dalpha = (x_tot - X) * T + (pi - 2.f * om * Bp) * (T * T) -
+                                  (T_final * inv_om) * bgdot;
+          X = alpha * x_tot + om * X;
+          Bp = alpha * pi + (om * om) * Bp;
 
-          // background (backward.cu:850-858); the phasor term is added after the T^2 scaling
-          const float bgf = -T_final / om;
-          float dL_dalpha = bgf * bgdot_c;
-          dLa_p += bgf * bgdot_p;
-          dL_dalpha += dLa_c;
-          dL_dalpha += dLa_p;
-          dL_dalpha += dLa_d;
-          dL_dalpha += dLa_a;
-          dL_dalpha += dLa_dd;
-
-          // advance the back-to-front recurrences for the next (nearer) Gaussian
-          ar_c0 = alpha * g2.x + om * ar_c0;
-          ar_c1 = alpha * g2.y + om * ar_c1;
-          ar_c2 = alpha * g2.z + om * ar_c2;
-          const float om2 = om * om;
-          ar_p0 = alpha * g3.x + om2 * ar_p0;
-          ar_p1 = alpha * g3.y + om2 * ar_p1;
-          ar_p2 = alpha * g3.z + om2 * ar_p2;
-          ar_p3 = alpha * g3.w + om2 * ar_p3;
-          ar_p4 = alpha * g4.x + om2 * ar_p4;
-          ar_p5 = alpha * g4.y + om2 * ar_p5;
-          ar_p6 = alpha * g4.z + om2 * ar_p6;
-          ar_d = alpha * g2.w + om * ar_d;
-          ar_a = alpha + om * ar_a;
-          ar_dd = alpha * dL_dw + om * ar_dd;
-
-          // backward.cu:869-886
-          const float dL_dG = g1.w * dL_dalpha;
-          const float gdx = G * dx, gdy = G * dy;
-          const float dG_ddelx = -gdx * g1.x - gdy * g1.y;
-          const float dG_ddely = -gdy * g1.z - gdx * g1.y;
-          v[0] = dL_dG * dG_ddelx * ddelx_dx;   // mean2D.x
-          v[1] = dL_dG * dG_ddely * ddely_dy;   // mean2D.y
-          v[2] = -0.5f * gdx * dx * dL_dG;      // conic.x
-          v[3] = -0.5f * gdx * dy * dL_dG;      // conic.y
-          v[5] = -0.5f * gdy * dy * dL_dG;      // conic.w   (rec 4)
-          v[6] = G * dL_dalpha;                 // opacity   (rec 5)
-          v[7] = w * gc0;                       // rec 6
-          v[8] = w * gc1;                       // rec 7
-          v[10] = w * gc2;                      // rec 8
-          v[11] = w * gd;                       // rec 9  dist
-          v[12] = g_ndc;                        // rec 10 ndc
-          v[13] = wp * gp0;                     // rec 11
-          v[15] = wp * gp1;                     // rec 12
-          v[16] = wp * gp2;                     // rec 13
-          v[17] = wp * gp3;                     // rec 14
-          v[18] = wp * gp4;                     // rec 15
-          v[4] = wp * gp5;                      // rec 16
-          v[9] = wp * gp6;                      // rec 17
+          const float h = g1.w * dL_dalpha * G;   // dL_dG * G
+          const float hx = h * dx, hy = h * dy;
+          v[0] = hx;
+          v[1] = hy;
+          v[2] = hx * dx;
+          v[3] = hx * dy;
+          v[4] = hy * dy;
+          v[5] = G * dL_dalpha;
+          v[6] = w * gc0;
+          v[7] = w * gc1;
+          v[8] = w * gc2;
+          v[9] = w * gd;
+          v[10] = w * (2.f * z * k2 - k1);
+          v[11] = wp * gA;
+          v[12] = wp * gB;
+          v[13] = wp * gp2;
+          v[14] = wp * gS;
         }
 
-        // ---- halving butterfly over the warp --------------------------------------------
-        float r[10];
+        // ---- halving butterfly: value i ends complete in lanes 2i and 2i+1 -----------------
+        float a8[8];
         {
           const bool up = (lane & 16u) != 0u;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const float send = up ? v[i] : v[i + 10];
-            const float keep = up ? v[i + 10] : v[i];
-            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8];
+            const float keep = up ? v[i + 8] : v[i];
+            a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
           }
         }
-        float q[5];
+        float a4[4];
         {
           const bool up = (lane & 8u) != 0u;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const float send = up ? r[i] : r[i + 5];
-            const float keep = up ? r[i + 5] : r[i];
-            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          for (int i = 0; i < 4; ++i) {
+            const float send = up ? a8[i] : a8[i + 4];
+            const float keep = up ? a8[i + 4] : a8[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
           }
         }
+        float a2[2];
+        {
+          const bool up = (lane & 4u) != 0u;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-          for (int i = 0; i < 5; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+          for (int i = 0; i < 2; ++i) {
+            const float send = up ? a4[i] : a4[i + 2];
+            const float keep = up ? a4[i + 2] : a4[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
         }
-        if ((lane & 7u) == 0u) {
-          const uint32_t grp = lane >> 3;
-          float* dst = p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS;
-          atomicAdd(reinterpret_cast<float4*>(dst) + grp, make_float4(q[0], q[1], q[2], q[3]));
-          if (grp < 2u) atomicAdd(dst + 16 + grp, q[4]);
+        float a1;
+        {
+          const bool up = (lane & 2u) != 0u;
+          const float send = up ? a2[0] : a2[1];
+          const float keep = up ? a2[1] : a2[0];
+          a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
         }
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        if ((lane & 1u) == 0u && lane != 30u)   // lane 30 holds the unused slot 15
+          atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), a1);
       }
     }
+    cur ^= 1;
   }
 }
 
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
-  blend_bwd_kernel<<<tiles, GFT_BLOCK, 0, stream>>>(p);
+  const int smem = 2 * (int)sizeof(BwdBuf);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(blend_bwd_kernel, smem, &smem_ok);
+  blend_bwd_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
   note_launches(1);
 }
 

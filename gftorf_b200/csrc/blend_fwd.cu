@@ -5,7 +5,8 @@
 //
 // What is different from the reference kernel, and why the results are still the same:
 //   - every per-Gaussian quantity (xy, conic+opacity, rgb, 7 phasor channels, dist, ndc) is
-//     staged in shared memory from ONE 80-byte record per Gaussian; the reference stages 7 floats
+//     staged in shared memory from ONE 80-byte record per Gaussian, gathered with cp.async into a
+//     double buffer so the next batch's gather overlaps the blending of the current one; the reference stages 7 floats
 //     and re-gathers 12 more from global memory for every contributing (pixel, Gaussian) pair
 //     (forward.cu:551-572).
 //   - a 16x16 tile is covered by 8 warps of 8x4 pixels.  Each warp tests, 32 Gaussians at a time,
@@ -27,7 +28,7 @@ namespace {
 
 constexpr int BATCH = 256;
 
-struct FwdSmem {
+struct FwdBuf {
   float4 r0[BATCH];  // x y ex ey
   float4 r1[BATCH];  // conA conB conC opacity
   float4 r2[BATCH];  // r g b dist
@@ -37,11 +38,19 @@ struct FwdSmem {
   int cnt[BATCH];
 };
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 }  // namespace
 
-__global__ void __launch_bounds__(GFT_BLOCK)
+__global__ void __launch_bounds__(GFT_BLOCK, 3)
 blend_fwd_kernel(BlendFwdParams p) {
-  __shared__ FwdSmem s;
+  extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
+  FwdBuf* buf = reinterpret_cast<FwdBuf*>(fwd_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
@@ -68,23 +77,34 @@ blend_fwd_kernel(BlendFwdParams p) {
   float WD0 = 0.f, WD1 = 0.f, WD2 = 0.f;
   bool first_hit = true;
 
-  for (int base = 0; base < n; base += BATCH) {
-    // End if the entire block votes that it is done (forward.cu:500-502)
-    if (__syncthreads_and(done)) break;
-
+  // gather one batch of the tile list into a shared-memory buffer with cp.async
+  auto stage = [&](int base, int which) {
     const int m = min(BATCH, n - base);
     if ((int)tid < m) {
       const int g = (int)__ldg(p.point_list + range.x + base + tid);
       const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
-      s.id[tid] = g;
-      s.cnt[tid] = 0;
-      s.r0[tid] = __ldg(r + 0);
-      s.r1[tid] = __ldg(r + 1);
-      s.r2[tid] = __ldg(r + 2);
-      s.r3[tid] = __ldg(r + 3);
-      s.r4[tid] = __ldg(r + 4);
+      FwdBuf& d = buf[which];
+      d.id[tid] = g;
+      d.cnt[tid] = 0;
+      cp_async16(&d.r0[tid], r + 0);
+      cp_async16(&d.r1[tid], r + 1);
+      cp_async16(&d.r2[tid], r + 2);
+      cp_async16(&d.r3[tid], r + 3);
+      cp_async16(&d.r4[tid], r + 4);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+
+  int cur = 0;
+  if (n > 0) stage(0, cur);
+  for (int base = 0; base < n; base += BATCH) {
+    cp_async_wait_all();
+    // End if the entire block votes that it is done (forward.cu:500-502); the same barrier
+    // publishes batch `base` in buf[cur] and retires every reader of buf[cur^1].
+    if (__syncthreads_and(done)) break;
+    if (base + BATCH < n) stage(base + BATCH, cur ^ 1);   // overlaps with the work below
+    FwdBuf& s = buf[cur];
+    const int m = min(BATCH, n - base);
 
     if (!warp_done) {
       for (int c = 0; c < m; c += 32) {
@@ -172,7 +192,9 @@ blend_fwd_kernel(BlendFwdParams p) {
       const int cnt = s.cnt[tid];
       if (cnt) atomicAdd(p.pixels + s.id[tid], (float)cnt);
     }
+    cur ^= 1;
   }
+  cp_async_wait_all();   // a prefetch may still be in flight when the tile finished early
 
   if (inside) {
     const size_t HW = (size_t)p.H * (size_t)p.W;
@@ -216,7 +238,10 @@ blend_fwd_kernel(BlendFwdParams p) {
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
-  blend_fwd_kernel<<<tiles, GFT_BLOCK, 0, stream>>>(p);
+  const int smem = 2 * (int)sizeof(FwdBuf);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(blend_fwd_kernel, smem, &smem_ok);
+  blend_fwd_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
   note_launches(1);
 }
 

@@ -19,7 +19,7 @@
 #define GFT_TILE_X 16
 #define GFT_TILE_Y 16
 #define GFT_REC_FLOATS 20   // blend record: 5 x float4 per Gaussian
-#define GFT_GRAD_FLOATS 20  // blend-gradient record: 5 x float4 per Gaussian
+#define GFT_GRAD_FLOATS 16  // blend-gradient record: 64 bytes per Gaussian (layout: blend_bwd.cu)
 
 namespace gft {
 
@@ -184,6 +184,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// ---- warp-cooperative staging of per-Gaussian rows ------------------------------------------
+// The SH tensors are [P][ROW] row-major, so the rows of a warp's 32 consecutive Gaussians are one
+// contiguous chunk of global memory.  These helpers move the chunk between global memory (fully
+// coalesced: lane l touches element l, l+32, ...) and a warp-private shared buffer with row stride
+// ROW+1 floats, in which lane l then walks row l without bank conflicts ((ROW+1) is odd).
+template <int ROW>
+__device__ __forceinline__ void warp_stage_in(const float* __restrict__ gbase, int nrows,
+                                              float* sbuf, uint32_t lane) {
+  const int total = nrows * ROW;
+#pragma unroll 4
+  for (int e = (int)lane; e < total; e += 32) {
+    const int r = e / ROW, c = e - r * ROW;
+    sbuf[r * (ROW + 1) + c] = __ldg(gbase + e);
+  }
+}
+template <int ROW>
+__device__ __forceinline__ void warp_stage_out(float* __restrict__ gbase, int nrows,
+                                               const float* sbuf, uint32_t lane) {
+  const int total = nrows * ROW;
+#pragma unroll 4
+  for (int e = (int)lane; e < total; e += 32) {
+    const int r = e / ROW, c = e - r * ROW;
+    gbase[e] = sbuf[r * (ROW + 1) + c];
+  }
+}
+#define GFT_STAGE_FLOATS_PER_WARP (32 * 49)
 
 // Relaxed/acquire 64-bit accesses for the decoupled look-back scan.
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {

@@ -9,6 +9,18 @@ namespace gft {
 // process-wide count of kernels launched by this library (gft_launch_count in the C ABI)
 void note_launches(int n);
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is
+// per device; setting it on every launch costs a driver call each time).
+template <typename K>
+inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+}
+
 struct PreprocessParams {
   int P, D, M, M_p;
   int W, H, grid_x, grid_y, num_tiles;
@@ -101,7 +113,7 @@ struct BlendBwdParams {
   const float* dL_ddepth;
   const float* dL_dacc;
   const float* dL_ddd;
-  float* grad_rec;  // [P][20], zero-filled before launch
+  float* grad_rec;  // [P][16], zero-filled before launch
 };
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream);
 
@@ -124,7 +136,7 @@ struct PreprocessBwdParams {
   float focal_x, focal_y, tan_fovx, tan_fovy;
   const float* rec;       // forward blend records (dist)
   const float* pa;        // [P][2]
-  const float* grad_rec;  // [P][20] from blend backward
+  const float* grad_rec;  // [P][16] from blend backward
   float near_n, far_n, dist2phase;
   int use_view_dependent_phase;
   float phase_offset, dc_offset;
@@ -139,7 +151,6 @@ struct PreprocessBwdParams {
   float* dL_dphase_offset;
   float* dL_ddc_offset;
   float* dL_dcolors;
-  float* dL_dphasors;
   float* dL_dcov3D;
   float* dL_dconic;
   float* dL_ddist;

@@ -24,57 +24,88 @@ namespace gft {
 namespace {
 
 __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
-  // Basis values multiplying sh[1..15], in the association of forward.cu:37-59 (SH_Ck * poly).
+  // Basis values multiplying sh[1..15] (forward.cu:37-59), in the dataflow of the reference
+  // binary (SASS of preprocessCUDA, sm_100a): every product rounded, except the four polynomial
+  // terms the compiler fused: 3xx-yy, 2zz-3xx-3yy (two FMAs), xx-3yy.  The phase SH term is
+  // recovered by cancelling a large DC value, so one ulp here is visible in the phasor image.
   if (deg > 0) {
-    b[1] = -kSH_C1 * y;
-    b[2] = kSH_C1 * z;
-    b[3] = -kSH_C1 * x;
+    b[1] = -__fmul_rn(kSH_C1, y);
+    b[2] = __fmul_rn(kSH_C1, z);
+    b[3] = -__fmul_rn(kSH_C1, x);
     if (deg > 1) {
-      const float xx = x * x, yy = y * y, zz = z * z;
-      const float xy = x * y, yz = y * z, xz = x * z;
-      b[4] = kSH_C2_0 * xy;
-      b[5] = kSH_C2_1 * yz;
-      b[6] = kSH_C2_2 * (2.0f * zz - xx - yy);
-      b[7] = kSH_C2_3 * xz;
-      b[8] = kSH_C2_4 * (xx - yy);
+      const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+      const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+      const float zz2 = __fadd_rn(zz, zz);
+      const float xx_yy = __fsub_rn(xx, yy);
+      b[4] = __fmul_rn(xy, kSH_C2_0);
+      b[5] = __fmul_rn(yz, kSH_C2_1);
+      b[6] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), kSH_C2_2);
+      b[7] = __fmul_rn(xz, kSH_C2_3);
+      b[8] = __fmul_rn(xx_yy, kSH_C2_4);
       if (deg > 2) {
-        b[9] = kSH_C3_0 * y * (3.0f * xx - yy);
-        b[10] = kSH_C3_1 * xy * z;
-        b[11] = kSH_C3_2 * y * (4.0f * zz - xx - yy);
-        b[12] = kSH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-        b[13] = kSH_C3_4 * x * (4.0f * zz - xx - yy);
-        b[14] = kSH_C3_5 * z * (xx - yy);
-        b[15] = kSH_C3_6 * x * (xx - 3.0f * yy);
+        const float t11 = __fsub_rn(__fmaf_rn(zz, 4.f, -xx), yy);
+        b[9] = __fmul_rn(__fmul_rn(y, kSH_C3_0), __fmaf_rn(xx, 3.f, -yy));
+        b[10] = __fmul_rn(__fmul_rn(xy, kSH_C3_1), z);
+        b[11] = __fmul_rn(__fmul_rn(y, kSH_C3_2), t11);
+        b[12] = __fmul_rn(__fmul_rn(z, kSH_C3_3), __fmaf_rn(yy, -3.f, __fmaf_rn(xx, -3.f, zz2)));
+        b[13] = __fmul_rn(t11, __fmul_rn(x, kSH_C3_4));
+        b[14] = __fmul_rn(xx_yy, __fmul_rn(z, kSH_C3_5));
+        b[15] = __fmul_rn(__fmul_rn(x, kSH_C3_6), __fmaf_rn(yy, -3.f, xx));
       }
     }
   }
 }
 
-// Load n floats of one SH row; 16-byte vector loads when the row is 16-byte aligned.
-template <int MAXN>
-__device__ __forceinline__ void load_row(const float* __restrict__ row, int n, float* dst) {
-  if ((((uintptr_t)row) & 15) == 0) {
-    const float4* r4 = reinterpret_cast<const float4*>(row);
-    const int n4 = n >> 2;
+}  // namespace
+
+namespace {
+
+// SH -> RGB before the +0.5 (forward.cu:30-62); `sh` may point to global or shared memory
+__device__ __forceinline__ void eval_sh_rgb(int D, const float* sh, const float* basis, float& r0,
+                                            float& r1, float& r2) {
+  r0 = __fmul_rn(kSH_C0, sh[0]); r1 = __fmul_rn(kSH_C0, sh[1]); r2 = __fmul_rn(kSH_C0, sh[2]);
+  if (D > 0) {
+    // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3   (basis carries the sign)
 #pragma unroll
-    for (int i = 0; i < MAXN / 4; ++i) {
-      if (i < n4) {
-        const float4 v = __ldg(r4 + i);
-        dst[4 * i + 0] = v.x;
-        dst[4 * i + 1] = v.y;
-        dst[4 * i + 2] = v.z;
-        dst[4 * i + 3] = v.w;
+    for (int k = 1; k < 4; ++k) {
+      r0 = __fmaf_rn(basis[k], sh[3 * k + 0], r0);
+      r1 = __fmaf_rn(basis[k], sh[3 * k + 1], r1);
+      r2 = __fmaf_rn(basis[k], sh[3 * k + 2], r2);
+    }
+    if (D > 1) {
+#pragma unroll
+      for (int k = 4; k < 9; ++k) {
+        r0 = __fmaf_rn(basis[k], sh[3 * k + 0], r0);
+        r1 = __fmaf_rn(basis[k], sh[3 * k + 1], r1);
+        r2 = __fmaf_rn(basis[k], sh[3 * k + 2], r2);
+      }
+      if (D > 2) {
+#pragma unroll
+        for (int k = 9; k < 16; ++k) {
+          r0 = __fmaf_rn(basis[k], sh[3 * k + 0], r0);
+          r1 = __fmaf_rn(basis[k], sh[3 * k + 1], r1);
+          r2 = __fmaf_rn(basis[k], sh[3 * k + 2], r2);
+        }
       }
     }
+  }
+}
+
+// SH -> (phase, amplitude) before the +0.5 (forward.cu:79-111)
+__device__ __forceinline__ void eval_sh_pa(int D, const float* sp, const float* basis, float& q0,
+                                           float& q1) {
+  q0 = __fmul_rn(kSH_C0, sp[0]); q1 = __fmul_rn(kSH_C0, sp[1]);
+  if (D > 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int k = 4 * n4 + i;
-      if (k < n) dst[k] = __ldg(row + k);
+    for (int k = 1; k < 4; ++k) { q0 = __fmaf_rn(basis[k], sp[2 * k], q0); q1 = __fmaf_rn(basis[k], sp[2 * k + 1], q1); }
+    if (D > 1) {
+#pragma unroll
+      for (int k = 4; k < 9; ++k) { q0 = __fmaf_rn(basis[k], sp[2 * k], q0); q1 = __fmaf_rn(basis[k], sp[2 * k + 1], q1); }
+      if (D > 2) {
+#pragma unroll
+        for (int k = 9; k < 16; ++k) { q0 = __fmaf_rn(basis[k], sp[2 * k], q0); q1 = __fmaf_rn(basis[k], sp[2 * k + 1], q1); }
+      }
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < MAXN; ++i)
-      if (i < n) dst[i] = __ldg(row + i);
   }
 }
 
@@ -82,6 +113,7 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, int n, f
 
 __global__ void __launch_bounds__(GFT_BLOCK)
 preprocess_fwd_kernel(PreprocessParams p) {
+  extern __shared__ float fwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
   __shared__ uint32_t s_vbid;
   __shared__ uint32_t s_warp_tot[GFT_BLOCK / 32];
   __shared__ uint32_t s_prefix;
@@ -92,34 +124,37 @@ preprocess_fwd_kernel(PreprocessParams p) {
   __syncthreads();
   const uint32_t vb = s_vbid;
   const int idx = (int)(vb * GFT_BLOCK + threadIdx.x);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
   // Zero tile ranges (empty tiles must read (0,0), rasterizer_impl.cu:341).
   for (int t = idx; t < p.num_tiles; t += gridDim.x * GFT_BLOCK) p.ranges[t] = make_uint2(0u, 0u);
 
   uint32_t tiles = 0;
-  if (idx < p.P) {
-    int radius_i = 0;
-    uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
-    p.pixels[idx] = 0.f;
+  const bool in_range = idx < p.P;
+  int radius_i = 0;
+  uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+  float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, pix_x = 0.f, pix_y = 0.f;
+  float3 cov = make_float3(0.f, 0.f, 0.f);
+  float det = 0.f;
+  bool alive = false;
+  const float* __restrict__ V = p.viewmatrix;
+  const float* __restrict__ PM = p.projmatrix;
 
-    const float* __restrict__ V = p.viewmatrix;
-    const float* __restrict__ PM = p.projmatrix;
-    const float px = __ldg(p.means3D + 3 * idx + 0);
-    const float py = __ldg(p.means3D + 3 * idx + 1);
-    const float pz = __ldg(p.means3D + 3 * idx + 2);
+  // ---- phase 1: cull, project, covariance, radius, tile rectangle -----------------------------
+  if (in_range) {
+    p.pixels[idx] = 0.f;
+    px = __ldg(p.means3D + 3 * idx + 0);
+    py = __ldg(p.means3D + 3 * idx + 1);
+    pz = __ldg(p.means3D + 3 * idx + 2);
 
     // in_frustum, auxiliary.h:152-179: z-only test (NaN passes, as in the reference).
-    const float vz = xform_row(V, 2, px, py, pz);
-    bool alive = !(vz < p.near_n || vz > p.far_n);
+    vz = xform_row(V, 2, px, py, pz);
+    alive = !(vz < p.near_n || vz > p.far_n);
     if (!alive && p.prefiltered) {
       printf("Point is filtered although prefiltered is set. This shouldn't happen!");
       __trap();
     }
 
-    float vx = 0.f, vy = 0.f, pix_x = 0.f, pix_y = 0.f;
-    float3 cov = make_float3(0.f, 0.f, 0.f);
-    float det = 0.f;
-    Cov3 c3;
     if (alive) {
       vx = xform_row(V, 0, px, py, pz);
       vy = xform_row(V, 1, px, py, pz);
@@ -130,6 +165,7 @@ preprocess_fwd_kernel(PreprocessParams p) {
       const float projx = __fmul_rn(hx, p_w);
       const float projy = __fmul_rn(hy, p_w);
 
+      Cov3 c3;
       if (p.cov3D_precomp != nullptr) {
         const float* c = p.cov3D_precomp + 6 * (size_t)idx;
         c3.c0 = __ldg(c + 0); c3.c1 = __ldg(c + 1); c3.c2 = __ldg(c + 2);
@@ -164,179 +200,165 @@ preprocess_fwd_kernel(PreprocessParams p) {
         alive = tiles != 0;
       }
     }
-
-    if (alive) {
-      const float det_inv = __frcp_rn(det);
-      const float conA = __fmul_rn(cov.z, det_inv);
-      const float conB = __fmul_rn(cov.y, -det_inv);
-      const float conC = __fmul_rn(cov.x, det_inv);
-      const float opacity = __ldg(p.opacities + idx);
-
-      // ---- view direction and SH basis (forward.cu:25-27,74-76) ------------------------
-      float basis[16];
-      float dirx = 0.f, diry = 0.f, dirz = 0.f;
-      if (p.shs != nullptr || p.shs_p != nullptr) {
-        const float cxw = __ldg(p.campos + 0), cyw = __ldg(p.campos + 1), czw = __ldg(p.campos + 2);
-        dirx = px - cxw;
-        diry = py - cyw;
-        dirz = pz - czw;
-        const float len = sqrtf(dirx * dirx + diry * diry + dirz * dirz);
-        dirx = dirx / len;
-        diry = diry / len;
-        dirz = dirz / len;
-        sh_basis(p.D, dirx, diry, dirz, basis);
-      }
-      const int ncoef = (p.D + 1) * (p.D + 1);
-
-      // ---- colour (forward.cu:346-359) ---------------------------------------------------
-      float cr = 0.f, cg = 0.f, cb = 0.f;
-      uint32_t clamp_bits = 0;
-      if (p.colors_precomp != nullptr) {
-        cr = __ldg(p.colors_precomp + 3 * (size_t)idx + 0);
-        cg = __ldg(p.colors_precomp + 3 * (size_t)idx + 1);
-        cb = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
-      }
-      if (p.shs != nullptr) {
-        float sh[48];
-        const int n = min(ncoef, p.M);
-        load_row<48>(p.shs + (size_t)idx * p.M * 3, 3 * n, sh);
-        float r0 = kSH_C0 * sh[0], r1 = kSH_C0 * sh[1], r2 = kSH_C0 * sh[2];
-        if (p.D > 0) {
-          // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3   (basis carries the sign)
-#pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            r0 += basis[k] * sh[3 * k + 0];
-            r1 += basis[k] * sh[3 * k + 1];
-            r2 += basis[k] * sh[3 * k + 2];
-          }
-          if (p.D > 1) {
-#pragma unroll
-            for (int k = 4; k < 9; ++k) {
-              r0 += basis[k] * sh[3 * k + 0];
-              r1 += basis[k] * sh[3 * k + 1];
-              r2 += basis[k] * sh[3 * k + 2];
-            }
-            if (p.D > 2) {
-#pragma unroll
-              for (int k = 9; k < 16; ++k) {
-                r0 += basis[k] * sh[3 * k + 0];
-                r1 += basis[k] * sh[3 * k + 1];
-                r2 += basis[k] * sh[3 * k + 2];
-              }
-            }
-          }
-        }
-        r0 += 0.5f; r1 += 0.5f; r2 += 0.5f;
-        clamp_bits |= (r0 < 0.f) ? 1u : 0u;
-        clamp_bits |= (r1 < 0.f) ? (1u << 8) : 0u;
-        clamp_bits |= (r2 < 0.f) ? (1u << 16) : 0u;
-        cr = fmaxf(r0, 0.f); cg = fmaxf(r1, 0.f); cb = fmaxf(r2, 0.f);
-      }
-
-      // ---- distance to light, falloff (forward.cu:361-363) -------------------------------
-      const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
-      const float ndc = p.far_n / (p.far_n - p.near_n) * (1 - p.near_n / dist);
-      const float factor = 1.0f / (dist * dist);
-
-      // ---- phasor (forward.cu:365-407) ----------------------------------------------------
-      // With neither shs_p nor phasors_precomp the reference leaves real_img_amp uninitialised
-      // (SURVEY A.7-7); we define those features as 0.
-      float ph[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float pa0 = 0.f, pa1 = 0.f;
-      bool have_ph = false;
-      float phase = 0.f, amp = 0.f;
-      if (p.phasors_precomp != nullptr) {
-        phase = dist * p.dist2phase;
-        pa0 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 0);
-        pa1 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 1);
-        if (p.use_view_dependent_phase) phase += pa0;
-        amp = pa1;
-        have_ph = true;
-      }
-      if (p.shs_p != nullptr) {
-        float sp[32];
-        const int n = min(ncoef, p.M_p);
-        load_row<32>(p.shs_p + (size_t)idx * p.M_p * 2, 2 * n, sp);
-        float q0 = kSH_C0 * sp[0], q1 = kSH_C0 * sp[1];
-        if (p.D > 0) {
-#pragma unroll
-          for (int k = 1; k < 4; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
-          if (p.D > 1) {
-#pragma unroll
-            for (int k = 4; k < 9; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
-            if (p.D > 2) {
-#pragma unroll
-              for (int k = 9; k < 16; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
-            }
-          }
-        }
-        q0 += 0.5f; q1 += 0.5f;
-        q0 = q0 - 0.5f - kSH_C0 * sp[0];  // remove phase DC (forward.cu:115)
-        if (q1 < 0.f) { clamp_bits |= (1u << 24); q1 = 0.f; }
-        pa0 = q0; pa1 = q1;
-        phase = dist * p.dist2phase + p.phase_offset;
-        if (p.use_view_dependent_phase) phase += q0;
-        amp = q1;
-        have_ph = true;
-      }
-      if (have_ph) {
-        float sn, cs;
-        sincosf(phase, &sn, &cs);
-        ph[0] = cs * amp * factor;
-        ph[1] = sn * amp * factor;
-        ph[2] = amp * factor;
-        ph[3] = (cs + p.dc_offset) * amp * factor;
-        ph[4] = (-cs + p.dc_offset) * amp * factor;
-        ph[5] = (sn + p.dc_offset) * amp * factor;
-        ph[6] = (-sn + p.dc_offset) * amp * factor;
-      }
-
-      // ---- conservative contribution extents for sub-tile culling -----------------------
-      // A pixel can pass the alpha test only if opacity*exp(power) >= 1/255, i.e.
-      // d^T Q d <= 2 ln(255*opacity).  The rounding error of the float `power` chain is bounded
-      // by 2k*cond(Sigma)*q (k = 4e-7), so inflating the threshold by 1/(1-4k*cond) keeps the box
-      // a superset of what the reference's arithmetic can accept.  Anything doubtful -> no cull.
-      float ex = __int_as_float(0x7f800000), ey = __int_as_float(0x7f800000);  // +inf
-      if (!p.subtile_cull) {
-        // keep +inf: no culling
-      } else if (opacity < (1.0f / 255.0f)) {
-        ex = ey = -__int_as_float(0x7f800000);  // alpha <= opacity < 1/255: can never contribute
-      } else {
-        const double dA = (double)conA, dB = (double)conB, dC = (double)conC;
-        const double dq = dA * dC - dB * dB;
-        const float mid = 0.5f * (cov.x + cov.z);
-        const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
-        const float lmax = mid + sq, lmin = mid - sq;
-        const float cond = lmax / lmin;
-        if (dq > 0.0 && dA > 0.0 && dC > 0.0 && lmin > 0.f && cond < 2.0e5f && cond == cond) {
-          const float t2 = (2.0f * __logf(255.0f * opacity) + 0.04f) / (1.0f - 1.6e-6f * cond);
-          const float sxx = (float)(dC / dq), syy = (float)(dA / dq);
-          ex = sqrtf(t2 * sxx) * 1.0001f + 0.02f;
-          ey = sqrtf(t2 * syy) * 1.0001f + 0.02f;
-        }
-      }
-
-      float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS);
-      rec[0] = make_float4(pix_x, pix_y, ex, ey);
-      rec[1] = make_float4(conA, conB, conC, opacity);
-      rec[2] = make_float4(cr, cg, cb, dist);
-      rec[3] = make_float4(ph[0], ph[1], ph[2], ph[3]);
-      rec[4] = make_float4(ph[4], ph[5], ph[6], ndc);
-      p.depths[idx] = vz;
-      p.clamped[idx] = clamp_bits;
-      reinterpret_cast<float2*>(p.pa)[idx] = make_float2(pa0, pa1);
-      reinterpret_cast<uint2*>(p.rect)[idx] =
-          make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
-    } else {
-      tiles = 0;
-      radius_i = 0;
-    }
-    p.radii[idx] = alive ? radius_i : 0;
+    if (!alive) { tiles = 0; radius_i = 0; }
+    p.radii[idx] = radius_i;
     p.tiles_touched[idx] = tiles;
   }
 
+  // ---- phase 2: appearance.  The SH rows of a warp's 32 consecutive Gaussians are one contiguous
+  // chunk of global memory: it is staged through shared memory with coalesced loads whenever a
+  // lane of the warp survived the culling. ------------------------------------------------------
+  float* wbuf = fwd_stage + warp * GFT_STAGE_FLOATS_PER_WARP;
+  const int wfirst = (int)(vb * GFT_BLOCK + warp * 32);
+  const int nrows = max(0, min(32, p.P - wfirst));
+  const bool any_alive = __any_sync(0xffffffffu, alive);
+  const bool st_sh = p.shs != nullptr && p.M == 16 && any_alive;
+  const bool st_shp = p.shs_p != nullptr && p.M_p == 16 && any_alive;
+  if (st_sh) {
+    warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
+    __syncwarp();
+  }
+
+  float basis[16];
+  float cr = 0.f, cg = 0.f, cb = 0.f;
+  uint32_t clamp_bits = 0;
+  if (alive) {
+    // ---- view direction and SH basis (forward.cu:25-27,74-76) ------------------------------
+    if (p.shs != nullptr || p.shs_p != nullptr) {
+      const float cxw = __ldg(p.campos + 0), cyw = __ldg(p.campos + 1), czw = __ldg(p.campos + 2);
+      // pinned to the reference binary: FMUL(dy,dy) -> FFMA(dx,dx,.) -> FFMA(dz,dz,.), IEEE sqrt/div
+      float dirx = __fsub_rn(px, cxw);
+      float diry = __fsub_rn(py, cyw);
+      float dirz = __fsub_rn(pz, czw);
+      const float len = __fsqrt_rn(dot3c(dirx, dirx, diry, diry, dirz, dirz));
+      dirx = __fdiv_rn(dirx, len);
+      diry = __fdiv_rn(diry, len);
+      dirz = __fdiv_rn(dirz, len);
+      sh_basis(p.D, dirx, diry, dirz, basis);
+    }
+    // ---- colour (forward.cu:346-359) ---------------------------------------------------------
+    if (p.colors_precomp != nullptr) {
+      cr = __ldg(p.colors_precomp + 3 * (size_t)idx + 0);
+      cg = __ldg(p.colors_precomp + 3 * (size_t)idx + 1);
+      cb = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
+    }
+    if (p.shs != nullptr) {
+      float r0, r1, r2;
+      if (st_sh) eval_sh_rgb(p.D, wbuf + lane * 49, basis, r0, r1, r2);
+      else eval_sh_rgb(p.D, p.shs + (size_t)idx * p.M * 3, basis, r0, r1, r2);
+      r0 = __fadd_rn(r0, 0.5f); r1 = __fadd_rn(r1, 0.5f); r2 = __fadd_rn(r2, 0.5f);
+      clamp_bits |= (r0 < 0.f) ? 1u : 0u;
+      clamp_bits |= (r1 < 0.f) ? (1u << 8) : 0u;
+      clamp_bits |= (r2 < 0.f) ? (1u << 16) : 0u;
+      cr = fmaxf(r0, 0.f); cg = fmaxf(r1, 0.f); cb = fmaxf(r2, 0.f);
+    }
+  }
+  __syncwarp();
+  if (st_shp) {
+    warp_stage_in<32>(p.shs_p + (size_t)wfirst * 32, nrows, wbuf, lane);
+    __syncwarp();
+  }
+
+  if (alive) {
+    const float det_inv = __frcp_rn(det);
+    const float conA = __fmul_rn(cov.z, det_inv);
+    const float conB = __fmul_rn(cov.y, -det_inv);
+    const float conC = __fmul_rn(cov.x, det_inv);
+    const float opacity = __ldg(p.opacities + idx);
+
+    // ---- distance to light, falloff (forward.cu:361-363) -----------------------------------
+    // pinned to the reference binary (SASS of preprocessCUDA): y^2 rounded, x^2 and z^2 fused
+    const float dist = __fsqrt_rn(dot3c(vx, vx, vy, vy, vz, vz));
+    const float ndc = __fmul_rn(__fsub_rn(1.f, __fdiv_rn(p.near_n, dist)),
+                                __fdiv_rn(p.far_n, __fsub_rn(p.far_n, p.near_n)));
+    const float factor = __frcp_rn(__fmul_rn(dist, dist));
+
+    // ---- phasor (forward.cu:365-407) --------------------------------------------------------
+    // With neither shs_p nor phasors_precomp the reference leaves real_img_amp uninitialised
+    // (SURVEY A.7-7); we define those features as 0.
+    float ph[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float pa0 = 0.f, pa1 = 0.f;
+    bool have_ph = false;
+    float phase = 0.f, amp = 0.f;
+    if (p.phasors_precomp != nullptr) {
+      phase = __fmul_rn(dist, p.dist2phase);
+      pa0 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 0);
+      pa1 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 1);
+      if (p.use_view_dependent_phase) phase = __fadd_rn(phase, pa0);
+      amp = pa1;
+      have_ph = true;
+    }
+    if (p.shs_p != nullptr) {
+      float q0, q1, dc0;
+      if (st_shp) {
+        eval_sh_pa(p.D, wbuf + lane * 33, basis, q0, q1);
+        dc0 = wbuf[lane * 33];
+      } else {
+        const float* sp = p.shs_p + (size_t)idx * p.M_p * 2;
+        eval_sh_pa(p.D, sp, basis, q0, q1);
+        dc0 = sp[0];
+      }
+      q1 = __fadd_rn(q1, 0.5f);
+      // remove phase DC (forward.cu:115): ((q0 + 0.5) - 0.5) - FMUL(C0, sh_p[0].x)
+      q0 = __fsub_rn(__fsub_rn(__fadd_rn(q0, 0.5f), 0.5f), __fmul_rn(kSH_C0, dc0));
+      if (q1 < 0.f) { clamp_bits |= (1u << 24); q1 = 0.f; }
+      pa0 = q0; pa1 = q1;
+      phase = __fmaf_rn(dist, p.dist2phase, p.phase_offset);
+      if (p.use_view_dependent_phase) phase = __fadd_rn(q0, phase);
+      amp = q1;
+      have_ph = true;
+    }
+    if (have_ph) {
+      float sn, cs;
+      sincosf(phase, &sn, &cs);
+      const float dc = p.dc_offset;   // (trig +- dc) * amp * factor, left to right (forward.cu:399-406)
+      ph[0] = __fmul_rn(__fmul_rn(cs, amp), factor);
+      ph[1] = __fmul_rn(__fmul_rn(sn, amp), factor);
+      ph[2] = __fmul_rn(amp, factor);
+      ph[3] = __fmul_rn(__fmul_rn(__fadd_rn(cs, dc), amp), factor);
+      ph[4] = __fmul_rn(__fmul_rn(__fadd_rn(-cs, dc), amp), factor);
+      ph[5] = __fmul_rn(__fmul_rn(__fadd_rn(sn, dc), amp), factor);
+      ph[6] = __fmul_rn(__fmul_rn(__fadd_rn(-sn, dc), amp), factor);
+    }
+
+    // ---- conservative contribution extents for sub-tile culling ---------------------------
+    // A pixel can pass the alpha test only if opacity*exp(power) >= 1/255, i.e.
+    // d^T Q d <= 2 ln(255*opacity).  The rounding error of the float `power` chain is bounded
+    // by 2k*cond(Sigma)*q (k = 4e-7), so inflating the threshold by 1/(1-4k*cond) keeps the box
+    // a superset of what the reference's arithmetic can accept.  Anything doubtful -> no cull.
+    float ex = __int_as_float(0x7f800000), ey = __int_as_float(0x7f800000);  // +inf
+    if (!p.subtile_cull) {
+      // keep +inf: no culling
+    } else if (opacity < (1.0f / 255.0f)) {
+      ex = ey = -__int_as_float(0x7f800000);  // alpha <= opacity < 1/255: can never contribute
+    } else {
+      const double dA = (double)conA, dB = (double)conB, dC = (double)conC;
+      const double dq = dA * dC - dB * dB;
+      const float mid = 0.5f * (cov.x + cov.z);
+      const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+      const float lmax = mid + sq, lmin = mid - sq;
+      const float cond = lmax / lmin;
+      if (dq > 0.0 && dA > 0.0 && dC > 0.0 && lmin > 0.f && cond < 2.0e5f && cond == cond) {
+        const float t2 = (2.0f * __logf(255.0f * opacity) + 0.04f) / (1.0f - 1.6e-6f * cond);
+        const float sxx = (float)(dC / dq), syy = (float)(dA / dq);
+        ex = sqrtf(t2 * sxx) * 1.0001f + 0.02f;
+        ey = sqrtf(t2 * syy) * 1.0001f + 0.02f;
+      }
+    }
+
+    float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS);
+    rec[0] = make_float4(pix_x, pix_y, ex, ey);
+    rec[1] = make_float4(conA, conB, conC, opacity);
+    rec[2] = make_float4(cr, cg, cb, dist);
+    rec[3] = make_float4(ph[0], ph[1], ph[2], ph[3]);
+    rec[4] = make_float4(ph[4], ph[5], ph[6], ndc);
+    p.depths[idx] = vz;
+    p.clamped[idx] = clamp_bits;
+    reinterpret_cast<float2*>(p.pa)[idx] = make_float2(pa0, pa1);
+    reinterpret_cast<uint2*>(p.rect)[idx] = make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
+  }
+
   // ---- block-wide inclusive scan of `tiles` ------------------------------------------------
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   uint32_t incl = tiles;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -406,7 +428,10 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
-  preprocess_fwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+  const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(preprocess_fwd_kernel, smem, &smem_ok);
+  preprocess_fwd_kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
   note_launches(1);
 }
 

@@ -31,24 +31,19 @@ __device__ __forceinline__ V3 dnormvdv3(V3 v, V3 dv) {
   return o;
 }
 
-// SH backward shared by colour (NC=3) and phasor (NC=2): writes dL_dsh rows [0, ncoef) and zero
-// rows [ncoef, M); returns dL/ddir (before the normalisation Jacobian).
+// SH backward shared by colour (NC=3) and phasor (NC=2) (backward.cu:20-139, 143-260).
+// Reads the coefficient row `sh` first (direction derivative), THEN writes the gradient row `dsh`
+// — rows [0, ncoef) and zeros for rows [ncoef, M) — so `dsh` may alias `sh` (in-place in the
+// warp's shared staging buffer).  Returns dL/ddir before the normalisation Jacobian.
 template <int NC>
-__device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, float z,
-                                          const float* __restrict__ sh, const float* g,
-                                          float* __restrict__ dsh) {
+__device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, float z, const float* sh,
+                                          const float* g, float* dsh) {
   float dx[NC], dy[NC], dz[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) { dx[c] = 0.f; dy[c] = 0.f; dz[c] = 0.f; }
-  auto put = [&](int k, float basis) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = basis * g[c];
-  };
-  put(0, kSH_C0);
+  const float xx = x * x, yy = y * y, zz = z * z;
+  const float xy = x * y, yz = y * z, xz = x * z;
   if (deg > 0) {
-    put(1, -kSH_C1 * y);
-    put(2, kSH_C1 * z);
-    put(3, -kSH_C1 * x);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       dx[c] = -kSH_C1 * sh[3 * NC + c];
@@ -56,13 +51,6 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, floa
       dz[c] = kSH_C1 * sh[2 * NC + c];
     }
     if (deg > 1) {
-      const float xx = x * x, yy = y * y, zz = z * z;
-      const float xy = x * y, yz = y * z, xz = x * z;
-      put(4, kSH_C2_0 * xy);
-      put(5, kSH_C2_1 * yz);
-      put(6, kSH_C2_2 * (2.f * zz - xx - yy));
-      put(7, kSH_C2_3 * xz);
-      put(8, kSH_C2_4 * (xx - yy));
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const float s4 = sh[4 * NC + c], s5 = sh[5 * NC + c], s6 = sh[6 * NC + c],
@@ -74,13 +62,6 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, floa
         dz[c] += kSH_C2_1 * y * s5 + kSH_C2_2 * 2.f * 2.f * z * s6 + kSH_C2_3 * x * s7;
       }
       if (deg > 2) {
-        put(9, kSH_C3_0 * y * (3.f * xx - yy));
-        put(10, kSH_C3_1 * xy * z);
-        put(11, kSH_C3_2 * y * (4.f * zz - xx - yy));
-        put(12, kSH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-        put(13, kSH_C3_4 * x * (4.f * zz - xx - yy));
-        put(14, kSH_C3_5 * z * (xx - yy));
-        put(15, kSH_C3_6 * x * (xx - 3.f * yy));
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const float s9 = sh[9 * NC + c], s10 = sh[10 * NC + c], s11 = sh[11 * NC + c],
@@ -98,6 +79,33 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, floa
                     kSH_C3_3 * s12 * 3.f * (2.f * zz - xx - yy) +
                     kSH_C3_4 * s13 * 4.f * 2.f * xz + kSH_C3_5 * s14 * (xx - yy));
         }
+      }
+    }
+  }
+  // all reads of `sh` are done; now the gradient row
+  auto put = [&](int k, float basis) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = basis * g[c];
+  };
+  put(0, kSH_C0);
+  if (deg > 0) {
+    put(1, -kSH_C1 * y);
+    put(2, kSH_C1 * z);
+    put(3, -kSH_C1 * x);
+    if (deg > 1) {
+      put(4, kSH_C2_0 * xy);
+      put(5, kSH_C2_1 * yz);
+      put(6, kSH_C2_2 * (2.f * zz - xx - yy));
+      put(7, kSH_C2_3 * xz);
+      put(8, kSH_C2_4 * (xx - yy));
+      if (deg > 2) {
+        put(9, kSH_C3_0 * y * (3.f * xx - yy));
+        put(10, kSH_C3_1 * xy * z);
+        put(11, kSH_C3_2 * y * (4.f * zz - xx - yy));
+        put(12, kSH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
+        put(13, kSH_C3_4 * x * (4.f * zz - xx - yy));
+        put(14, kSH_C3_5 * z * (xx - yy));
+        put(15, kSH_C3_6 * x * (xx - 3.f * yy));
       }
     }
   }
@@ -132,17 +140,31 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 
 }  // namespace
 
+// Order of work per Gaussian (the mean gradient is a sum of five parts; they are accumulated in
+// the order SH colour, phasor, depth, cov2D, projection — the reference's order is cov2D,
+// projection, SH colour, phasor, depth; float addition order is the only difference):
+//   1. SH colour backward and 2. phasor + SH(phase, amplitude) backward: the coefficient rows of
+//      the warp's 32 Gaussians are one contiguous chunk, staged through shared memory (coalesced
+//      in), differentiated in place, and streamed out coalesced as dL_dsh / dL_dsh_p;
+//   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation.
 __global__ void __launch_bounds__(GFT_BLOCK)
 preprocess_bwd_kernel(PreprocessBwdParams p) {
+  extern __shared__ float bwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
   __shared__ float s_red[GFT_BLOCK / 32];
   const int idx = blockIdx.x * GFT_BLOCK + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = idx < p.P;
   const bool vis = in_range && (__ldg(p.radii + idx) > 0);
+  float* wbuf = bwd_stage + warp * GFT_STAGE_FLOATS_PER_WARP;
+  const int wfirst = blockIdx.x * GFT_BLOCK + (int)warp * 32;
+  const int nrows = max(0, min(32, p.P - wfirst));
+  const bool any_vis = __any_sync(0xffffffffu, vis);
 
   float part_phase = 0.f, part_dc = 0.f;
 
   if (in_range && !vis) {
-    // culled: every output row is zero (the reference leaves its zero-filled tensors untouched)
+    // culled: every output row is zero (the reference leaves its zero-filled tensors untouched);
+    // the SH gradient rows are zeroed through the staged path below when it is active
     p.dL_dmeans2D[3 * (size_t)idx + 0] = 0.f;
     p.dL_dmeans2D[3 * (size_t)idx + 1] = 0.f;
     p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
@@ -150,34 +172,165 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
     p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
     p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
-    if (p.dL_dsh) for (int k = 0; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * 3 * p.M + k] = 0.f;
-    if (p.dL_dsh_p) for (int k = 0; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * 2 * p.M_p + k] = 0.f;
     if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
     if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = 0.f;
-    if (p.dL_dphasors) for (int k = 0; k < 7; ++k) p.dL_dphasors[7 * (size_t)idx + k] = 0.f;
     if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
     if (p.dL_dconic) for (int k = 0; k < 4; ++k) p.dL_dconic[4 * (size_t)idx + k] = 0.f;
     if (p.dL_ddist) p.dL_ddist[idx] = 0.f;
     if (p.dL_dndc) p.dL_dndc[idx] = 0.f;
   }
 
+  // ---- per-Gaussian inputs kept in registers across the staged sections ----------------------
+  const float* __restrict__ V = p.viewmatrix;
+  const float* __restrict__ proj = p.projmatrix;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  V3 dir_orig = {0.f, 0.f, 0.f};
+  float dirx = 0.f, diry = 0.f, dirz = 0.f;
+  uint32_t clamp_bits = 0;
+  float dmx = 0.f, dmy = 0.f, dmz = 0.f;
   if (vis) {
     const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * GFT_GRAD_FLOATS);
-    const float4 a0 = __ldg(gr + 0), a1 = __ldg(gr + 1), a2 = __ldg(gr + 2), a3 = __ldg(gr + 3),
-                 a4 = __ldg(gr + 4);
-    const float dm2x = a0.x, dm2y = a0.y;
-    const float dcon_x = a0.z, dcon_y = a0.w, dcon_w = a1.x;
-    const float dopac = a1.y;
-    const float dcol[3] = {a1.z, a1.w, a2.x};
-    const float ddist_rec = a2.y, dndc_rec = a2.z;
-    const float dph[7] = {a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y};
+    // record: S_x S_y S_xx S_xy | S_yy opac col.r col.g | col.b dist ndc phA | phB phC phS -
+    a0 = __ldg(gr + 0); a1 = __ldg(gr + 1); a2 = __ldg(gr + 2); a3 = __ldg(gr + 3);
+    mx = __ldg(p.means3D + 3 * (size_t)idx + 0);
+    my = __ldg(p.means3D + 3 * (size_t)idx + 1);
+    mz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+    clamp_bits = __ldg(p.clamped + idx);
+    if (p.shs != nullptr || p.shs_p != nullptr) {
+      dir_orig.x = mx - __ldg(p.campos + 0);
+      dir_orig.y = my - __ldg(p.campos + 1);
+      dir_orig.z = mz - __ldg(p.campos + 2);
+      const float len =
+          sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+      dirx = dir_orig.x / len;
+      diry = dir_orig.y / len;
+      dirz = dir_orig.z / len;
+    }
+  }
+  const float dcol[3] = {a1.z, a1.w, a2.x};
 
-    const float* __restrict__ V = p.viewmatrix;
-    const float* __restrict__ proj = p.projmatrix;
-    const float mx = __ldg(p.means3D + 3 * (size_t)idx + 0);
-    const float my = __ldg(p.means3D + 3 * (size_t)idx + 1);
-    const float mz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+  // ---------------- 1. SH colour backward (backward.cu:20-139) --------------------------------
+  if (p.shs != nullptr) {
+    const bool staged = p.M == 16;
+    if (staged && any_vis) {
+      warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
+      __syncwarp();
+    }
+    if (vis) {
+      float g[3] = {dcol[0], dcol[1], dcol[2]};
+      g[0] *= (clamp_bits & 0x1u) ? 0.f : 1.f;
+      g[1] *= (clamp_bits & 0x100u) ? 0.f : 1.f;
+      g[2] *= (clamp_bits & 0x10000u) ? 0.f : 1.f;
+      V3 dL_ddir;
+      if (staged) {
+        float* row = wbuf + lane * 49;
+        dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, row, g, row);
+      } else {
+        dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g,
+                                 p.dL_dsh + (size_t)idx * p.M * 3);
+      }
+      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
+      dmx += dm.x; dmy += dm.y; dmz += dm.z;
+    } else if (in_range) {
+      if (staged) {
+        if (any_vis) for (int k = 0; k < 48; ++k) wbuf[lane * 49 + k] = 0.f;
+      } else {
+        for (int k = 0; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * 3 * p.M + k] = 0.f;
+      }
+    }
+    if (staged) {
+      if (any_vis) {
+        __syncwarp();
+        warp_stage_out<48>(p.dL_dsh + (size_t)wfirst * 48, nrows, wbuf, lane);
+        __syncwarp();
+      } else {
+        for (int e = (int)lane; e < nrows * 48; e += 32) p.dL_dsh[(size_t)wfirst * 48 + e] = 0.f;
+      }
+    }
+  }
+
+  // ---------------- 2. phasor backward (backward.cu:525-587) ----------------------------------
+  float dist = 0.f, m_view_x = 0.f, m_view_y = 0.f, m_view_z = 0.f;
+  if (vis) {
+    dist = __ldg(p.rec + (size_t)idx * GFT_REC_FLOATS + 11);
+    m_view_x = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+    m_view_y = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+    m_view_z = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+  }
+  if (p.shs_p != nullptr) {
+    const bool staged = p.M_p == 16;
+    if (staged && any_vis) {
+      warp_stage_in<32>(p.shs_p + (size_t)wfirst * 32, nrows, wbuf, lane);
+      __syncwarp();
+    }
+    if (vis) {
+      const float phA = a2.w, phB = a3.x, phC = a3.y, phS = a3.z;
+      const float2 pa = __ldg(reinterpret_cast<const float2*>(p.pa) + idx);
+      float phase = dist * p.dist2phase + p.phase_offset;
+      if (p.use_view_dependent_phase) phase += pa.x;
+      const float amplitude = pa.y;
+      const float factor = 1.0f / (dist * dist);
+      float sin_p, cos_p;
+      sincosf(phase, &sin_p, &cos_p);
+      const float dc = p.dc_offset;
+      // phA = dR+dq1-dq2, phB = dI+dq3-dq4, phC = dA, phS = dq1+dq2+dq3+dq4 (summed in blend_bwd)
+      const float dphase_sum = cos_p * phB - sin_p * phA;                // backward.cu:551-559
+      const float damp_sum = cos_p * phA + sin_p * phB + phC + dc * phS;  // backward.cu:562-566
+      float gpa[2] = {0.f, 0.f};
+      if (p.use_view_dependent_phase) gpa[0] = dphase_sum * amplitude * factor;
+      part_phase = dphase_sum * amplitude * factor;
+      gpa[1] = damp_sum * factor;
+      part_dc = phS * amplitude * factor;                                 // backward.cu:567
+      const float coeff = dphase_sum * p.dist2phase * amplitude * factor / dist -
+                          damp_sum * 2.0f * amplitude * factor * factor;  // backward.cu:570-577
+      const float dxv = m_view_x * coeff, dyv = m_view_y * coeff, dzv = m_view_z * coeff;
+      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
+      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
+      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
+
+      // computePhasorFromSH backward.  The reference reads its 2-float local gradient array with
+      // the Gaussian index (backward.cu:154,586; DESIGN.md defect D1); the evident intent — the
+      // array's own two entries — is what is implemented.  No special case for the removed phase
+      // DC term.
+      gpa[1] *= (clamp_bits & 0x1000000u) ? 0.f : 1.f;
+      V3 dL_ddir;
+      if (staged) {
+        float* row = wbuf + lane * 33;
+        dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, row, gpa, row);
+      } else {
+        dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2,
+                                 gpa, p.dL_dsh_p + (size_t)idx * p.M_p * 2);
+      }
+      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
+      dmx += dm.x; dmy += dm.y; dmz += dm.z;
+    } else if (in_range) {
+      if (staged) {
+        if (any_vis) for (int k = 0; k < 32; ++k) wbuf[lane * 33 + k] = 0.f;
+      } else {
+        for (int k = 0; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * 2 * p.M_p + k] = 0.f;
+      }
+    }
+    if (staged) {
+      if (any_vis) {
+        __syncwarp();
+        warp_stage_out<32>(p.dL_dsh_p + (size_t)wfirst * 32, nrows, wbuf, lane);
+        __syncwarp();
+      } else {
+        for (int e = (int)lane; e < nrows * 32; e += 32) p.dL_dsh_p[(size_t)wfirst * 32 + e] = 0.f;
+      }
+    }
+  }
+
+  if (vis) {
+    const float4 co = __ldg(reinterpret_cast<const float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS) + 1);
+    // backward.cu:872-883 with the per-Gaussian conic factors pulled out of the pixel sums
+    const float dm2x = -(co.x * a0.x + co.y * a0.y) * (0.5f * (float)p.W);
+    const float dm2y = -(co.z * a0.y + co.y * a0.x) * (0.5f * (float)p.H);
+    const float dcon_x = -0.5f * a0.z, dcon_y = -0.5f * a0.w, dcon_w = -0.5f * a1.x;
+    const float dopac = a1.y;
+    const float ddist_rec = a2.y, dndc_rec = a2.z;
 
     // pass-through outputs
     p.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
@@ -185,21 +338,30 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
     p.dL_dopacity[idx] = dopac;
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol[k];
-    if (p.dL_dphasors) for (int k = 0; k < 7; ++k) p.dL_dphasors[7 * (size_t)idx + k] = dph[k];
     if (p.dL_dconic) {
       reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
     }
     if (p.dL_ddist) p.dL_ddist[idx] = ddist_rec;
     if (p.dL_dndc) p.dL_dndc[idx] = dndc_rec;
 
-    // ---------------- cov2D backward (backward.cu:276-394) -----------------------------------
+    // ---------------- 3. depth / ndc -> mean (backward.cu:589-601) ---------------------------
+    {
+      const float dndc_ddist = (p.far_n * p.near_n) / ((p.far_n - p.near_n) * dist * dist);
+      const float dL_ddist = dndc_rec * dndc_ddist + ddist_rec;
+      const float dxv = dL_ddist * m_view_x / dist;
+      const float dyv = dL_ddist * m_view_y / dist;
+      const float dzv = dL_ddist * m_view_z / dist;
+      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
+      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
+      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
+    }
+
+    // ---------------- cov2D backward (4., backward.cu:276-394) ------------------------------
     const float* c3 = p.cov3D + 6 * (size_t)idx;
     const float v0 = __ldg(c3 + 0), v1 = __ldg(c3 + 1), v2 = __ldg(c3 + 2), v3 = __ldg(c3 + 3),
                 v4 = __ldg(c3 + 4), v5 = __ldg(c3 + 5);
-    float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
-    float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
-    const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
-    const float m_view_x = tx, m_view_y = ty, m_view_z = tz;
+    float tx = m_view_x, ty = m_view_y;
+    const float tz = m_view_z;
     const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
     const float txtz = tx / tz, tytz = ty / tz;
     tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
@@ -264,9 +426,9 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     const float dL_dtz = -h_x * itz2 * dL_dJ00 - h_y * itz2 * dL_dJ11 +
                          (2 * h_x * tx) * itz3 * dL_dJ02 + (2 * h_y * ty) * itz3 * dL_dJ12;
     // transformVec4x3Transpose (auxiliary.h:91-100)
-    float dmx = V[0] * dL_dtx + V[1] * dL_dty + V[2] * dL_dtz;
-    float dmy = V[4] * dL_dtx + V[5] * dL_dty + V[6] * dL_dtz;
-    float dmz = V[8] * dL_dtx + V[9] * dL_dty + V[10] * dL_dtz;
+    dmx += V[0] * dL_dtx + V[1] * dL_dty + V[2] * dL_dtz;
+    dmy += V[4] * dL_dtx + V[5] * dL_dty + V[6] * dL_dtz;
+    dmz += V[8] * dL_dtx + V[9] * dL_dty + V[10] * dL_dtz;
 
     // ---------------- mean2D -> mean3D (backward.cu:498-519) ---------------------------------
     {
@@ -279,84 +441,6 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dmz += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
     }
 
-    // ---------------- view direction ---------------------------------------------------------
-    V3 dir_orig = {0.f, 0.f, 0.f};
-    float dirx = 0.f, diry = 0.f, dirz = 0.f;
-    if (p.shs != nullptr || p.shs_p != nullptr) {
-      dir_orig.x = mx - __ldg(p.campos + 0);
-      dir_orig.y = my - __ldg(p.campos + 1);
-      dir_orig.z = mz - __ldg(p.campos + 2);
-      const float len =
-          sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-      dirx = dir_orig.x / len;
-      diry = dir_orig.y / len;
-      dirz = dir_orig.z / len;
-    }
-    const uint32_t clamp_bits = __ldg(p.clamped + idx);
-
-    // ---------------- SH colour backward (backward.cu:20-139) --------------------------------
-    if (p.shs != nullptr) {
-      float g[3] = {dcol[0], dcol[1], dcol[2]};
-      g[0] *= (clamp_bits & 0x1u) ? 0.f : 1.f;
-      g[1] *= (clamp_bits & 0x100u) ? 0.f : 1.f;
-      g[2] *= (clamp_bits & 0x10000u) ? 0.f : 1.f;
-      const float* sh = p.shs + (size_t)idx * p.M * 3;
-      float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
-      const V3 dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, sh, g, dsh);
-      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
-      dmx += dm.x; dmy += dm.y; dmz += dm.z;
-    }
-
-    // ---------------- phasor backward (backward.cu:525-587) ----------------------------------
-    const float dist = __ldg(p.rec + (size_t)idx * GFT_REC_FLOATS + 11);
-    if (p.shs_p != nullptr) {
-      const float2 pa = __ldg(reinterpret_cast<const float2*>(p.pa) + idx);
-      float phase = dist * p.dist2phase + p.phase_offset;
-      if (p.use_view_dependent_phase) phase += pa.x;
-      const float amplitude = pa.y;
-      const float factor = 1.0f / (dist * dist);
-      const float dL_dR = dph[0], dL_dI = dph[1], dL_dA = dph[2];
-      const float dq1 = dph[3], dq2 = dph[4], dq3 = dph[5], dq4 = dph[6];
-      float sin_p, cos_p;
-      sincosf(phase, &sin_p, &cos_p);
-      const float dc = p.dc_offset;
-      const float dphase_sum = dL_dR * -sin_p + dL_dI * cos_p + dq1 * -sin_p + dq2 * sin_p +
-                               dq3 * cos_p + dq4 * -cos_p;
-      float gpa[2] = {0.f, 0.f};
-      if (p.use_view_dependent_phase) gpa[0] = dphase_sum * amplitude * factor;
-      part_phase = dphase_sum * amplitude * factor;
-      gpa[1] = (dL_dR * cos_p + dL_dI * sin_p + dL_dA + dq1 * (cos_p + dc) + dq2 * (-cos_p + dc) +
-                dq3 * (sin_p + dc) + dq4 * (-sin_p + dc)) * factor;
-      part_dc = (dq1 + dq2 + dq3 + dq4) * amplitude * factor;
-      const float coeff =
-          dphase_sum * p.dist2phase * amplitude * factor / dist +
-          (dL_dR * -cos_p + dL_dI * -sin_p - dL_dA + dq1 * -(cos_p + dc) + dq2 * (cos_p - dc) +
-           dq3 * -(sin_p + dc) + dq4 * (sin_p - dc)) * 2.0f * amplitude * factor * factor;
-      const float dxv = m_view_x * coeff, dyv = m_view_y * coeff, dzv = m_view_z * coeff;
-      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
-      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
-      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
-
-      // computePhasorFromSH backward (no special case for the removed phase DC: SURVEY A.5)
-      gpa[1] *= (clamp_bits & 0x1000000u) ? 0.f : 1.f;
-      const float* shp = p.shs_p + (size_t)idx * p.M_p * 2;
-      float* dshp = p.dL_dsh_p + (size_t)idx * p.M_p * 2;
-      const V3 dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, shp, gpa, dshp);
-      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
-      dmx += dm.x; dmy += dm.y; dmz += dm.z;
-    }
-
-    // ---------------- depth / ndc -> mean (backward.cu:589-601) ------------------------------
-    {
-      const float dndc_ddist = (p.far_n * p.near_n) / ((p.far_n - p.near_n) * dist * dist);
-      const float dL_ddist = dndc_rec * dndc_ddist + ddist_rec;
-      const float dxv = dL_ddist * m_view_x / dist;
-      const float dyv = dL_ddist * m_view_y / dist;
-      const float dzv = dL_ddist * m_view_z / dist;
-      dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
-      dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
-      dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
-    }
     p.dL_dmeans3D[3 * (size_t)idx + 0] = dmx;
     p.dL_dmeans3D[3 * (size_t)idx + 1] = dmy;
     p.dL_dmeans3D[3 * (size_t)idx + 2] = dmz;
@@ -430,7 +514,10 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
   note_launches(1);
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
-  preprocess_bwd_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(p);
+  const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(preprocess_bwd_kernel, smem, &smem_ok);
+  preprocess_bwd_kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
   note_launches(1);
 }
 

@@ -247,9 +247,8 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
   rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
   note_launches(2 + npass);
 
-  // per-device attribute; cheap enough to set on every call (keeps the library state-free)
-  cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)sizeof(RsSmem));
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(rs_onesweep_kernel, (int)sizeof(RsSmem), &smem_ok);
   uint64_t* kin = keys_a; uint64_t* kout = keys_b;
   uint32_t* vin = vals_a; uint32_t* vout = vals_b;
   for (int p = 0; p < npass; ++p) {

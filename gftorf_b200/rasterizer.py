@@ -217,7 +217,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
 
     # One flat allocation for every gradient + the scratch records.  Nothing needs a zero fill
     # except the scratch, which the library clears itself.
-    sizes = [("means3D", 3 * P), ("means2D", 3 * P), ("colors", 3 * P), ("phasors", 7 * P),
+    sizes = [("means3D", 3 * P), ("means2D", 3 * P), ("colors", 3 * P),
              ("opacity", P), ("cov3D", 6 * P), ("sh", 3 * M * P), ("sh_p", 2 * M_p * P),
              ("scales", 3 * P), ("rot", 4 * P), ("phase_offset", 1), ("dc_offset", 1)]
     scratch_floats = lib.gft_backward_scratch_bytes(P) // 4
@@ -234,7 +234,9 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
         return flat[o:o + n].view(*shape)
 
     dL_dmeans3D, dL_dmeans2D = view("means3D", P, 3), view("means2D", P, 3)
-    dL_dcolors, dL_dphasors = view("colors", P, 3), view("phasors", P, 7)
+    dL_dcolors = view("colors", P, 3)
+    # grad_phasors_precomp ([P,7] for a [P,2] input in the reference) is not produced
+    dL_dphasors = None
     dL_dopacity, dL_dcov3D = view("opacity", P, 1), view("cov3D", P, 6)
     dL_dsh, dL_dsh_p = view("sh", P, M, 3), view("sh_p", P, M_p, 2)
     dL_dscales, dL_drotations = view("scales", P, 3), view("rot", P, 4)
@@ -273,7 +275,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     a.dL_dscales = _ptr(dL_dscales) if have_scales else None
     a.dL_drotations = _ptr(dL_drotations) if have_scales else None
     a.dL_dphase_offset, a.dL_ddc_offset = dL_dphase_offset.data_ptr(), dL_ddc_offset.data_ptr()
-    a.dL_dcolors, a.dL_dphasors, a.dL_dcov3D = _ptr(dL_dcolors), _ptr(dL_dphasors), _ptr(dL_dcov3D)
+    a.dL_dcolors, a.dL_dphasors, a.dL_dcov3D = _ptr(dL_dcolors), None, _ptr(dL_dcov3D)
     a.dL_dconic = a.dL_ddist = a.dL_dndc = None
     a.scratch = flat[scratch_off:].data_ptr()
     a.debug = int(bool(debug))

@@ -159,7 +159,9 @@ typedef struct GftBackwardArgs {
   /* Optional intermediates (reference materialises them always, rasterize_points.cu:222-236);
    * NULL = keep in registers only: */
   float* dL_dcolors;        /* [P,3]  grad of colors_precomp */
-  float* dL_dphasors;       /* [P,7] */
+  float* dL_dphasors;       /* [P,7]  REFERENCE-ONLY: must be NULL for gft_backward (the blend
+                               backward reduces the 7 phasor gradients to the 4 combinations the
+                               phasor backward consumes); used by the oracle shim */
   float* dL_dcov3D;         /* [P,6]  grad of cov3D_precomp */
   float* dL_dconic;         /* [P,4]  (x, y, unused, w) as the reference's [P,2,2] */
   float* dL_ddist;          /* [P] */

@@ -79,20 +79,24 @@ struct State {  // what the reference keeps in its geometry / binning / image bu
 
 thread_local std::string g_err;
 
-// SH basis values multiplying coefficients 1..15 for unit direction (x,y,z)
+// SH basis values multiplying coefficients 1..15 for unit direction (x,y,z), forward.cu:37-59 in
+// the reference binary's dataflow (SASS): products rounded, except the fused polynomial terms
+// 3xx-yy, 2zz-3xx-3yy and xx-3yy.
 void sh_basis(int deg, float x, float y, float z, float* b) {
   if (deg < 1) return;
-  b[1] = -C1 * y; b[2] = C1 * z; b[3] = -C1 * x;
+  b[1] = -(C1 * y); b[2] = C1 * z; b[3] = -(C1 * x);
   if (deg < 2) return;
   const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  b[4] = C2[0] * xy; b[5] = C2[1] * yz; b[6] = C2[2] * (2.0f * zz - xx - yy);
-  b[7] = C2[3] * xz; b[8] = C2[4] * (xx - yy);
+  const float zz2 = zz + zz, xx_yy = xx - yy;
+  b[4] = xy * C2[0]; b[5] = yz * C2[1]; b[6] = ((zz2 - xx) - yy) * C2[2];
+  b[7] = xz * C2[3]; b[8] = xx_yy * C2[4];
   if (deg < 3) return;
-  b[9] = C3[0] * y * (3.0f * xx - yy); b[10] = C3[1] * xy * z;
-  b[11] = C3[2] * y * (4.0f * zz - xx - yy);
-  b[12] = C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-  b[13] = C3[4] * x * (4.0f * zz - xx - yy); b[14] = C3[5] * z * (xx - yy);
-  b[15] = C3[6] * x * (xx - 3.0f * yy);
+  const float t11 = fmaf(zz, 4.f, -xx) - yy;
+  b[9] = (y * C3[0]) * fmaf(xx, 3.f, -yy); b[10] = (xy * C3[1]) * z;
+  b[11] = (y * C3[2]) * t11;
+  b[12] = (z * C3[3]) * fmaf(yy, -3.f, fmaf(xx, -3.f, zz2));
+  b[13] = t11 * (x * C3[4]); b[14] = xx_yy * (z * C3[5]);
+  b[15] = (x * C3[6]) * fmaf(yy, -3.f, xx);
 }
 
 struct Tm { float T00, T01, T02, T10, T11, T12; };
@@ -209,7 +213,7 @@ void preprocess_one(const GftForwardArgs& a, State& s, int i, float fx, float fy
   float dx = 0, dy = 0, dz = 0;
   if (a.shs || a.shs_p) {
     dx = px - a.campos[0]; dy = py - a.campos[1]; dz = pz - a.campos[2];
-    const float len = std::sqrt(dx * dx + dy * dy + dz * dz);
+    const float len = std::sqrt(dot3(dx, dx, dy, dy, dz, dz));
     dx /= len; dy /= len; dz /= len;
     sh_basis(a.sh_degree, dx, dy, dz, basis);
   }
@@ -220,14 +224,14 @@ void preprocess_one(const GftForwardArgs& a, State& s, int i, float fx, float fy
     const float* sh = a.shs + (size_t)i * a.M * 3;
     for (int c = 0; c < 3; ++c) {
       float r = C0 * sh[c];
-      for (int k = 1; k < nco; ++k) r += basis[k] * sh[3 * k + c];
+      for (int k = 1; k < nco; ++k) r = fmaf(basis[k], sh[3 * k + c], r);
       r += 0.5f;
       s.clamped[3 * (size_t)i + c] = r < 0.f;
       rgb[c] = std::fmax(r, 0.f);
     }
   }
-  const float dist = std::sqrt(vx * vx + vy * vy + vz * vz);
-  const float ndc = a.far_n / (a.far_n - a.near_n) * (1 - a.near_n / dist);
+  const float dist = std::sqrt(dot3(vx, vx, vy, vy, vz, vz));  // SASS: y^2 rounded, x^2, z^2 fused
+  const float ndc = (1.f - a.near_n / dist) * (a.far_n / (a.far_n - a.near_n));
   const float factor = 1.0f / (dist * dist);
   float* ria = &s.ria[7 * (size_t)i];
   for (int c = 0; c < 7; ++c) ria[c] = 0.f;  // uninitialised in the reference when no phasor input
@@ -243,13 +247,13 @@ void preprocess_one(const GftForwardArgs& a, State& s, int i, float fx, float fy
   if (a.shs_p) {  // forward.cu:73-125, 389-407
     const float* sp = a.shs_p + (size_t)i * a.M_p * 2;
     float q0 = C0 * sp[0], q1 = C0 * sp[1];
-    for (int k = 1; k < nco; ++k) { q0 += basis[k] * sp[2 * k]; q1 += basis[k] * sp[2 * k + 1]; }
-    q0 += 0.5f; q1 += 0.5f;
-    q0 = q0 - 0.5f - C0 * sp[0];
+    for (int k = 1; k < nco; ++k) { q0 = fmaf(basis[k], sp[2 * k], q0); q1 = fmaf(basis[k], sp[2 * k + 1], q1); }
+    q1 += 0.5f;
+    q0 = ((q0 + 0.5f) - 0.5f) - C0 * sp[0];
     s.clamped_p[i] = q1 < 0.f;
     if (q1 < 0.f) q1 = 0.f;
     s.pa[2 * (size_t)i] = q0; s.pa[2 * (size_t)i + 1] = q1;
-    phase = dist * d2p + a.phase_offset;
+    phase = fmaf(dist, d2p, a.phase_offset);
     if (a.use_view_dependent_phase) phase += q0;
     amp = q1; have = true;
   }
