@@ -188,26 +188,29 @@ def run_gpu(args, impl):
     P = wl["P"]
     npix = sum(v["W"] * v["H"] for v in views)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    bucket_flat = torch.zeros(P * parallel.FLOATS_PER_GAUSSIAN + 4, dtype=torch.float32, device=dev)
-
-    def accumulate(b):
-        # gradients of the two views add (autograd's AccumulateGrad in the reference's training loop)
-        o = 0
-        for t in (b[4], b[6], b[7], b[3], b[8], b[9]):
-            n = t.numel()
-            bucket_flat[o:o + n] += t.reshape(-1)
-            o += n
+    # the flat gradient bucket [P*91 + 2 scalars]; the backward adds each view's gradients into it
+    scal = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
+    bucket = parallel.GradBucket(params, scal)
+    grad_out = bucket.grad_out() if impl == "ours" else None
+    bucket_views = dict(zip(bucket.names, bucket.views()[:len(bucket.names)]))
 
     def step_resident():
-        bucket_flat.zero_()
+        bucket.zero()
         stats = []
         for v in views:
             f = mod.rasterize_gaussians(*fwd_args(params, v, empty))
-            b = mod.rasterize_gaussians_backward(*bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]))
-            accumulate(b)
+            if impl == "ours":
+                mod.rasterize_gaussians_backward(
+                    *bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]), grad_out=grad_out)
+            else:
+                # the reference's gradients of the two views add in autograd's AccumulateGrad
+                b = mod.rasterize_gaussians_backward(*bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]))
+                for name, t in (("means3D", b[4]), ("shs", b[6]), ("shs_p", b[7]), ("opacities", b[3]),
+                                ("scales", b[8]), ("rotations", b[9])):
+                    bucket_views[name] += t
             stats.append((f[0], f[11]))
         if world > 1:
-            dist.all_reduce(bucket_flat)
+            bucket.allreduce()
         return stats
 
     # ---- e2e: public autograd surface, host buffers --------------------------------------------
@@ -233,25 +236,45 @@ def run_gpu(args, impl):
         # ref_driver, so the e2e arm drives forward/backward explicitly with the same copies
         Settings = Raster = None
 
+    # persistent device-side staging (what an application keeps): the H2D copies land in these
+    dev_params = {k: torch.empty_like(params[k]) for k in names}
+    dev_bg = torch.empty_like(views[0]["bg"])
+    dev_views = []
+    for v in views:
+        dv = {k: torch.empty_like(v[k]) for k in ("viewmatrix", "projmatrix", "campos")}
+        dv["grads"] = {k: torch.empty_like(g) for k, g in v["grads"].items()}
+        dev_views.append(dv)
+    if impl == "ours":
+        for k in names:
+            dev_params[k].requires_grad_(True)
+        dev_m2d = torch.zeros_like(params["means3D"], requires_grad=True)
+
     def step_e2e():
-        dp = {k: host_params[k].to(dev, non_blocking=True) for k in names}
-        bg = host_bg.to(dev, non_blocking=True)
+        with torch.no_grad():
+            for k in names:
+                dev_params[k].copy_(host_params[k], non_blocking=True)
+            dev_bg.copy_(host_bg, non_blocking=True)
+            for hv, dv in zip(host_views, dev_views):
+                for k in ("viewmatrix", "projmatrix", "campos"):
+                    dv[k].copy_(hv[k], non_blocking=True)
+                for k, t in hv["grads"].items():
+                    dv["grads"][k].copy_(t, non_blocking=True)
+        dp, bg = dev_params, dev_bg
         acc = None
-        for v, hv, himg in zip(views, host_views, host_imgs):
-            vm = hv["viewmatrix"].to(dev, non_blocking=True)
-            pm = hv["projmatrix"].to(dev, non_blocking=True)
-            cp = hv["campos"].to(dev, non_blocking=True)
-            g = {k: t.to(dev, non_blocking=True) for k, t in hv["grads"].items()}
+        if impl == "ours":
+            for k in names:
+                dp[k].grad = None
+            dev_m2d.grad = None
+        for v, dv, himg in zip(views, dev_views, host_imgs):
+            vm, pm, cp, g = dv["viewmatrix"], dv["projmatrix"], dv["campos"], dv["grads"]
             if impl == "ours":
-                leaves = {k: dp[k].requires_grad_(True) for k in names}
-                m2d = torch.zeros_like(dp["means3D"], requires_grad=True)
                 s = Settings(image_height=v["H"], image_width=v["W"], tanfovx=v["tanfovx"],
                              tanfovy=v["tanfovy"], bg=bg, scale_modifier=1.0, viewmatrix=vm,
                              projmatrix=pm, sh_degree=3, campos=cp, prefiltered=False, debug=False,
                              near_n=v["near_n"], far_n=v["far_n"], depth_range=v["depth_range"])
-                out = Raster(s)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
-                                shs=leaves["shs"], shs_p=leaves["shs_p"], scales=leaves["scales"],
-                                rotations=leaves["rotations"])
+                out = Raster(s)(means3D=dp["means3D"], means2D=dev_m2d, opacities=dp["opacities"],
+                                shs=dp["shs"], shs_p=dp["shs_p"], scales=dp["scales"],
+                                rotations=dp["rotations"])
                 torch.autograd.backward(
                     [out[0], out[1], out[2], out[4], out[6]],
                     [g["color"], g["phasor"], g["depth"], g["acc"], g["depth_distortion"]])

@@ -64,6 +64,7 @@ class GftBackwardArgs(C.Structure):
         ("near_n", C.c_float), ("far_n", C.c_float), ("depth_range", C.c_float),
         ("use_view_dependent_phase", C.c_int),
         ("phase_offset", C.c_float), ("dc_offset", C.c_float),
+        ("accumulate", C.c_int),
     ]
 
 

@@ -348,8 +348,10 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   if (!a->dL_dphase_offset || !a->dL_ddc_offset)
     return fail(-1, "gft_backward: dL_dphase_offset / dL_ddc_offset are required");
   if (P == 0) {  // rasterize_points.cu:238
-    cudaMemsetAsync(a->dL_dphase_offset, 0, 4, stream);
-    cudaMemsetAsync(a->dL_ddc_offset, 0, 4, stream);
+    if (!a->accumulate) {
+      cudaMemsetAsync(a->dL_dphase_offset, 0, 4, stream);
+      cudaMemsetAsync(a->dL_ddc_offset, 0, 4, stream);
+    }
     GFT_CUDA_OK("backward(P=0)");
     return 0;
   }
@@ -418,6 +420,7 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   pb.dist2phase = 4.0f * GFT_PI_F / a->depth_range;  // backward.cu:936
   pb.use_view_dependent_phase = a->use_view_dependent_phase;
   pb.phase_offset = a->phase_offset; pb.dc_offset = a->dc_offset;
+  pb.accumulate = a->accumulate;
   pb.dL_dmeans2D = a->dL_dmeans2D; pb.dL_dopacity = a->dL_dopacity;
   pb.dL_dmeans3D = a->dL_dmeans3D; pb.dL_dsh = a->dL_dsh; pb.dL_dsh_p = a->dL_dsh_p;
   pb.dL_dscales = a->dL_dscales; pb.dL_drotations = a->dL_drotations;

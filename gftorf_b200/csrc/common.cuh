@@ -200,14 +200,15 @@ __device__ __forceinline__ void warp_stage_in(const float* __restrict__ gbase, i
     sbuf[r * (ROW + 1) + c] = __ldg(gbase + e);
   }
 }
-template <int ROW>
+template <int ROW, bool ACC = false>
 __device__ __forceinline__ void warp_stage_out(float* __restrict__ gbase, int nrows,
                                                const float* sbuf, uint32_t lane) {
   const int total = nrows * ROW;
 #pragma unroll 4
   for (int e = (int)lane; e < total; e += 32) {
     const int r = e / ROW, c = e - r * ROW;
-    gbase[e] = sbuf[r * (ROW + 1) + c];
+    if (ACC) gbase[e] += sbuf[r * (ROW + 1) + c];
+    else gbase[e] = sbuf[r * (ROW + 1) + c];
   }
 }
 #define GFT_STAGE_FLOATS_PER_WARP (32 * 49)

@@ -140,6 +140,7 @@ struct PreprocessBwdParams {
   float near_n, far_n, dist2phase;
   int use_view_dependent_phase;
   float phase_offset, dc_offset;
+  int accumulate;  // add into the parameter gradients instead of overwriting
   // outputs
   float* dL_dmeans2D;
   float* dL_dopacity;

@@ -147,8 +147,13 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 //      the warp's 32 Gaussians are one contiguous chunk, staged through shared memory (coalesced
 //      in), differentiated in place, and streamed out coalesced as dL_dsh / dL_dsh_p;
 //   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation.
+template <bool ACC>
 __global__ void __launch_bounds__(GFT_BLOCK)
 preprocess_bwd_kernel(PreprocessBwdParams p) {
+  // ACC: add into the six parameter-gradient outputs (means3D, sh, sh_p, opacity, scales,
+  // rotations) and the two scalar offsets instead of overwriting them — several views then
+  // accumulate straight into one gradient bucket, and culled Gaussians cost no gradient traffic.
+  // Per-view outputs (means2D and the optional intermediates) are always overwritten.
   extern __shared__ float bwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
   __shared__ float s_red[GFT_BLOCK / 32];
   const int idx = blockIdx.x * GFT_BLOCK + threadIdx.x;
@@ -168,12 +173,14 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     p.dL_dmeans2D[3 * (size_t)idx + 0] = 0.f;
     p.dL_dmeans2D[3 * (size_t)idx + 1] = 0.f;
     p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    p.dL_dopacity[idx] = 0.f;
-    p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
-    p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
-    p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
-    if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
-    if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
+    if (!ACC) {
+      p.dL_dopacity[idx] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
+      if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
+      if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
+    }
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = 0.f;
     if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
     if (p.dL_dconic) for (int k = 0; k < 4; ++k) p.dL_dconic[4 * (size_t)idx + k] = 0.f;
@@ -227,25 +234,30 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       if (staged) {
         float* row = wbuf + lane * 49;
         dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, row, g, row);
-      } else {
+      } else if (!ACC) {
         dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g,
                                  p.dL_dsh + (size_t)idx * p.M * 3);
+      } else {
+        float tmp[48];
+        dL_ddir = sh_backward<3>(p.D, min(p.M, 16), dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g, tmp);
+        const int ncf = 3 * (p.D + 1) * (p.D + 1);
+        for (int k = 0; k < ncf; ++k) p.dL_dsh[(size_t)idx * p.M * 3 + k] += tmp[k];
       }
       const V3 dm = dnormvdv3(dir_orig, dL_ddir);
       dmx += dm.x; dmy += dm.y; dmz += dm.z;
     } else if (in_range) {
       if (staged) {
         if (any_vis) for (int k = 0; k < 48; ++k) wbuf[lane * 49 + k] = 0.f;
-      } else {
+      } else if (!ACC) {
         for (int k = 0; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * 3 * p.M + k] = 0.f;
       }
     }
     if (staged) {
       if (any_vis) {
         __syncwarp();
-        warp_stage_out<48>(p.dL_dsh + (size_t)wfirst * 48, nrows, wbuf, lane);
+        warp_stage_out<48, ACC>(p.dL_dsh + (size_t)wfirst * 48, nrows, wbuf, lane);
         __syncwarp();
-      } else {
+      } else if (!ACC) {
         for (int e = (int)lane; e < nrows * 48; e += 32) p.dL_dsh[(size_t)wfirst * 48 + e] = 0.f;
       }
     }
@@ -299,25 +311,30 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       if (staged) {
         float* row = wbuf + lane * 33;
         dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, row, gpa, row);
-      } else {
+      } else if (!ACC) {
         dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2,
                                  gpa, p.dL_dsh_p + (size_t)idx * p.M_p * 2);
+      } else {
+        float tmp[32];
+        dL_ddir = sh_backward<2>(p.D, min(p.M_p, 16), dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2, gpa, tmp);
+        const int ncf = 2 * (p.D + 1) * (p.D + 1);
+        for (int k = 0; k < ncf; ++k) p.dL_dsh_p[(size_t)idx * p.M_p * 2 + k] += tmp[k];
       }
       const V3 dm = dnormvdv3(dir_orig, dL_ddir);
       dmx += dm.x; dmy += dm.y; dmz += dm.z;
     } else if (in_range) {
       if (staged) {
         if (any_vis) for (int k = 0; k < 32; ++k) wbuf[lane * 33 + k] = 0.f;
-      } else {
+      } else if (!ACC) {
         for (int k = 0; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * 2 * p.M_p + k] = 0.f;
       }
     }
     if (staged) {
       if (any_vis) {
         __syncwarp();
-        warp_stage_out<32>(p.dL_dsh_p + (size_t)wfirst * 32, nrows, wbuf, lane);
+        warp_stage_out<32, ACC>(p.dL_dsh_p + (size_t)wfirst * 32, nrows, wbuf, lane);
         __syncwarp();
-      } else {
+      } else if (!ACC) {
         for (int e = (int)lane; e < nrows * 32; e += 32) p.dL_dsh_p[(size_t)wfirst * 32 + e] = 0.f;
       }
     }
@@ -336,7 +353,7 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     p.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
     p.dL_dmeans2D[3 * (size_t)idx + 1] = dm2y;
     p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    p.dL_dopacity[idx] = dopac;
+    if (ACC) p.dL_dopacity[idx] += dopac; else p.dL_dopacity[idx] = dopac;
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol[k];
     if (p.dL_dconic) {
       reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
@@ -441,9 +458,15 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dmz += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
     }
 
-    p.dL_dmeans3D[3 * (size_t)idx + 0] = dmx;
-    p.dL_dmeans3D[3 * (size_t)idx + 1] = dmy;
-    p.dL_dmeans3D[3 * (size_t)idx + 2] = dmz;
+    if (ACC) {
+      p.dL_dmeans3D[3 * (size_t)idx + 0] += dmx;
+      p.dL_dmeans3D[3 * (size_t)idx + 1] += dmy;
+      p.dL_dmeans3D[3 * (size_t)idx + 2] += dmz;
+    } else {
+      p.dL_dmeans3D[3 * (size_t)idx + 0] = dmx;
+      p.dL_dmeans3D[3 * (size_t)idx + 1] = dmy;
+      p.dL_dmeans3D[3 * (size_t)idx + 2] = dmz;
+    }
 
     // ---------------- cov3D -> scale, rotation (backward.cu:399-462) -------------------------
     if (p.scales != nullptr) {
@@ -477,9 +500,15 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       const float ds_x = R00 * D00 + R10 * D10 + R20 * D20;
       const float ds_y = R01 * D01 + R11 * D11 + R21 * D21;
       const float ds_z = R02 * D02 + R12 * D12 + R22 * D22;
-      p.dL_dscales[3 * (size_t)idx + 0] = ds_x;
-      p.dL_dscales[3 * (size_t)idx + 1] = ds_y;
-      p.dL_dscales[3 * (size_t)idx + 2] = ds_z;
+      if (ACC) {
+        p.dL_dscales[3 * (size_t)idx + 0] += ds_x;
+        p.dL_dscales[3 * (size_t)idx + 1] += ds_y;
+        p.dL_dscales[3 * (size_t)idx + 2] += ds_z;
+      } else {
+        p.dL_dscales[3 * (size_t)idx + 0] = ds_x;
+        p.dL_dscales[3 * (size_t)idx + 1] = ds_y;
+        p.dL_dscales[3 * (size_t)idx + 2] = ds_z;
+      }
       // dL_dMt[i] *= s_i ; Mt[i][j] = D[j][i] * s_i
       const float t00 = D00 * sx, t01 = D10 * sx, t02 = D20 * sx;
       const float t10 = D01 * sy, t11 = D11 * sy, t12 = D21 * sy;
@@ -489,7 +518,12 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dq.y = 2 * y * (t10 + t01) + 2 * z * (t20 + t02) + 2 * r * (t12 - t21) - 4 * x * (t22 + t11);
       dq.z = 2 * x * (t10 + t01) + 2 * r * (t20 - t02) + 2 * z * (t12 + t21) - 4 * y * (t22 + t00);
       dq.w = 2 * r * (t01 - t10) + 2 * x * (t20 + t02) + 2 * y * (t12 + t21) - 4 * z * (t11 + t00);
-      reinterpret_cast<float4*>(p.dL_drotations)[idx] = dq;
+      float4* dq_out = reinterpret_cast<float4*>(p.dL_drotations) + idx;
+      if (ACC) {
+        const float4 o = *dq_out;
+        dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+      }
+      *dq_out = dq;
     }
   }
 
@@ -510,14 +544,21 @@ __global__ void zero_scalars_kernel(float* a, float* b) {
 }
 
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
-  zero_scalars_kernel<<<1, 1, 0, stream>>>(p.dL_dphase_offset, p.dL_ddc_offset);
-  note_launches(1);
+  if (!p.accumulate) {
+    zero_scalars_kernel<<<1, 1, 0, stream>>>(p.dL_dphase_offset, p.dL_ddc_offset);
+    note_launches(1);
+  }
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(preprocess_bwd_kernel, smem, &smem_ok);
-  preprocess_bwd_kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  static unsigned long long smem_ok0 = 0, smem_ok1 = 0;
+  if (p.accumulate) {
+    ensure_dynamic_smem(preprocess_bwd_kernel<true>, smem, &smem_ok1);
+    preprocess_bwd_kernel<true><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  } else {
+    ensure_dynamic_smem(preprocess_bwd_kernel<false>, smem, &smem_ok0);
+    preprocess_bwd_kernel<false><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  }
   note_launches(1);
 }
 

@@ -63,6 +63,16 @@ class GradBucket:
             t.grad = v
         return self
 
+    def grad_out(self):
+        """The bucket's slices keyed the way `rasterizer._native_backward(..., grad_out=...)` wants
+        them: the backward kernel then ADDS each view's gradients straight into the bucket
+        (no autograd accumulation pass, no copy)."""
+        out = dict(zip(self.names, self.views()[:len(self.names)]))
+        sc = self.views()[len(self.names):]
+        if len(sc) >= 2:
+            out["phase_offset"], out["dc_offset"] = sc[0], sc[1]
+        return out
+
     def zero(self):
         self.flat.zero_()
 

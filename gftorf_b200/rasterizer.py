@@ -204,10 +204,17 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
                      grad_out_color, grad_out_phasor, grad_out_depth, grad_out_normal,
                      grad_out_acc, grad_entropy, grad_depth_distortion, grad_amp_distortion,
                      sh, sh_p, degree, campos, geomBuffer, R, binningBuffer, imgBuffer, debug,
-                     near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset):
+                     near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset,
+                     grad_out=None):
     """Same argument order and 12-tuple result as `_C.rasterize_gaussians_backward`
     (rasterize_points.cu:167-281).  grad_out_normal / grad_entropy / grad_amp_distortion are
-    accepted and ignored, as in the reference (backward.cu never reads them)."""
+    accepted and ignored, as in the reference (backward.cu never reads them).
+
+    `grad_out` (not in the reference): dict with contiguous fp32 tensors `means3D [P,3]`,
+    `shs [P,M,3]`, `shs_p [P,M_p,2]`, `opacities [P,1]`, `scales [P,3]`, `rotations [P,4]`,
+    `phase_offset [1]`, `dc_offset [1]` that the parameter gradients are ADDED INTO
+    (GftBackwardArgs.accumulate) — the slices of a `parallel.GradBucket`, so the views of a batch
+    accumulate in the buffer the collective runs on."""
     lib = _capi.lib()
     dev = means3D.device
     P = int(means3D.shape[0])
@@ -233,18 +240,38 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
         o, n = offs[name]
         return flat[o:o + n].view(*shape)
 
-    dL_dmeans3D, dL_dmeans2D = view("means3D", P, 3), view("means2D", P, 3)
+    if grad_out is not None:
+        sizes = [(n, (0 if n in ("means3D", "opacity", "sh", "sh_p", "scales", "rot", "phase_offset",
+                                 "dc_offset") else k)) for n, k in sizes]
+        offs, cur = {}, 0
+        for name, n in sizes:
+            offs[name] = (cur, n)
+            cur += (n + 3) // 4 * 4
+        scratch_off = cur
+        flat = torch.empty(cur + scratch_floats, **f32)
+    dL_dmeans3D, dL_dmeans2D = view("means3D", P, 3) if grad_out is None else None, view("means2D", P, 3)
     dL_dcolors = view("colors", P, 3)
     # grad_phasors_precomp ([P,7] for a [P,2] input in the reference) is not produced
     dL_dphasors = None
-    dL_dopacity, dL_dcov3D = view("opacity", P, 1), view("cov3D", P, 6)
-    dL_dsh, dL_dsh_p = view("sh", P, M, 3), view("sh_p", P, M_p, 2)
-    dL_dscales, dL_drotations = view("scales", P, 3), view("rot", P, 4)
-    dL_dphase_offset, dL_ddc_offset = view("phase_offset", 1), view("dc_offset", 1)
+    dL_dcov3D = view("cov3D", P, 6)
     have_scales = scales is not None and scales.numel() != 0
-    if not have_scales and P > 0:
-        dL_dscales.zero_()
-        dL_drotations.zero_()
+    if grad_out is None:
+        dL_dopacity = view("opacity", P, 1)
+        dL_dsh, dL_dsh_p = view("sh", P, M, 3), view("sh_p", P, M_p, 2)
+        dL_dscales, dL_drotations = view("scales", P, 3), view("rot", P, 4)
+        dL_dphase_offset, dL_ddc_offset = view("phase_offset", 1), view("dc_offset", 1)
+        if not have_scales and P > 0:
+            dL_dscales.zero_()
+            dL_drotations.zero_()
+    else:
+        dL_dmeans3D, dL_dopacity = grad_out["means3D"], grad_out["opacities"]
+        dL_dsh, dL_dsh_p = grad_out["shs"], grad_out["shs_p"]
+        dL_dscales, dL_drotations = grad_out["scales"], grad_out["rotations"]
+        dL_dphase_offset, dL_ddc_offset = grad_out["phase_offset"], grad_out["dc_offset"]
+        for t in (dL_dmeans3D, dL_dopacity, dL_dsh, dL_dsh_p, dL_dscales, dL_drotations,
+                  dL_dphase_offset, dL_ddc_offset):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise RuntimeError("grad_out tensors must be contiguous fp32 tensors on the input's device")
 
     means3D = _f32c(means3D)
     sh, sh_p = _f32c(sh), _f32c(sh_p)
@@ -282,6 +309,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     a.near_n, a.far_n, a.depth_range = float(near_n), float(far_n), float(depth_range)
     a.use_view_dependent_phase = int(bool(use_view_dependent_phase))
     a.phase_offset, a.dc_offset = _as_float(phase_offset), _as_float(dc_offset)
+    a.accumulate = 0 if grad_out is None else 1
 
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):

@@ -175,6 +175,13 @@ typedef struct GftBackwardArgs {
   float near_n, far_n, depth_range;
   int use_view_dependent_phase;
   float phase_offset, dc_offset;
+
+  /* 0 (reference semantics): every output is overwritten.  1: dL_dmeans3D, dL_dsh, dL_dsh_p,
+   * dL_dopacity, dL_dscales, dL_drotations, dL_dphase_offset and dL_ddc_offset are ADDED TO
+   * (rows of culled Gaussians untouched), so the views of a multi-camera batch accumulate
+   * straight into one gradient bucket (the reference gets the same sum from autograd's
+   * AccumulateGrad, train.py:279).  dL_dmeans2D and the optional intermediates stay per view. */
+  int accumulate;
 } GftBackwardArgs;
 
 size_t gft_backward_scratch_bytes(int P);

@@ -502,3 +502,32 @@ def test_autograd_surface_matches_reference_binding():
     assert harness.rel_l2(phase.grad, rb[10]) <= harness.GRAD_REL_L2
     assert harness.rel_l2(dc.grad, rb[11]) <= harness.GRAD_REL_L2
     assert float(means2D.grad[:, 2].abs().max()) == 0.0
+
+
+def test_accumulate_mode_adds_views_into_the_bucket():
+    """GftBackwardArgs.accumulate: two views' gradients added straight into a GradBucket equal the
+    sum of the two plain backward results; rows of Gaussians culled in both views stay zero."""
+    from gftorf_b200 import parallel
+    inp_a = harness.build_inputs(device="cuda", P=6000, W=128, H=96, kind="trained", seed=31)
+    inp_b = harness.build_inputs(device="cuda", P=6000, W=96, H=80, kind="trained", seed=31, pose="orbit")
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p"):
+        inp_b[k] = inp_a[k]                       # same Gaussians, two cameras
+    params = {k: inp_a[k] for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p")}
+    scal = [torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")]
+    bucket = parallel.GradBucket(params, scal)
+    go = bucket.grad_out()
+    plain, vis = [], None
+    for inp in (inp_a, inp_b):
+        f = harness.call_forward(rasterizer._C, inp)
+        plain.append(harness.call_backward(rasterizer._C, inp, f))
+        acc = harness.call_backward(rasterizer._C, inp, f, grad_out=go)
+        assert harness.rel_l2(acc[0], plain[-1][0]) <= 1e-6       # means2D stays per view
+        vis = (f[11] > 0) if vis is None else (vis | (f[11] > 0))
+    pairs = dict(means3D=4, shs=6, shs_p=7, opacities=3, scales=8, rotations=9)
+    for name, i in pairs.items():
+        expect = plain[0][i] + plain[1][i]
+        assert harness.rel_l2(go[name], expect) <= 1e-5, name
+        assert float(go[name][~vis].abs().sum()) == 0.0, name
+    assert harness.rel_l2(go["phase_offset"], plain[0][10] + plain[1][10]) <= 1e-5
+    assert harness.rel_l2(go["dc_offset"], plain[0][11] + plain[1][11]) <= 1e-5
+    assert bucket.flat.data_ptr() == go["means3D"].data_ptr()
