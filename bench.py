@@ -194,11 +194,23 @@ def run_gpu(args, impl):
     grad_out = bucket.grad_out() if impl == "ours" else None
     bucket_views = dict(zip(bucket.names, bucket.views()[:len(bucket.names)]))
 
+    r_last = {}
+
+    def fwd(v):
+        if impl != "ours":
+            return mod.rasterize_gaussians(*fwd_args(params, v, empty))
+        # hinted mode: the previous step's instance count (+25 %) sizes the binning workspace, so
+        # the forward is enqueued without a host round trip in the middle
+        hint = int(r_last[id(v)] * 1.25) + 4096 if id(v) in r_last else 0
+        f = mod.rasterize_gaussians(*fwd_args(params, v, empty), R_hint=hint)
+        r_last[id(v)] = f[0]
+        return f
+
     def step_resident():
         bucket.zero()
         stats = []
         for v in views:
-            f = mod.rasterize_gaussians(*fwd_args(params, v, empty))
+            f = fwd(v)
             if impl == "ours":
                 mod.rasterize_gaussians_backward(
                     *bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]), grad_out=grad_out)
@@ -347,7 +359,7 @@ def run_gpu(args, impl):
     # render-only throughput (forward only, all outputs) — BASELINE's second metric
     def step_render():
         for v in views:
-            mod.rasterize_gaussians(*fwd_args(params, v, empty))
+            fwd(v)
     render_ms, _, _, _, _ = timed(step_render, K, W)
 
     if rank != 0:

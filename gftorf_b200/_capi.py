@@ -34,6 +34,7 @@ class GftForwardArgs(C.Structure):
         ("out_normal", C.c_void_p), ("out_acc", C.c_void_p), ("out_entropy", C.c_void_p),
         ("out_depth_distortion", C.c_void_p), ("out_amp_distortion", C.c_void_p),
         ("pixels", C.c_void_p), ("out_distribution", C.c_void_p), ("radii", C.c_void_p),
+        ("R_hint", C.c_int),
     ]
 
 

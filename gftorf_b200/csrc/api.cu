@@ -130,14 +130,28 @@ BinWs bin_layout(int R) {
   const size_t n = (size_t)(R > 0 ? R : 1);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
+  b.vals_a = take(n * 4);   // offset 0: where the sorted point list always ends up
+  b.vals_b = take(n * 4);
   b.keys_a = take(n * 8);
   b.keys_b = take(n * 8);
-  b.vals_a = take(n * 4);
-  b.vals_b = take(n * 4);
   b.temp_bytes = gft::radix_sort_temp_bytes((int)n);
   b.temp = take(b.temp_bytes);
   b.total = off;
   return b;
+}
+
+// Pinned word + event per device for reading num_rendered back without a full stream sync.
+struct HostSync { cudaEvent_t ev; uint32_t* pinned; };
+thread_local HostSync g_hs[64] = {};
+HostSync* host_sync() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostSync& h = g_hs[dev];
+  if (!h.pinned) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h.pinned), 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &h;
 }
 
 #define GFT_CUDA_OK(stage)                                                                  \
@@ -193,11 +207,11 @@ void gft_workspace_layout(int P, int R, int width, int height, GftWorkspaceLayou
   o->geom_total = g.total;
   const BinWs b = bin_layout(R);
   const int gx = (width + GFT_TILE_X - 1) / GFT_TILE_X, gy = (height + GFT_TILE_Y - 1) / GFT_TILE_Y;
-  const bool in_b = gft::sort_lands_in_out(32 + tile_bits((uint32_t)(gx * gy)));
-  o->bin_keys = in_b ? b.keys_b : b.keys_a;
-  o->bin_keys_unsorted = in_b ? b.keys_a : b.keys_b;  // overwritten by the ping-pong passes
-  o->bin_point_list = in_b ? b.vals_b : b.vals_a;
-  o->bin_point_list_unsorted = in_b ? b.vals_a : b.vals_b;
+  (void)gx; (void)gy;
+  o->bin_keys = b.keys_a;             // the ping-pong is started so that it always ends in "a"
+  o->bin_keys_unsorted = b.keys_b;    // scratch: overwritten by the passes
+  o->bin_point_list = b.vals_a;
+  o->bin_point_list_unsorted = b.vals_b;
   o->bin_total = b.total;
   const ImgWs m = img_layout(width, height);
   o->img_state = m.state;
@@ -287,55 +301,97 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   { Stage st("preprocess_fwd", stream); gft::launch_preprocess_fwd(pp, stream); }
   GFT_CUDA_OK("preprocess");
 
-  // R sizes the binning workspace, so it has to reach the host (rasterizer_impl.cu:310-315)
-  uint32_t R_u = 0;
-  cudaError_t e = cudaMemcpyAsync(&R_u, hdr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  // R sizes the binning workspace, so it has to reach the host (rasterizer_impl.cu:310-315).  It
+  // travels through a pinned word and an event, so the host waits for the preprocess kernel only.
+  HostSync* hs = host_sync();
+  if (!hs) return fail(-2, "gft_forward: cannot create the pinned word / event for num_rendered");
+  uint32_t* d_R = hdr + 1;
+  cudaError_t e = cudaMemcpyAsync(hs->pinned, d_R, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaEventRecord(hs->ev, stream);
   if (e != cudaSuccess)
     return fail(-2, std::string("CUDA error reading num_rendered: ") + cudaGetErrorString(e));
-  if (R_u > 0x7fffffffu) return fail(-4, "gft_forward: num_rendered exceeds 2^31-1");
-  const int R = (int)R_u;
 
-  const BinWs bl = bin_layout(R);
-  char* bin = binning_alloc(ctx, bl.total);
-  if (!bin) return fail(-3, "gft_forward: binning workspace callback returned null");
-  uint64_t* keys_a = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
-  uint64_t* keys_b = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
-  uint32_t* vals_a = reinterpret_cast<uint32_t*>(bin + bl.vals_a);
-  uint32_t* vals_b = reinterpret_cast<uint32_t*>(bin + bl.vals_b);
-  const uint64_t* keys_sorted = keys_a;
-  const uint32_t* point_list = vals_a;
-  if (R > 0) {
-    { Stage st("duplicate_keys", stream);
-      gft::launch_duplicate_keys(P, a->radii, pp.rect, pp.depths, pp.point_offsets, keys_a, vals_a,
-                                 gx, stream); }
-    GFT_CUDA_OK("duplicate_keys");
-    const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
-    int rc;
-    { Stage st("radix_sort", stream);
-      rc = gft::sort_pairs(bin + bl.temp, bl.temp_bytes, keys_a, keys_b, vals_a, vals_b, R, end_bit,
-                           stream); }
-    if (rc < 0) return fail(-2, "gft_forward: radix sort failed");
-    GFT_CUDA_OK("sort");
-    if (gft::sort_result_in_out(end_bit)) { keys_sorted = keys_b; point_list = vals_b; }
-    { Stage st("identify_ranges", stream); gft::launch_identify_ranges(R, keys_sorted, pp.ranges, stream); }
-    GFT_CUDA_OK("identify_ranges");
+  const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
+  uint2* ranges = pp.ranges;
+
+  // Everything after the preprocess kernel, for a binning workspace of `cap` pairs.  With
+  // dev_count != nullptr the kernels read the actual pair count from device memory, so they can be
+  // enqueued before the host knows it.
+  auto bin_and_blend = [&](int cap, const uint32_t* dev_count) -> int {
+    const BinWs bl = bin_layout(cap);
+    char* bin = binning_alloc(ctx, bl.total);
+    if (!bin) return fail(-3, "gft_forward: binning workspace callback returned null");
+    uint64_t* keys_a = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
+    uint64_t* keys_b = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
+    uint32_t* vals_a = reinterpret_cast<uint32_t*>(bin + bl.vals_a);
+    uint32_t* vals_b = reinterpret_cast<uint32_t*>(bin + bl.vals_b);
+    if (cap > 0) {
+      // start the ping-pong in the buffer that makes the last pass land in (keys_a, vals_a)
+      const bool flip = gft::sort_result_in_out(end_bit);
+      uint64_t* kin = flip ? keys_b : keys_a; uint64_t* kout = flip ? keys_a : keys_b;
+      uint32_t* vin = flip ? vals_b : vals_a; uint32_t* vout = flip ? vals_a : vals_b;
+      { Stage st("duplicate_keys", stream);
+        gft::launch_duplicate_keys(P, a->radii, pp.rect, pp.depths, pp.point_offsets, kin, vin, gx,
+                                   (uint32_t)cap, stream); }
+      GFT_CUDA_OK("duplicate_keys");
+      int rc;
+      { Stage st("radix_sort", stream);
+        rc = gft::sort_pairs(bin + bl.temp, bl.temp_bytes, kin, kout, vin, vout, cap, end_bit, stream,
+                             dev_count); }
+      if (rc < 0) return fail(-2, "gft_forward: radix sort failed");
+      GFT_CUDA_OK("sort");
+      { Stage st("identify_ranges", stream);
+        gft::launch_identify_ranges(cap, dev_count, keys_a, ranges, stream); }
+      GFT_CUDA_OK("identify_ranges");
+    }
+    gft::BlendFwdParams bp;
+    std::memset(&bp, 0, sizeof(bp));
+    bp.W = W; bp.H = H; bp.grid_x = gx; bp.grid_y = gy;
+    bp.ranges = ranges; bp.point_list = vals_a;
+    bp.rec = reinterpret_cast<const float4*>(pp.rec);
+    bp.bg = a->background; bp.bg_mode = a->bg_mode;
+    bp.img_state = reinterpret_cast<float4*>(img + il.state);
+    bp.out_color = a->out_color; bp.out_phasor = a->out_phasor; bp.out_depth = a->out_depth;
+    bp.out_normal = a->out_normal; bp.out_acc = a->out_acc; bp.out_entropy = a->out_entropy;
+    bp.out_depth_distortion = a->out_depth_distortion;
+    bp.out_amp_distortion = a->out_amp_distortion; bp.out_distribution = a->out_distribution;
+    bp.pixels = a->pixels;
+    { Stage st("blend_fwd", stream); gft::launch_blend_fwd(bp, stream); }
+    GFT_CUDA_OK("blend_fwd");
+    return 0;
+  };
+  auto wait_R = [&](int& R_out) -> int {
+    const cudaError_t ee = cudaEventSynchronize(hs->ev);
+    if (ee != cudaSuccess)
+      return fail(-2, std::string("CUDA error reading num_rendered: ") + cudaGetErrorString(ee));
+    const uint32_t R_u = *hs->pinned;
+    if (R_u > 0x7fffffffu) return fail(-4, "gft_forward: num_rendered exceeds 2^31-1");
+    R_out = (int)R_u;
+    return 0;
+  };
+
+  int R = 0;
+  const bool hinted = a->R_hint > 0 && gft::sort_backend() == 0;
+  if (!hinted) {
+    // exact mode (reference behaviour): wait for the count, then size the workspace from it
+    int rc = wait_R(R);
+    if (rc < 0) return rc;
+    rc = bin_and_blend(R, nullptr);
+    if (rc < 0) return rc;
+  } else {
+    // hinted mode: the caller's estimate sizes the workspace, all kernels are enqueued at once and
+    // read the count on the device; the host only learns R afterwards (no bubble in the stream).
+    int rc = bin_and_blend(a->R_hint, d_R);
+    if (rc < 0) return rc;
+    rc = wait_R(R);
+    if (rc < 0) return rc;
+    if (R > a->R_hint) {   // estimate too small: redo binning + blend with the exact size
+      cudaMemsetAsync(a->pixels, 0, (size_t)P * sizeof(float), stream);
+      cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), stream);
+      rc = bin_and_blend(R, nullptr);
+      if (rc < 0) return rc;
+    }
   }
-
-  gft::BlendFwdParams bp;
-  std::memset(&bp, 0, sizeof(bp));
-  bp.W = W; bp.H = H; bp.grid_x = gx; bp.grid_y = gy;
-  bp.ranges = pp.ranges; bp.point_list = point_list;
-  bp.rec = reinterpret_cast<const float4*>(pp.rec);
-  bp.bg = a->background; bp.bg_mode = a->bg_mode;
-  bp.img_state = reinterpret_cast<float4*>(img + il.state);
-  bp.out_color = a->out_color; bp.out_phasor = a->out_phasor; bp.out_depth = a->out_depth;
-  bp.out_normal = a->out_normal; bp.out_acc = a->out_acc; bp.out_entropy = a->out_entropy;
-  bp.out_depth_distortion = a->out_depth_distortion;
-  bp.out_amp_distortion = a->out_amp_distortion; bp.out_distribution = a->out_distribution;
-  bp.pixels = a->pixels;
-  { Stage st("blend_fwd", stream); gft::launch_blend_fwd(bp, stream); }
-  GFT_CUDA_OK("blend_fwd");
   return R;
 }
 
@@ -374,7 +430,6 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
   const int gx = (W + GFT_TILE_X - 1) / GFT_TILE_X, gy = (H + GFT_TILE_Y - 1) / GFT_TILE_Y;
   const GeomWs gl = geom_layout(P);
   const ImgWs il = img_layout(W, H);
-  const BinWs bl = bin_layout(a->R);
   const char* geom = a->geom_buffer;
   const char* img = a->img_buffer;
   const char* bin = a->binning_buffer;
@@ -383,13 +438,11 @@ int gft_backward(const GftBackwardArgs* a, gft_stream_t stream_) {
     cudaMemsetAsync(a->scratch, 0, (size_t)P * GFT_GRAD_FLOATS * 4, stream); }
 
   if (a->R > 0) {
-    const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
     gft::BlendBwdParams bp;
     std::memset(&bp, 0, sizeof(bp));
     bp.W = W; bp.H = H; bp.grid_x = gx; bp.grid_y = gy;
     bp.ranges = reinterpret_cast<const uint2*>(img + il.ranges);
-    bp.point_list = reinterpret_cast<const uint32_t*>(
-        bin + (gft::sort_result_in_out(end_bit) ? bl.vals_b : bl.vals_a));
+    bp.point_list = reinterpret_cast<const uint32_t*>(bin);  // sorted list: offset 0 of the workspace
     bp.rec = reinterpret_cast<const float4*>(geom + gl.rec);
     bp.bg = a->background; bp.bg_mode = a->bg_mode;
     bp.img_state = reinterpret_cast<const float4*>(img + il.state);

@@ -18,7 +18,7 @@ namespace gft {
 __global__ void __launch_bounds__(GFT_BLOCK)
 duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __restrict__ depths,
                       const uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys,
-                      uint32_t* __restrict__ values, int grid_x) {
+                      uint32_t* __restrict__ values, int grid_x, uint32_t capacity) {
   __shared__ uint32_t s_end[GFT_BLOCK];
   const int first = blockIdx.x * GFT_BLOCK;
   const int idx = first + threadIdx.x;
@@ -45,13 +45,17 @@ duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __r
     uint64_t key = (uint64_t)(ty * (uint32_t)grid_x + tx);
     key <<= 32;
     key |= (uint64_t)__float_as_uint(__ldg(depths + g));
-    keys[base + i] = key;
-    values[base + i] = (uint32_t)g;
+    if (base + i < capacity) {   // only ever false when a caller's size hint was too small
+      keys[base + i] = key;
+      values[base + i] = (uint32_t)g;
+    }
   }
 }
 
-__global__ void identify_ranges_kernel(int R, const uint64_t* __restrict__ keys,
+__global__ void identify_ranges_kernel(int R_cap, const uint32_t* __restrict__ d_R,
+                                       const uint64_t* __restrict__ keys,
                                        uint2* __restrict__ ranges) {
+  const int R = d_R ? (int)min(__ldg(d_R), (uint32_t)R_cap) : R_cap;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R) return;
   const uint32_t cur = (uint32_t)(keys[idx] >> 32);
@@ -69,16 +73,17 @@ __global__ void identify_ranges_kernel(int R, const uint64_t* __restrict__ keys,
 
 void launch_duplicate_keys(int P, const int* /*radii*/, const uint16_t* rect, const float* depths,
                            const uint32_t* point_offsets, uint64_t* keys, uint32_t* values,
-                           int grid_x, cudaStream_t stream) {
+                           int grid_x, uint32_t capacity, cudaStream_t stream) {
   const int blocks = (P + GFT_BLOCK - 1) / GFT_BLOCK;
   duplicate_keys_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(P, rect, depths, point_offsets, keys,
-                                                          values, grid_x);
+                                                          values, grid_x, capacity);
   note_launches(1);
 }
 
-void launch_identify_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream) {
+void launch_identify_ranges(int R, const uint32_t* d_R, const uint64_t* keys, uint2* ranges,
+                            cudaStream_t stream) {
   if (R <= 0) return;
-  identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, keys, ranges);
+  identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, d_R, keys, ranges);
   note_launches(1);
 }
 
@@ -88,9 +93,9 @@ size_t sort_pairs_temp_bytes(int R) { return radix_sort_temp_bytes(R); }
 
 int sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-               cudaStream_t stream) {
+               cudaStream_t stream, const uint32_t* d_R) {
   return radix_sort_pairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, R, end_bit,
-                          stream);
+                          stream, d_R);
 }
 
 }  // namespace gft

@@ -160,6 +160,108 @@ blend_bwd_kernel(BlendBwdParams p) {
     cp_async_commit();
   };
 
+  // backward.cu:739-754 — the same alpha chain as the forward, so the same pairs are replayed
+  auto eval_pair = [&](const BwdBuf& s, int base, int k, float& G, float& alpha, float& dx,
+                       float& dy) -> bool {
+    const float4 g0 = s.r0[k];
+    const float4 g1 = s.r1[k];
+    dx = __fsub_rn(g0.x, pixfx);
+    dy = __fsub_rn(g0.y, pixfy);
+    const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
+    const bool neg = !(power > 0.0f);
+    G = expf(neg ? power : 0.0f);
+    alpha = fminf(0.99f, __fmul_rn(g1.w, G));
+    return ((uint32_t)(base + k) < last_contributor) && neg && !(alpha < 1.0f / 255.0f);
+  };
+
+  auto replay = [&](const BwdBuf& s, int k, bool contrib, float G, float alpha, float dx, float dy) {
+    if (!__any_sync(0xffffffffu, contrib)) return;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if (contrib) {
+      const float4 g1 = s.r1[k];
+      const float4 g2 = s.r2[k];
+      const float4 g3 = s.r3[k];
+      const float4 g4 = s.r4[k];
+      const float om = 1.f - alpha;
+      const float inv_om = 1.0f / om;
+      T = T * inv_om;                 // backward.cu:756
+      const float w = alpha * T;      // weight of the alpha*T family
+      const float wp = w * T;         // weight of the phasor family, alpha*T*T
+
+      const float z = g4.w;
+      const float kappa = g2.x * gc0 + g2.y * gc1 + g2.z * gc2;
+      const float x_tot = kappa + g2.w * gd + (z * (z * k2 - k1) + k0);
+      const float pi = g3.x * gp0 + g3.y * gp1 + g3.z * gp2 + g3.w * gp3 + g4.x * gp4 +
+                       g4.y * gp5 + g4.z * gp6;
+      const float dL_dalpha = (x_tot - X) * T + (pi - 2.f * om * Bp) * (T * T) -
+                              (T_final * inv_om) * bgdot;
+      X = alpha * x_tot + om * X;
+      Bp = alpha * pi + (om * om) * Bp;
+
+      const float h = g1.w * dL_dalpha * G;   // dL_dG * G
+      const float hx = h * dx, hy = h * dy;
+      v[0] = hx;
+      v[1] = hy;
+      v[2] = hx * dx;
+      v[3] = hx * dy;
+      v[4] = hy * dy;
+      v[5] = G * dL_dalpha;
+      v[6] = w * gc0;
+      v[7] = w * gc1;
+      v[8] = w * gc2;
+      v[9] = w * gd;
+      v[10] = w * (2.f * z * k2 - k1);
+      v[11] = wp * gA;
+      v[12] = wp * gB;
+      v[13] = wp * gp2;
+      v[14] = wp * gS;
+    }
+
+    // ---- halving butterfly: value i ends complete in lanes 2i and 2i+1 ---------------------
+    float a8[8];
+    {
+      const bool up = (lane & 16u) != 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = up ? v[i] : v[i + 8];
+        const float keep = up ? v[i + 8] : v[i];
+        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    float a4[4];
+    {
+      const bool up = (lane & 8u) != 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = up ? a8[i] : a8[i + 4];
+        const float keep = up ? a8[i + 4] : a8[i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    float a2[2];
+    {
+      const bool up = (lane & 4u) != 0u;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = up ? a4[i] : a4[i + 2];
+        const float keep = up ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+    float a1;
+    {
+      const bool up = (lane & 2u) != 0u;
+      const float send = up ? a2[0] : a2[1];
+      const float keep = up ? a2[1] : a2[0];
+      a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if ((lane & 1u) == 0u && lane != 30u)   // lane 30 holds the unused slot 15
+      atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), a1);
+  };
+
   int cur = 0;
   if (nb > 0) stage(nb - 1, cur);
   for (int b = nb - 1; b >= 0; --b) {
@@ -181,107 +283,18 @@ blend_bwd_kernel(BlendBwdParams p) {
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {
-        const int bsel = 31 - __clz(mask);
-        mask &= ~(1u << bsel);
-        const int k = c + bsel;
-        const float4 g0 = s.r0[k];
-        const float4 g1 = s.r1[k];
-        const float dx = __fsub_rn(g0.x, pixfx);
-        const float dy = __fsub_rn(g0.y, pixfy);
-        const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
-        // backward.cu:739-754 — the same alpha chain as the forward, so the same pairs are replayed
-        bool contrib = ((uint32_t)(base + k) < last_contributor) && !(power > 0.0f);
-        float G = 0.f, alpha = 0.f;
-        if (contrib) {
-          G = expf(power);
-          alpha = fminf(0.99f, __fmul_rn(g1.w, G));
-          contrib = !(alpha < 1.0f / 255.0f);
-        }
-        if (!__any_sync(0xffffffffu, contrib)) continue;
-
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        if (contrib) {
-          const float4 g2 = s.r2[k];
-          const float4 g3 = s.r3[k];
-          const float4 g4 = s.r4[k];
-          const float om = 1.f - alpha;
-          const float inv_om = 1.0f / om;
-          T = T * inv_om;                 // backward.cu:756
-          const float w = alpha * T;      // weight of the alpha*T family
-          const float wp = w * T;         // weight of the phasor family, alpha*T*T
-
-          const float z = g4.w;
-          const float kappa = g2.x * gc0 + g2.y * gc1 + g2.z * gc2;
-          const float x_tot = kappa + g2.w * gd + (z * (z * k2 - k1) + k0);
-          const float pi = g3.x * gp0 + g3.y * gp1 + g3.z * gp2 + g3.w * gp3 + g4.x * gp4 +
-                           g4.y * gp5 + g4.z * gp6;
-          const float dL_dalpha = (x_tot - X) * T + (pi - 2.f * om * Bp) * (T * T) -
-                                  (T_final * inv_om) * bgdot;
-          X = alpha * x_tot + om * X;
-          Bp = alpha * pi + (om * om) * Bp;
-
-          const float h = g1.w * dL_dalpha * G;   // dL_dG * G
-          const float hx = h * dx, hy = h * dy;
-          v[0] = hx;
-          v[1] = hy;
-          v[2] = hx * dx;
-          v[3] = hx * dy;
-          v[4] = hy * dy;
-          v[5] = G * dL_dalpha;
-          v[6] = w * gc0;
-          v[7] = w * gc1;
-          v[8] = w * gc2;
-          v[9] = w * gd;
-          v[10] = w * (2.f * z * k2 - k1);
-          v[11] = wp * gA;
-          v[12] = wp * gB;
-          v[13] = wp * gp2;
-          v[14] = wp * gS;
-        }
-
-        // ---- halving butterfly: value i ends complete in lanes 2i and 2i+1 -----------------
-        float a8[8];
-        {
-          const bool up = (lane & 16u) != 0u;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float send = up ? v[i] : v[i + 8];
-            const float keep = up ? v[i + 8] : v[i];
-            a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-        }
-        float a4[4];
-        {
-          const bool up = (lane & 8u) != 0u;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float send = up ? a8[i] : a8[i + 4];
-            const float keep = up ? a8[i + 4] : a8[i];
-            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-        }
-        float a2[2];
-        {
-          const bool up = (lane & 4u) != 0u;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float send = up ? a4[i] : a4[i + 2];
-            const float keep = up ? a4[i + 2] : a4[i];
-            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          }
-        }
-        float a1;
-        {
-          const bool up = (lane & 2u) != 0u;
-          const float send = up ? a2[0] : a2[1];
-          const float keep = up ? a2[1] : a2[0];
-          a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-        if ((lane & 1u) == 0u && lane != 30u)   // lane 30 holds the unused slot 15
-          atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), a1);
+        // two candidates per trip (back to front): their alpha chains are independent of the
+        // pixel's running state and overlap; the replay itself stays sequential
+        const int s1 = 31 - __clz(mask);
+        mask &= ~(1u << s1);
+        const bool two = mask != 0u;
+        const int s2 = two ? (31 - __clz(mask)) : s1;
+        if (two) mask &= ~(1u << s2);
+        float G1, G2, al1, al2, dx1, dy1, dx2, dy2;
+        const bool c1 = eval_pair(s, base, c + s1, G1, al1, dx1, dy1);
+        const bool c2 = eval_pair(s, base, c + s2, G2, al2, dx2, dy2);
+        replay(s, c + s1, c1, G1, al1, dx1, dy1);
+        if (two) replay(s, c + s2, c2, G2, al2, dx2, dy2);
       }
     }
     cur ^= 1;

@@ -47,7 +47,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 }  // namespace
 
-__global__ void __launch_bounds__(GFT_BLOCK, 3)
+__global__ void __launch_bounds__(GFT_BLOCK, 4)
 blend_fwd_kernel(BlendFwdParams p) {
   extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
   FwdBuf* buf = reinterpret_cast<FwdBuf*>(fwd_smem_raw);
@@ -95,13 +95,84 @@ blend_fwd_kernel(BlendFwdParams p) {
     cp_async_commit();
   };
 
-  int cur = 0;
+  // One (pixel, Gaussian) pair, after its alpha has been evaluated.  Sequential per pixel: the
+  // transmittance test and the accumulators depend on every earlier Gaussian.
+  auto apply = [&](const FwdBuf& s, int base, int k, int b, float alpha, bool pass, int& mycnt) {
+    bool contrib = !done && pass;
+    float test_T = 0.f;
+    if (contrib) {
+      test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+      if (test_T < 0.0001f) {   // forward.cu:538-543: done BEFORE applying this Gaussian
+        done = true;
+        contrib = false;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
+    if ((int)lane == b) mycnt = __popc(bal);
+    if (contrib) {
+      const float4 g2 = s.r2[k];
+      const float4 g3 = s.r3[k];
+      const float4 g4 = s.r4[k];
+      const float w = __fmul_rn(T, alpha);
+      const float wp = __fmul_rn(T, w);
+      C0 = __fmaf_rn(w, g2.x, C0);
+      C1 = __fmaf_rn(w, g2.y, C1);
+      C2 = __fmaf_rn(w, g2.z, C2);
+      P0 = __fmaf_rn(wp, g3.x, P0);
+      P1 = __fmaf_rn(wp, g3.y, P1);
+      P2 = __fmaf_rn(wp, g3.z, P2);
+      P3 = __fmaf_rn(wp, g3.w, P3);
+      P4 = __fmaf_rn(wp, g4.x, P4);
+      P5 = __fmaf_rn(wp, g4.y, P5);
+      P6 = __fmaf_rn(wp, g4.z, P6);
+      if (first_hit) {  // first applied Gaussian (forward.cu:561-567)
+        WD0 = alpha;
+        WD1 = g2.w;
+        WD2 = g3.z;
+        first_hit = false;
+      }
+      // depth distortion, forward.cu:572-578 in the reference's evaluation order
+      const float z = g4.w;
+      const float z2 = __fmul_rn(z, z);
+      const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
+      float t2 = __fmaf_rn(A, z2, -t1);
+      const float wz = __fmul_rn(w, z);
+      t2 = __fadd_rn(DD_D2, t2);
+      DD_D = __fadd_rn(DD_D, wz);
+      DD_D2 = __fmaf_rn(z, wz, DD_D2);
+      D = __fmaf_rn(w, g2.w, D);
+      DD = __fmaf_rn(w, t2, DD);
+      A = __fadd_rn(A, w);
+      T = test_T;
+      last_contributor = (uint32_t)(base + k + 1);
+    }
+  };
+  // alpha of one pair (forward.cu:524-537), independent of the pixel's running state, so two
+  // Gaussians are evaluated side by side to overlap their expf latency chains
+  auto eval_alpha = [&](const FwdBuf& s, int k, float& alpha) -> bool {
+    const float4 g0 = s.r0[k];
+    const float4 g1 = s.r1[k];
+    const float dx = __fsub_rn(g0.x, pixfx);
+    const float dy = __fsub_rn(g0.y, pixfy);
+    const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
+    const bool neg = !(power > 0.0f);
+    alpha = fminf(0.99f, __fmul_rn(g1.w, expf(neg ? power : 0.0f)));
+    return neg && !(alpha < 1.0f / 255.0f);
+  };
+
+  int cur = 0, prev_m = 0;
   if (n > 0) stage(0, cur);
   for (int base = 0; base < n; base += BATCH) {
     cp_async_wait_all();
-    // End if the entire block votes that it is done (forward.cu:500-502); the same barrier
-    // publishes batch `base` in buf[cur] and retires every reader of buf[cur^1].
-    if (__syncthreads_and(done)) break;
+    // One barrier per batch: it publishes batch `base` in buf[cur], retires every reader of
+    // buf[cur^1], and carries the block-wide "everyone is done" vote (forward.cu:500-502).
+    const bool all_done = __syncthreads_and(done);
+    if ((int)tid < prev_m) {   // pixel counts of the batch all warps have just left
+      const int cnt = buf[cur ^ 1].cnt[tid];
+      if (cnt) atomicAdd(p.pixels + buf[cur ^ 1].id[tid], (float)cnt);
+    }
+    prev_m = 0;
+    if (all_done) break;
     if (base + BATCH < n) stage(base + BATCH, cur ^ 1);   // overlaps with the work below
     FwdBuf& s = buf[cur];
     const int m = min(BATCH, n - base);
@@ -119,66 +190,16 @@ blend_fwd_kernel(BlendFwdParams p) {
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
         int mycnt = 0;
         while (mask) {
-          const int b = __ffs(mask) - 1;
+          const int b1 = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int k = c + b;
-          const float4 g0 = s.r0[k];
-          const float4 g1 = s.r1[k];
-          const float dx = __fsub_rn(g0.x, pixfx);
-          const float dy = __fsub_rn(g0.y, pixfy);
-          const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
-          bool contrib = !done && !(power > 0.0f);
-          float alpha = 0.f, test_T = 0.f;
-          if (contrib) {
-            alpha = fminf(0.99f, __fmul_rn(g1.w, expf(power)));
-            contrib = !(alpha < 1.0f / 255.0f);
-            if (contrib) {
-              test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-              if (test_T < 0.0001f) {
-                done = true;
-                contrib = false;
-              }
-            }
-          }
-          const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
-          if ((int)lane == b) mycnt = __popc(bal);
-          if (contrib) {
-            const float4 g2 = s.r2[k];
-            const float4 g3 = s.r3[k];
-            const float4 g4 = s.r4[k];
-            const float w = __fmul_rn(T, alpha);
-            const float wp = __fmul_rn(T, w);
-            C0 = __fmaf_rn(w, g2.x, C0);
-            C1 = __fmaf_rn(w, g2.y, C1);
-            C2 = __fmaf_rn(w, g2.z, C2);
-            P0 = __fmaf_rn(wp, g3.x, P0);
-            P1 = __fmaf_rn(wp, g3.y, P1);
-            P2 = __fmaf_rn(wp, g3.z, P2);
-            P3 = __fmaf_rn(wp, g3.w, P3);
-            P4 = __fmaf_rn(wp, g4.x, P4);
-            P5 = __fmaf_rn(wp, g4.y, P5);
-            P6 = __fmaf_rn(wp, g4.z, P6);
-            if (first_hit) {  // first applied Gaussian (forward.cu:561-567)
-              WD0 = alpha;
-              WD1 = g2.w;
-              WD2 = g3.z;
-              first_hit = false;
-            }
-            // depth distortion, forward.cu:572-578 in the reference's evaluation order
-            const float z = g4.w;
-            const float z2 = __fmul_rn(z, z);
-            const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
-            float t2 = __fmaf_rn(A, z2, -t1);
-            const float wz = __fmul_rn(w, z);
-            t2 = __fadd_rn(DD_D2, t2);
-            DD_D = __fadd_rn(DD_D, wz);
-            DD_D2 = __fmaf_rn(z, wz, DD_D2);
-            D = __fmaf_rn(w, g2.w, D);
-            DD = __fmaf_rn(w, t2, DD);
-            A = __fadd_rn(A, w);
-            T = test_T;
-            last_contributor = (uint32_t)(base + k + 1);
-          }
+          const bool two = mask != 0u;
+          const int b2 = two ? (__ffs(mask) - 1) : b1;
+          if (two) mask &= mask - 1;
+          float alpha1, alpha2;
+          const bool pass1 = eval_alpha(s, c + b1, alpha1);
+          const bool pass2 = eval_alpha(s, c + b2, alpha2);
+          apply(s, base, c + b1, b1, alpha1, pass1, mycnt);
+          if (two) apply(s, base, c + b2, b2, alpha2, pass2, mycnt);
         }
         if (mycnt) atomicAdd(&s.cnt[jj], mycnt);
         if (__all_sync(0xffffffffu, done)) {
@@ -187,12 +208,13 @@ blend_fwd_kernel(BlendFwdParams p) {
         }
       }
     }
-    __syncthreads();
-    if ((int)tid < m) {
-      const int cnt = s.cnt[tid];
-      if (cnt) atomicAdd(p.pixels + s.id[tid], (float)cnt);
-    }
+    prev_m = m;
     cur ^= 1;
+  }
+  __syncthreads();
+  if ((int)tid < prev_m) {   // the last batch that was processed
+    const int cnt = buf[cur ^ 1].cnt[tid];
+    if (cnt) atomicAdd(p.pixels + buf[cur ^ 1].id[tid], (float)cnt);
   }
   cp_async_wait_all();   // a prefetch may still be in flight when the tile finished early
 

@@ -68,15 +68,17 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
 // ---- binning ---------------------------------------------------------------------------------
 void launch_duplicate_keys(int P, const int* radii, const uint16_t* rect, const float* depths,
                            const uint32_t* point_offsets, uint64_t* keys, uint32_t* values,
-                           int grid_x, cudaStream_t stream);
+                           int grid_x, uint32_t capacity, cudaStream_t stream);
 // Stable LSD radix sort of (key,value) pairs on bits [0, end_bit).  Returns temp bytes needed
 // when d_temp == nullptr.
 size_t sort_pairs_temp_bytes(int R);
+// R: capacity (grid / temp sizing); d_R: optional device pointer to the actual count (<= R)
 int sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-               cudaStream_t stream);
+               cudaStream_t stream, const uint32_t* d_R = nullptr);
 bool sort_result_in_out(int end_bit);
-void launch_identify_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+void launch_identify_ranges(int R, const uint32_t* d_R, const uint64_t* keys, uint2* ranges,
+                            cudaStream_t stream);
 
 // ---- blend -----------------------------------------------------------------------------------
 struct BlendFwdParams {

@@ -13,15 +13,17 @@
 namespace gft {
 
 size_t radix_sort_temp_bytes(int R);
+// d_R (optional): device pointer to the actual pair count, <= R; R is then only the capacity the
+// grids and the temp storage are sized for (own back-end only).
 int radix_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                      const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const uint32_t* d_R = nullptr);
 
 // own back-end (radix_sort_own.cu)
 size_t own_sort_temp_bytes(int R);
 int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                    const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const uint32_t* d_R = nullptr);
 
 // cub back-end (radix_sort_cub.cu)
 size_t cub_sort_temp_bytes(int R);

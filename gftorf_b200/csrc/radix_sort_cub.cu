@@ -45,12 +45,14 @@ bool sort_lands_in_out(int end_bit) {
 
 int radix_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                      const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-                     cudaStream_t stream) {
-  if (sort_backend() == 1)
+                     cudaStream_t stream, const uint32_t* d_R) {
+  if (sort_backend() == 1) {
+    if (d_R) return -3;  // the library call needs the count on the host
     return cub_sort_pairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, R, end_bit,
                           stream);
+  }
   return own_sort_pairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, R, end_bit,
-                        stream);
+                        stream, d_R);
 }
 
 }  // namespace gft

@@ -40,8 +40,10 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 
 // hist[pass][bin] over all keys; one read of the keys for all passes.
 __global__ void __launch_bounds__(RS_THREADS)
-rs_histogram_kernel(const uint64_t* __restrict__ keys, int R, int npass, int end_bit,
-                    uint32_t* __restrict__ hist) {
+rs_histogram_kernel(const uint64_t* __restrict__ keys, int R_cap, const uint32_t* __restrict__ d_R,
+                    int npass, int end_bit, uint32_t* __restrict__ hist) {
+  // the pair count lives on the device when the caller sized the buffers from a hint
+  const int R = d_R ? (int)min(__ldg(d_R), (uint32_t)R_cap) : R_cap;
   __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_BINS];
   for (int i = threadIdx.x; i < npass * RS_BINS; i += RS_THREADS) s_hist[i] = 0;
   __syncthreads();
@@ -92,18 +94,23 @@ struct RsSmem {
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
-                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int R,
-                   int shift, int nbits, const uint32_t* __restrict__ digit_base,
-                   uint32_t* __restrict__ ticket, uint32_t* __restrict__ state) {
+                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int R_cap,
+                   const uint32_t* __restrict__ d_R, int shift, int nbits,
+                   const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ ticket,
+                   uint32_t* __restrict__ state) {
   extern __shared__ __align__(16) unsigned char rs_smem_raw[];
   RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = d_R ? (int)min(__ldg(d_R), (uint32_t)R_cap) : R_cap;
 
   if (tid == 0) s.tile_id = atomicAdd(ticket, 1u);
   for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&s.warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s.tile_id;
   const uint32_t tile_base = tile * RS_TILE;
+  // the grid is sized for R_cap; tiles past the actual count have nothing to do and nobody waits
+  // on them (tickets are handed out in order, so every real tile is claimed by some block)
+  if (tile_base >= (uint32_t)R) return;
   const uint32_t dmask = (1u << nbits) - 1u;
 
   // ---- load (warp-striped: warp w owns RS_ITEMS*32 consecutive pairs) and rank -------------
@@ -227,7 +234,7 @@ size_t own_sort_temp_bytes(int R) {
 // b when the pass count is odd and in a when it is even.  Returns the pass count, <0 on error.
 int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, uint64_t* keys_b,
                    const uint32_t* vals_a_c, uint32_t* vals_b, int R, int end_bit,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const uint32_t* d_R) {
   if (R <= 0) return 0;
   if (end_bit > 64 || end_bit <= 0) return -1;
   if (temp_bytes < own_sort_temp_bytes(R)) return -2;
@@ -243,7 +250,7 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
 
   int hblocks = (R + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
   hblocks = max(1, min(hblocks, 148 * 8));
-  rs_histogram_kernel<<<hblocks, RS_THREADS, 0, stream>>>(keys_a, R, npass, end_bit, hist);
+  rs_histogram_kernel<<<hblocks, RS_THREADS, 0, stream>>>(keys_a, R, d_R, npass, end_bit, hist);
   rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
   note_launches(2 + npass);
 
@@ -255,7 +262,7 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
     const int shift = 8 * p;
     const int nb = min(8, end_bit - shift);
     rs_onesweep_kernel<<<tiles, RS_THREADS, sizeof(RsSmem), stream>>>(
-        kin, kout, vin, vout, R, shift, nb, hist + p * RS_BINS, ticket + p,
+        kin, kout, vin, vout, R, d_R, shift, nb, hist + p * RS_BINS, ticket + p,
         state + (size_t)p * tiles * RS_BINS);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

@@ -132,9 +132,14 @@ def _sh_count(t):
 def _native_forward(bg, means3D, colors_precomp, phasors_precomp, opacities, scales, rotations,
                     scale_modifier, cov3Ds_precomp, viewmatrix, projmatrix, tanfovx, tanfovy,
                     image_height, image_width, sh, sh_p, degree, campos, prefiltered, debug,
-                    near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset):
+                    near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset,
+                    R_hint=0):
     """Same argument order and 15-tuple result as `_C.rasterize_gaussians`
-    (rasterize_points.cu:35-165)."""
+    (rasterize_points.cu:35-165).
+
+    `R_hint` (not in the reference): an estimate of num_rendered; > 0 selects the library's hinted
+    mode (GftForwardArgs.R_hint) in which the host does not wait for the instance count in the
+    middle of the forward.  Results are identical."""
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -188,6 +193,7 @@ def _native_forward(bg, means3D, colors_precomp, phasors_precomp, opacities, sca
     if P == 0:  # the library still needs valid pointers to validate; nothing is written to them
         a.pixels = planes.data_ptr()
         a.radii = planes.data_ptr()
+    a.R_hint = int(R_hint) if R_hint and R_hint > 0 else 0
 
     ws = _Workspaces(dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -345,6 +351,19 @@ class _NativeModule:
 
 _C = _NativeModule
 
+# Last instance count per (device, P, H, W): the next forward of the same shape is enqueued in one go
+# with a 25 % margin instead of stalling on the count (see GftForwardArgs.R_hint).  GFT_NO_HINT=1
+# restores the reference's exact-size behaviour.
+_R_HISTORY = {}
+
+
+def _r_hint(key):
+    import os
+    if os.environ.get("GFT_NO_HINT") == "1":
+        return 0
+    last = _R_HISTORY.get(key)
+    return 0 if last is None else int(last * 1.25) + 4096
+
 
 # --------------------------------------------------------------------------------------------
 # the reference's public surface
@@ -376,16 +395,20 @@ class _RasterizeGaussians(torch.autograd.Function):
             raster_settings.depth_range, raster_settings.use_view_dependent_phase,
             _as_float(phase_f), _as_float(dc_f),
         )
+        hint_key = (means3D.device.index, int(means3D.shape[0]), int(raster_settings.image_height),
+                    int(raster_settings.image_width))
+        kw = {"R_hint": _r_hint(hint_key)} if _C is _NativeModule else {}
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
-                out = _C.rasterize_gaussians(*args)
+                out = _C.rasterize_gaussians(*args, **kw)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out = _C.rasterize_gaussians(*args)
+            out = _C.rasterize_gaussians(*args, **kw)
+        _R_HISTORY[hint_key] = int(out[0])
         (num_rendered, color, phasor, depth, normal, acc, entropy, depth_distortion,
          amp_distortion, pixels, distribution, radii, geomBuffer, binningBuffer, imgBuffer) = out
 

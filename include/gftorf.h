@@ -95,10 +95,18 @@ typedef struct GftForwardArgs {
   float* pixels;               /* [P]  number of pixels each Gaussian contributed to */
   float* out_distribution;     /* [3,H,W] first hit: alpha, dist, amp */
   int* radii;                  /* [P] */
+
+  /* 0: exact mode (reference behaviour) — the host waits for the instance count R before it sizes
+   * the binning workspace.  > 0: an estimate of R (e.g. 1.25x the previous call's): the workspace
+   * is sized from it, every kernel is enqueued at once and reads R on the device, and the host
+   * learns R afterwards; if R exceeds the estimate the binning callback is called a second time
+   * with the exact size and the tail of the pipeline re-runs.  Results are identical. */
+  int R_hint;
 } GftForwardArgs;
 
 /* Returns num_rendered R (>=0), or <0 on error.  The three callbacks are called exactly once
- * each (geom, img before the first kernel; binning after the tile-count scan). */
+ * each (geom, img before the first kernel; binning after the tile-count scan — a second time
+ * only when R_hint was too small). */
 int gft_forward(const GftForwardArgs* args,
                 gft_alloc_fn geom_alloc, gft_alloc_fn binning_alloc, gft_alloc_fn img_alloc,
                 void* alloc_ctx, gft_stream_t stream);
