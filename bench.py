@@ -108,14 +108,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, interval_ms=100):
+        self.index, self.proc, self.lines, self.interval_ms = index, None, [], interval_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -321,6 +321,9 @@ def run_gpu(args, impl):
             _capi.profile_read(4096)
             _capi.profile_enable(True)
         n0 = _capi.launch_count() if impl == "ours" else 0
+        import gc
+        gc.collect()
+        gc.disable()      # a cyclic-GC pause inside a 2 ms step would be charged to the step
         t0 = time.perf_counter()
         stats = None
         for i in range(K):
@@ -330,26 +333,30 @@ def run_gpu(args, impl):
             evs[i][1].record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
+        gc.enable()
         launches = (_capi.launch_count() - n0) if impl == "ours" else None
         stages = []
         if profile and impl == "ours":
             stages = _capi.profile_read(4096)
             _capi.profile_enable(False)
         ms = [a.elapsed_time(b) for a, b in evs]
+        timed.last_steps = ms
         total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
         return float(total.item()), wall, launches, stages, stats
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local, args.clock_interval_ms)
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     total_ms, wall_ms, launches, stages, stats = timed(step_resident, K, W, profile=True)
-    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sorted(timed.last_steps)
+    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
     if args.resident_only:
         if rank == 0:
             print(json.dumps({"resident_only": True, "ms_per_step": total_ms / K,
+                              "step_ms_min_med_max": [step_ms[0], step_ms[len(step_ms) // 2], step_ms[-1]],
                               "gpu_launches": launches}), flush=True)
         if world > 1:
             dist.destroy_process_group()
@@ -380,6 +387,7 @@ def run_gpu(args, impl):
                    "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
                    "timing": "sum of per-step CUDA-event durations, max over ranks"},
         "fwd_bwd_ms_per_iter": round(total_ms / K, 4),
+        "step_ms_min_med_max": [round(step_ms[0], 4), round(step_ms[len(step_ms) // 2], 4), round(step_ms[-1], 4)],
         "wall_ms_total_incl_flush": round(wall_ms, 2),
         "render_mpix_s": round(mpix * K / (render_ms / 1e3), 3),
         "render_ms_per_step": round(render_ms / K, 4),
@@ -500,6 +508,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the run")
+    ap.add_argument("--clock-interval-ms", type=int, default=100)
     ap.add_argument("--resident-only", action="store_true",
                     help="skip the e2e / render-only / cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()

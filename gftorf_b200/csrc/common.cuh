@@ -213,14 +213,15 @@ __device__ __forceinline__ void warp_stage_out(float* __restrict__ gbase, int nr
 }
 #define GFT_STAGE_FLOATS_PER_WARP (32 * 49)
 
-// Relaxed/acquire 64-bit accesses for the decoupled look-back scan.
+// 64-bit status words of the decoupled look-back scan.  flag and value travel in ONE word, so
+// relaxed gpu-scope accesses suffice (an acquire poll costs an L1 invalidate every time).
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 }  // namespace gft

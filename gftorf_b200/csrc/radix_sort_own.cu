@@ -29,13 +29,16 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PRE = 2u << 30;
 constexpr uint32_t VAL_MASK = (1u << 30) - 1;
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+// The look-back status word carries its payload (flag | count) in the same 32 bits, so relaxed
+// gpu-scope accesses are enough: nothing else has to be ordered after the flag.  (An acquire load
+// costs an L1 invalidate, CCTL.IVALL, on every poll.)
+__device__ __forceinline__ uint32_t ld_status_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_status_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // hist[pass][bin] over all keys; one read of the keys for all passes.
@@ -157,18 +160,29 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
     uint32_t* st = state + (size_t)tile * RS_BINS + d;
     uint32_t excl = 0;
     if (tile == 0) {
-      st_release_u32(st, FLAG_PRE | count);
+      st_status_u32(st, FLAG_PRE | count);
     } else {
-      st_release_u32(st, FLAG_AGG | count);
-      const uint32_t* pv = st - RS_BINS;
-      while (true) {
-        uint32_t v;
-        do { v = ld_acquire_u32(pv); } while ((v & ~VAL_MASK) == 0u);
-        excl += v & VAL_MASK;
-        if (v & FLAG_PRE) break;
-        pv -= RS_BINS;
+      st_status_u32(st, FLAG_AGG | count);
+      // decoupled look-back, 8 predecessor tiles per step: the eight polls are independent loads,
+      // so a step costs one L2 round trip instead of eight
+      int t = (int)tile - 1;
+      bool found = false;
+      while (!found) {
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = (t - i >= 0) ? ld_status_u32(state + (size_t)(t - i) * RS_BINS + d) : FLAG_PRE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!found) {
+            while ((v[i] & ~VAL_MASK) == 0u) v[i] = ld_status_u32(state + (size_t)(t - i) * RS_BINS + d);
+            excl += v[i] & VAL_MASK;
+            if (v[i] & FLAG_PRE) found = true;
+          }
+        }
+        t -= 8;
       }
-      st_release_u32(st, FLAG_PRE | (excl + count));
+      st_status_u32(st, FLAG_PRE | (excl + count));
     }
     // exclusive scan of `count` over the 256 digits
     uint32_t incl = count;
