@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU visit: parity tests, both bench arms, ncu launch list + full capture of one step.
+# usage (from the repo root on the GPU box): bash tools/gpu_round.sh <tag>
+tag=${1:-rX}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -m gpu -q > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
+tail -3 $out/pytest_gpu_$tag.log
+python bench.py --impl reference > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "ref rc=$?"
+python bench.py > $out/bench_ours_$tag.json 2> $out/bench_ours_$tag.err; echo "ours rc=$?"
+cat $out/bench_ours_$tag.json
+python bench.py --resident-only --steps 2 --warmup 3 > $out/plain_$tag.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file $out/launches_$tag.csv python bench.py --resident-only --steps 2 --warmup 3 > $out/ncu_l_$tag.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:gft --launch-skip 84 --launch-count 28 \
+    -o $out/prof_$tag -f python bench.py --resident-only --steps 2 --warmup 3 > $out/ncu_f_$tag.log 2>&1
+echo "full capture rc=$?"
