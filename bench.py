@@ -355,8 +355,12 @@ def run_gpu(args, impl):
     clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
     if args.resident_only:
         if rank == 0:
-            print(json.dumps({"resident_only": True, "ms_per_step": total_ms / K,
-                              "step_ms_min_med_max": [step_ms[0], step_ms[len(step_ms) // 2], step_ms[-1]],
+            share = {}
+            for name, ms in stages:
+                share[name] = share.get(name, 0.0) + ms / K
+            print(json.dumps({"resident_only": True, "ms_per_step": round(total_ms / K, 4),
+                              "step_ms_min_med_max": [round(step_ms[0], 4), round(step_ms[len(step_ms) // 2], 4), round(step_ms[-1], 4)],
+                              "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                               "gpu_launches": launches}), flush=True)
         if world > 1:
             dist.destroy_process_group()

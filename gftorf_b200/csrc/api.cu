@@ -68,6 +68,11 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+namespace gft {
+int set_error(int code, const char* msg) { return fail(code, msg); }   // for the other .cu files
+}  // namespace gft
+namespace {
 
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 

@@ -20,9 +20,13 @@
 //        sum G*dL/dalpha | sum w*g_c[3] | sum w*g_d | sum w*(2z*k2-k1) | sum wp*(gA,gB,gC,gS)
 //     where (gA,gB,gC,gS) are the four linear combinations of the 7 phasor pixel gradients that the
 //     phasor backward consumes (backward.cu:551-577).  15 values instead of 18.
-//   * Warp reduction with a halving butterfly: 16 -> 8 -> 4 -> 2 -> 1 values per lane (15 shuffles)
-//     plus one xor-1 step: 16 shuffles instead of 18*5 = 90.  Value i ends complete in lanes
-//     2i, 2i+1; the even lanes issue ONE reduction instruction onto the Gaussian's 64-byte record.
+//   * Warp reduction of the 15 partials.  Default: a transpose through a warp-private shared
+//     buffer — every lane stores its 15 values down one column (15 STS, conflict-free), lane j sums
+//     half a row with four 128-bit loads + 15 adds, one shuffle joins the halves: ~38 instructions.
+//     Alternative kept for A/B (GFT_BWD_SMEM_REDUCE=0): a halving butterfly 16 -> 8 -> 4 -> 2 -> 1
+//     values per lane (16 shuffles + 32 selects + 16 adds, ~64 instructions; 18*5 = 90 shuffles
+//     for a plain per-value reduction).  Either way value i ends in lanes 2i, 2i+1 and the even
+//     lanes issue ONE reduction instruction onto the Gaussian's 64-byte record.
 //   * a 16x16 tile is walked by 8 warps of 8x4 pixels, 32 Gaussians at a time; a warp skips
 //     Gaussians whose conservative alpha>=1/255 box misses its patch (exact, see blend_fwd.cu);
 //     batches behind the tile's furthest last-contributor are never loaded; the next batch is
@@ -34,13 +38,17 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace gft {
 
 namespace {
 
-constexpr int BATCH = 256;
+constexpr int RED_STRIDE = 36;
+constexpr int RED_FLOATS = 16 * RED_STRIDE;
 
-struct BwdBuf {
+template <int BATCH>
+struct BwdBufT {
   float4 r0[BATCH];  // x y ex ey
   float4 r1[BATCH];  // conA conB conC opacity
   float4 r2[BATCH];  // r g b dist
@@ -58,14 +66,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 }  // namespace
 
-__global__ void __launch_bounds__(GFT_BLOCK, 3)
+// WARPS warps = WARPS 8x4 patches of one tile per block (see blend_fwd.cu), BATCH = 32*WARPS.
+template <int WARPS, int MINB, bool SMEM_REDUCE>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 blend_bwd_kernel(BlendBwdParams p) {
+  constexpr int BATCH = WARPS * 32;
+  constexpr uint32_t SUBS = 8 / WARPS;
+  using BwdBuf = BwdBufT<BATCH>;
   extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
   BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw);
-  __shared__ uint32_t s_wmax[GFT_BLOCK / 32];
+  __shared__ uint32_t s_wmax[WARPS];
+  // SMEM_REDUCE: per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
+  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const uint32_t warp = (blockIdx.x % SUBS) * WARPS + wib;   // patch index within the tile
+  const uint32_t tile = blockIdx.x / SUBS;
   const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
@@ -130,11 +146,11 @@ blend_bwd_kernel(BlendBwdParams p) {
   uint32_t wmax = last_contributor;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s_wmax[warp] = wmax;
+  if (lane == 0) s_wmax[wib] = wmax;
   __syncthreads();
   uint32_t bmax = 0;
 #pragma unroll
-  for (int w = 0; w < GFT_BLOCK / 32; ++w) bmax = max(bmax, s_wmax[w]);
+  for (int w = 0; w < WARPS; ++w) bmax = max(bmax, s_wmax[w]);
   const int n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
 
   float T = T_final;
@@ -219,6 +235,23 @@ blend_bwd_kernel(BlendBwdParams p) {
       v[14] = wp * gS;
     }
 
+    if (SMEM_REDUCE) {
+      // Transpose through shared memory: lane l stores its 15 partials down column l (stride 36:
+      // conflict-free), then lane j sums one half (16 lanes) of row j>>1 with four 128-bit loads
+      // (the 8 lanes of a load phase hit 8 different bank groups) and one shuffle joins the halves.
+#pragma unroll
+      for (int i = 0; i < 15; ++i) red[i * RED_STRIDE + (int)lane] = v[i];
+      __syncwarp();
+      const float4* rp = reinterpret_cast<const float4*>(red + (lane >> 1) * RED_STRIDE + (lane & 1u) * 16u);
+      const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+      float sum = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
+                  (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      __syncwarp();
+      if ((lane & 1u) == 0u && lane != 30u)
+        atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), sum);
+      return;
+    }
     // ---- halving butterfly: value i ends complete in lanes 2i and 2i+1 ---------------------
     float a8[8];
     {
@@ -301,13 +334,46 @@ blend_bwd_kernel(BlendBwdParams p) {
   }
 }
 
+namespace {
+template <int WARPS, int MINB, bool SMEM_REDUCE>
+void launch_bwd_variant(const BlendBwdParams& p, int tiles, cudaStream_t stream) {
+  const int smem = 2 * (int)sizeof(BwdBufT<WARPS * 32>) + (SMEM_REDUCE ? WARPS * RED_FLOATS * 4 : 0);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE>, smem, &smem_ok);
+  blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
+}
+}  // namespace
+
+int blend_block_warps(int tiles) {
+  static const int forced = [] {
+    const char* e = std::getenv("GFT_BLEND_WARPS");
+    const int v = e ? std::atoi(e) : 0;
+    return (v == 8 || v == 4) ? v : 0;
+  }();
+  if (forced) return forced;
+  (void)tiles;
+  return 8;   // measured: 8 / 4 / 2 warps per block within 1 % of each other at 640x480 and 1080p
+}
+
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
-  const int smem = 2 * (int)sizeof(BwdBuf);
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_bwd_kernel, smem, &smem_ok);
-  blend_bwd_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
+  // Measured and rejected on B200 (c2 and c4 workloads): 64-register variants for one more resident
+  // block per SM (+4 %), and sending replays with few contributing pixels straight to the record
+  // with per-lane reductions instead of the butterfly (+4 %).
+  // default: reduce through shared memory (7 % faster than the shuffle butterfly on B200, c2 and
+  // c4 workloads); GFT_BWD_SMEM_REDUCE=0 selects the butterfly for A/B runs
+  static const bool smem_reduce = [] {
+    const char* e = std::getenv("GFT_BWD_SMEM_REDUCE");
+    return !(e && e[0] == '0');
+  }();
+  if (smem_reduce) {
+    if (blend_block_warps(tiles) == 8) launch_bwd_variant<8, 3, true>(p, tiles, stream);
+    else launch_bwd_variant<4, 6, true>(p, tiles, stream);
+  } else {
+    if (blend_block_warps(tiles) == 8) launch_bwd_variant<8, 3, false>(p, tiles, stream);
+    else launch_bwd_variant<4, 6, false>(p, tiles, stream);
+  }
   note_launches(1);
 }
 

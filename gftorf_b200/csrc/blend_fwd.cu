@@ -26,9 +26,13 @@ namespace gft {
 
 namespace {
 
-constexpr int BATCH = 256;
-
-struct FwdBuf {
+// A block is WARPS warps = WARPS 8x4 patches of one 16x16 tile (8 = the whole tile, 4 = a 16x8
+// half, 2 = a 16x4 quarter) and stages BATCH = 32*WARPS Gaussians at a time, one per thread.
+// Sub-tile blocks exist for load balance: at 640x480 there are only 1200 tiles for 148 SMs
+// (8.1 per SM -> the last round runs 10 % full); 2400 half tiles quantise twice as finely, and the
+// block-wide early-termination / furthest-contributor bounds get tighter.
+template <int BATCH>
+struct FwdBufT {
   float4 r0[BATCH];  // x y ex ey
   float4 r1[BATCH];  // conA conB conC opacity
   float4 r2[BATCH];  // r g b dist
@@ -47,12 +51,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 }  // namespace
 
-__global__ void __launch_bounds__(GFT_BLOCK, 4)
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 blend_fwd_kernel(BlendFwdParams p) {
+  constexpr int BATCH = WARPS * 32;
+  constexpr uint32_t SUBS = 8 / WARPS;     // blocks per tile
+  using FwdBuf = FwdBufT<BATCH>;
   extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
   FwdBuf* buf = reinterpret_cast<FwdBuf*>(fwd_smem_raw);
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint32_t warp = (blockIdx.x % SUBS) * WARPS + (tid >> 5);   // patch index within the tile
+  const uint32_t tile = blockIdx.x / SUBS;
   const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
   // warp patch: 8 wide x 4 high
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
@@ -257,13 +266,23 @@ blend_fwd_kernel(BlendFwdParams p) {
   }
 }
 
+namespace {
+template <int WARPS, int MINB>
+void launch_fwd_variant(const BlendFwdParams& p, int tiles, cudaStream_t stream) {
+  const int smem = 2 * (int)sizeof(FwdBufT<WARPS * 32>);
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(blend_fwd_kernel<WARPS, MINB>, smem, &smem_ok);
+  blend_fwd_kernel<WARPS, MINB><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
+}
+}  // namespace
+
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
-  const int smem = 2 * (int)sizeof(FwdBuf);
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_fwd_kernel, smem, &smem_ok);
-  blend_fwd_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
+  switch (blend_block_warps(tiles)) {
+    case 8: launch_fwd_variant<8, 4>(p, tiles, stream); break;
+    default: launch_fwd_variant<4, 8>(p, tiles, stream); break;
+  }
   note_launches(1);
 }
 

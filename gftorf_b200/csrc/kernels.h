@@ -21,6 +21,13 @@ inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_ma
   __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
 }
 
+// Records the thread-local error string behind gft_last_error() and returns `code` (api.cu).
+int set_error(int code, const char* msg);
+
+// Warps per blend block (8 = a whole 16x16 tile, 4 = a 16x8 half, 2 = a 16x4 quarter); see
+// blend_fwd.cu.  GFT_BLEND_WARPS overrides the choice (for A/B measurements).
+int blend_block_warps(int tiles);
+
 struct PreprocessParams {
   int P, D, M, M_p;
   int W, H, grid_x, grid_y, num_tiles;

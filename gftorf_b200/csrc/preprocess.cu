@@ -114,15 +114,15 @@ __device__ __forceinline__ void eval_sh_pa(int D, const float* sp, const float* 
 __global__ void __launch_bounds__(GFT_BLOCK)
 preprocess_fwd_kernel(PreprocessParams p) {
   extern __shared__ float fwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
-  __shared__ uint32_t s_vbid;
   __shared__ uint32_t s_warp_tot[GFT_BLOCK / 32];
   __shared__ uint32_t s_prefix;
 
-  // Dynamic block id: a block only ever waits on blocks that already hold a ticket, so the
-  // look-back below cannot deadlock whatever order the hardware schedules blocks in.
-  if (threadIdx.x == 0) s_vbid = atomicAdd(p.scan_ticket, 1u);
-  __syncthreads();
-  const uint32_t vb = s_vbid;
+  // Block id = blockIdx.x, as in cub::DeviceScan: a block publishes its aggregate right after
+  // phase 1 and only looks back at its very end, when every lower-numbered block has long been
+  // dispatched (blocks are dispatched in index order), so the look-back practically never waits.
+  // (A ticket counter would make the order explicit, but its atomic round trip stalls the whole
+  // block before any work can start: ncu showed 8.5 warps per issue waiting at barriers.)
+  const uint32_t vb = blockIdx.x;
   const int idx = (int)(vb * GFT_BLOCK + threadIdx.x);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
@@ -203,6 +203,30 @@ preprocess_fwd_kernel(PreprocessParams p) {
     if (!alive) { tiles = 0; radius_i = 0; }
     p.radii[idx] = radius_i;
     p.tiles_touched[idx] = tiles;
+  }
+
+  // ---- block-wide inclusive scan of `tiles` ------------------------------------------------
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += n;
+  }
+  if (lane == 31) s_warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t warp_base = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < GFT_BLOCK / 32; ++w) {
+    const uint32_t t = s_warp_tot[w];
+    if ((uint32_t)w < warp) warp_base += t;
+    block_total += t;
+  }
+  incl += warp_base;
+
+  // publish this block's aggregate now; the look-back happens after the appearance work
+  if (warp == 0 && lane == 0) {
+    if (vb == 0) st_release_u64(p.scan_state, (2ull << 32) | block_total);
+    else st_release_u64(p.scan_state + vb, (1ull << 32) | block_total);
   }
 
   // ---- phase 2: appearance.  The SH rows of a warp's 32 consecutive Gaussians are one contiguous
@@ -358,33 +382,12 @@ preprocess_fwd_kernel(PreprocessParams p) {
     reinterpret_cast<uint2*>(p.rect)[idx] = make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
   }
 
-  // ---- block-wide inclusive scan of `tiles` ------------------------------------------------
-  uint32_t incl = tiles;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (uint32_t)o) incl += n;
-  }
-  if (lane == 31) s_warp_tot[warp] = incl;
-  __syncthreads();
-  uint32_t warp_base = 0, block_total = 0;
-#pragma unroll
-  for (int w = 0; w < GFT_BLOCK / 32; ++w) {
-    const uint32_t t = s_warp_tot[w];
-    if ((uint32_t)w < warp) warp_base += t;
-    block_total += t;
-  }
-  incl += warp_base;
-
   // ---- chained scan across blocks: status word = flag<<32 | value --------------------------
   // flag 1 = block aggregate available, 2 = inclusive prefix available.
   if (warp == 0) {
     unsigned long long* st = p.scan_state;
     uint32_t excl = 0;
-    if (vb == 0) {
-      if (lane == 0) st_release_u64(st, (2ull << 32) | block_total);
-    } else {
-      if (lane == 0) st_release_u64(st + vb, (1ull << 32) | block_total);
+    if (vb != 0) {
       int base = (int)vb - 1;
       while (true) {
         const int j = base - (int)lane;

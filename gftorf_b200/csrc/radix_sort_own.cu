@@ -25,6 +25,7 @@ constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 pairs per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 
+constexpr int RS_LOOKBACK = 8;
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PRE = 2u << 30;
 constexpr uint32_t VAL_MASK = (1u << 30) - 1;
@@ -163,24 +164,26 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
       st_status_u32(st, FLAG_PRE | count);
     } else {
       st_status_u32(st, FLAG_AGG | count);
-      // decoupled look-back, 8 predecessor tiles per step: the eight polls are independent loads,
-      // so a step costs one L2 round trip instead of eight
+      // decoupled look-back, RS_LOOKBACK predecessor tiles per step: the polls are independent
+      // loads, so a step costs one L2 round trip.  (At R ~ 1e6 the whole grid is one wave, so a
+      // tile may have to walk back over every tile before it: the walk, not bandwidth, sets the
+      // duration of a pass.)
       int t = (int)tile - 1;
       bool found = false;
       while (!found) {
-        uint32_t v[8];
+        uint32_t v[RS_LOOKBACK];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RS_LOOKBACK; ++i)
           v[i] = (t - i >= 0) ? ld_status_u32(state + (size_t)(t - i) * RS_BINS + d) : FLAG_PRE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RS_LOOKBACK; ++i) {
           if (!found) {
             while ((v[i] & ~VAL_MASK) == 0u) v[i] = ld_status_u32(state + (size_t)(t - i) * RS_BINS + d);
             excl += v[i] & VAL_MASK;
             if (v[i] & FLAG_PRE) found = true;
           }
         }
-        t -= 8;
+        t -= RS_LOOKBACK;
       }
       st_status_u32(st, FLAG_PRE | (excl + count));
     }

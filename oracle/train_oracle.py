@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the PyTorch operator chains that sit either side
+of the rasterizer in the reference's training iteration.  The reference implements
+these steps in Python/PyTorch, so the restatement is PyTorch too (fp32, CPU or any device), written
+from the cited lines; autograd through it IS the reference's backward.
+
+  assemble()      gaussian_renderer/__init__.py:81-105 + scene/gaussian_model.py:35-43,123-157
+  loss_term()     utils/loss_utils.py:17-33 (l1 / l2 / weighted variants), :70-114 (SSIM),
+                  combined as in train.py:204-223
+  adam_step()     torch.optim.Adam as configured at scene/gaussian_model.py:272
+                  (lr per group, betas (0.9, 0.999), eps 1e-15, no weight decay, no amsgrad) —
+                  a third-party algorithm (PyTorch, pinned 1.12.1 in the reference's
+                  environment.yml:11); restated in numpy from the published update rule and pinned
+                  against torch.optim.Adam of this image in tests/test_train_ops.py.
+
+Only tests/, __graft_entry__.smoke() and bench.py may import this module.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ---- f1 -----------------------------------------------------------------------------------------
+def assemble(raw, motion_mask=None, deltas=None, isotropic=False, render_regions=("static", "dynamic")):
+    """Returns the six rasterizer inputs.  `raw` holds the GaussianModel's parameters
+    (xyz, opacity_raw, scaling_raw, rotation_raw, f_dc_color, f_rest_color, f_dc_phase,
+    f_rest_phase, f_dc_amp, f_rest_amp); `deltas` the deformation outputs in masked order."""
+    deltas = deltas or {}
+    xyz = raw["xyz"]
+    P = xyz.shape[0]
+    if motion_mask is None:
+        motion_mask = torch.zeros(P, dtype=torch.bool, device=xyz.device)
+    # the model's getters (gaussian_model.py:123-157)
+    scaling = torch.exp(raw["scaling_raw"].repeat(1, 3) if isotropic else raw["scaling_raw"])
+    opacity = torch.sigmoid(raw["opacity_raw"])
+    feat_color = torch.cat((raw["f_dc_color"], raw["f_rest_color"]), dim=1)
+    feat_phasor = torch.cat((torch.cat((raw["f_dc_phase"], raw["f_dc_amp"]), dim=-1),
+                             torch.cat((raw["f_rest_phase"], raw["f_rest_amp"]), dim=-1)), dim=1)
+    out = dict(means3D=torch.zeros_like(xyz), opacities=torch.zeros_like(opacity),
+               scales=torch.zeros_like(scaling), rotations=torch.zeros_like(raw["rotation_raw"]),
+               shs=torch.zeros_like(feat_color), shs_p=torch.zeros_like(feat_phasor))
+    m = motion_mask
+    if "static" in render_regions:       # __init__.py:81-88
+        out["means3D"][~m] = xyz[~m]
+        out["opacities"][~m] = opacity[~m]
+        out["scales"][~m] = scaling[~m]
+        out["rotations"][~m] = F.normalize(raw["rotation_raw"])[~m]
+        out["shs"][~m] = feat_color[~m]
+        out["shs_p"][~m] = feat_phasor[~m]
+    if "dynamic" in render_regions:      # __init__.py:89-96
+        zero = lambda t: 0.0 if t is None else t
+        out["means3D"][m] = xyz[m] + zero(deltas.get("d_xyz"))
+        out["opacities"][m] = opacity[m]
+        out["scales"][m] = scaling[m]
+        out["rotations"][m] = F.normalize(raw["rotation_raw"][m] + zero(deltas.get("d_rot")))
+        out["shs"][m] = feat_color[m] + zero(deltas.get("d_sh"))
+        out["shs_p"][m] = feat_phasor[m] + zero(deltas.get("d_sh_p"))
+    return out
+
+
+# ---- f3 -----------------------------------------------------------------------------------------
+def _window(channels, size=11, sigma=1.5):
+    g = torch.tensor([math.exp(-(x - size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(size)])
+    g = g / g.sum()
+    w2 = g.unsqueeze(1).mm(g.unsqueeze(0)).float()
+    return w2.expand(channels, 1, size, size).contiguous()
+
+
+def ssim(img1, img2, size=11):
+    """loss_utils.py:84-114 with size_average=True; inputs [C,H,W]."""
+    C = img1.shape[-3]
+    win = _window(C, size).to(img1)
+    conv = lambda t: F.conv2d(t, win, padding=size // 2, groups=C)
+    mu1, mu2 = conv(img1), conv(img2)
+    s11 = conv(img1 * img1) - mu1 * mu1
+    s22 = conv(img2 * img2) - mu2 * mu2
+    s12 = conv(img1 * img2) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m = ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s11 + s22 + C2))
+    return m.mean()
+
+
+def elementwise_term(img, gt, kind, w=0.0, nch=None):
+    if kind == "l1":                      # :17-18
+        return (img - gt).abs().mean()
+    if kind == "l2":                      # :20-21
+        return ((img - gt) ** 2).mean()
+    if kind == "weighted_l1":             # :23-25
+        n = img.shape[0] if nch is None else nch
+        weight = w + torch.sqrt(torch.sum(img ** 2, dim=0)).detach()
+        return ((img[:n] - gt[:n]) / weight).abs().mean()
+    if kind == "weighted_l1_quad":        # :27-29
+        weight = w + img.detach().abs()
+        return ((img - gt) / weight).abs().mean()
+    if kind == "weighted_l2_quad":        # :31-33
+        weight = w + img.detach().abs()
+        return torch.square((img - gt) / weight).mean()
+    raise ValueError(kind)
+
+
+def loss_term(img, gt, kind="l1", lam=1.0, lambda_dssim=0.2, w=0.0, nch=None):
+    """train.py:204-223: lam * ((1 - lambda_dssim) * L + lambda_dssim * (1 - ssim))."""
+    L = elementwise_term(img, gt, kind, w, nch)
+    if lambda_dssim == 0.0:
+        return lam * L
+    return lam * ((1.0 - lambda_dssim) * L + lambda_dssim * (1.0 - ssim(img, gt)))
+
+
+def ssim_bruteforce(img1, img2, size=11, sigma=1.5):
+    """Independent pin for ssim(): explicit loops over pixels and taps, float64, zero padding."""
+    a, b = img1.double().numpy(), img2.double().numpy()
+    C, H, W = a.shape
+    g = np.array([math.exp(-(x - size // 2) ** 2 / (2 * sigma ** 2)) for x in range(size)])
+    g = g / g.sum()
+    h = size // 2
+    tot = 0.0
+    for c in range(C):
+        for y in range(H):
+            for x in range(W):
+                mu1 = mu2 = xx = yy = xy = 0.0
+                for dy in range(-h, h + 1):
+                    for dx in range(-h, h + 1):
+                        yy_, xx_ = y + dy, x + dx
+                        if 0 <= yy_ < H and 0 <= xx_ < W:
+                            wgt = g[dy + h] * g[dx + h]
+                            u, v = a[c, yy_, xx_], b[c, yy_, xx_]
+                            mu1 += wgt * u; mu2 += wgt * v
+                            xx += wgt * u * u; yy += wgt * v * v; xy += wgt * u * v
+                s1, s2, s12 = xx - mu1 * mu1, yy - mu2 * mu2, xy - mu1 * mu2
+                tot += ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+    return tot / (C * H * W)
+
+
+# ---- f4 -----------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-15):
+    """One Adam update on float32 numpy arrays, in place; `step` counts from 1.
+    m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2;
+    p <- p - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)."""
+    f = np.float32
+    m += (g - m) * f(1.0 - beta1)
+    v *= f(beta2)
+    v += f(1.0 - beta2) * g * g
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    denom = np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)
+    p += f(-(lr / bc1)) * (m / denom)

@@ -335,7 +335,8 @@ def test_subtile_culling_is_exact():
             if x is None:
                 continue
             err = float((x.double() - y.double()).norm())
-            assert err <= 1e-5 * max(float(y.double().norm()), 1e-2 * scale)
+            # two runs differ by the order of the floating-point atomics only
+            assert err <= harness.GRAD_REL_L2 * max(float(y.double().norm()), 1e-2 * scale)
 
 
 def test_debug_mode_runs():
@@ -527,15 +528,15 @@ def test_accumulate_mode_adds_views_into_the_bucket():
         f = harness.call_forward(rasterizer._C, inp)
         plain.append(harness.call_backward(rasterizer._C, inp, f))
         acc = harness.call_backward(rasterizer._C, inp, f, grad_out=go)
-        assert harness.rel_l2(acc[0], plain[-1][0]) <= 1e-6       # means2D stays per view
+        assert harness.rel_l2(acc[0], plain[-1][0]) <= harness.GRAD_REL_L2   # means2D stays per view (atomic order differs)
         vis = (f[11] > 0) if vis is None else (vis | (f[11] > 0))
     pairs = dict(means3D=4, shs=6, shs_p=7, opacities=3, scales=8, rotations=9)
     for name, i in pairs.items():
         expect = plain[0][i] + plain[1][i]
-        assert harness.rel_l2(go[name], expect) <= 2e-5, name
+        assert harness.rel_l2(go[name], expect) <= harness.GRAD_REL_L2, name
         assert float(go[name][~vis].abs().sum()) == 0.0, name
-    assert harness.rel_l2(go["phase_offset"], plain[0][10] + plain[1][10]) <= 1e-5
-    assert harness.rel_l2(go["dc_offset"], plain[0][11] + plain[1][11]) <= 1e-5
+    assert harness.rel_l2(go["phase_offset"], plain[0][10] + plain[1][10]) <= harness.GRAD_REL_L2
+    assert harness.rel_l2(go["dc_offset"], plain[0][11] + plain[1][11]) <= harness.GRAD_REL_L2
     assert bucket.flat.data_ptr() == go["means3D"].data_ptr()
 
 

@@ -1,0 +1,283 @@
+"""The §8f operators (assembly, fused loss, flat Adam): oracle pins on CPU, parity on the GPU.
+
+CPU part: the restated oracle (oracle/train_oracle.py) is pinned against independent computations —
+torch.optim.Adam itself, a brute-force SSIM, and hand-derived gradients.  GPU part (-m gpu): the
+CUDA kernels behind include/gftorf_train.h against that oracle and its autograd, through the C ABI.
+Tolerances are floating point: 1e-6 relative for streaming arithmetic, 2e-5 for SSIM (separable
+vs 2-D window summation order)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------
+# inputs
+# ------------------------------------------------------------------------------------------------
+def make_raw(P, M=16, isotropic=False, seed=0, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    raw = dict(xyz=r(P, 3), opacity_raw=r(P, 1) * 2, scaling_raw=r(P, 1 if isotropic else 3) * 0.5 - 2,
+               rotation_raw=r(P, 4), f_dc_color=r(P, 1, 3), f_rest_color=r(P, M - 1, 3) * 0.1,
+               f_dc_phase=r(P, 1, 1), f_rest_phase=r(P, M - 1, 1) * 0.1, f_dc_amp=r(P, 1, 1),
+               f_rest_amp=r(P, M - 1, 1) * 0.1)
+    return {k: v.to(device) for k, v in raw.items()}
+
+
+def make_deltas(Nd, M=16, seed=1, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g) * 0.05
+    return {k: v.to(device) for k, v in dict(d_xyz=r(Nd, 3), d_rot=r(Nd, 4), d_sh=r(Nd, M, 3), d_sh_p=r(Nd, M, 2)).items()}
+
+
+def rel(a, b):
+    if b is None:               # autograd reports "input unused" as None; the kernels write zeros
+        b = torch.zeros_like(a)
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: the oracle is pinned
+# ------------------------------------------------------------------------------------------------
+def test_adam_restatement_matches_torch_optim_adam():
+    torch.manual_seed(0)
+    shapes, lrs = [(1000, 3), (1000, 15, 3), (1000, 1), (7,)], [1.6e-4, 1.25e-4, 0.05, 0.0]
+    params = [torch.randn(s) for s in shapes]
+    tp = [p.clone().requires_grad_(True) for p in params]
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(tp, lrs)], lr=0.0, eps=1e-15)
+    npp = [p.numpy().copy() for p in params]
+    m = [np.zeros_like(a) for a in npp]
+    v = [np.zeros_like(a) for a in npp]
+    for step in range(1, 8):
+        grads = [torch.randn(s) * (10.0 ** -(step % 4)) for s in shapes]
+        for p, g in zip(tp, grads):
+            p.grad = g.clone()
+        opt.step()
+        for a, g, mm, vv, lr in zip(npp, grads, m, v, lrs):
+            orc.adam_step(a, g.numpy(), mm, vv, lr, step)
+    for a, p, lr in zip(npp, tp, lrs):
+        assert rel(torch.from_numpy(a), p.detach()) < 2e-7
+        if lr == 0.0:
+            assert np.array_equal(a, p.detach().numpy())   # lr 0: the parameter must not move
+
+
+def test_ssim_restatement_matches_bruteforce():
+    torch.manual_seed(1)
+    a, b = torch.rand(2, 13, 17), torch.rand(2, 13, 17)
+    assert abs(float(orc.ssim(a, b)) - orc.ssim_bruteforce(a, b)) < 2e-6
+    assert abs(float(orc.ssim(a, a)) - 1.0) < 1e-6
+
+
+def test_assemble_restatement_semantics():
+    raw = make_raw(50)
+    mask = torch.zeros(50, dtype=torch.bool)
+    mask[::3] = True
+    d = make_deltas(int(mask.sum()))
+    o = orc.assemble(raw, mask, d)
+    assert torch.allclose(o["rotations"].norm(dim=1), torch.ones(50), atol=1e-6)
+    assert torch.equal(o["shs"][~mask][:, 0], raw["f_dc_color"][~mask][:, 0])
+    assert torch.allclose(o["means3D"][mask], raw["xyz"][mask] + d["d_xyz"])
+    only_static = orc.assemble(raw, mask, d, render_regions=("static",))
+    assert float(only_static["means3D"][mask].abs().max()) == 0.0 and float(only_static["opacities"][mask].abs().max()) == 0.0
+    iso = orc.assemble(make_raw(8, isotropic=True), None, None, isotropic=True)
+    assert torch.equal(iso["scales"][:, 0], iso["scales"][:, 2])
+
+
+def test_train_header_symbols_are_exported():
+    src = open(os.path.join(ROOT, "include", "gftorf_train.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(gft_[a-z0-9_]+)\s*\(", src)))
+    assert names == ["gft_adam_step", "gft_assemble_backward", "gft_assemble_forward", "gft_fused_loss",
+                     "gft_fused_loss_scratch_bytes"]
+    from gftorf_b200 import _capi
+    lib = C.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_train_ctypes_structs_match_the_c_layout(tmp_path):
+    import subprocess
+    from gftorf_b200 import train_ops as T
+    structs = {"GftAssembleArgs": T.GftAssembleArgs, "GftAssembleGrads": T.GftAssembleGrads,
+               "GftLossArgs": T.GftLossArgs, "GftAdamArgs": T.GftAdamArgs, "GftAdamSegment": T.GftAdamSegment}
+    cname = lambda f: "lambda" if f == "lambda_" else f
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gftorf_train.h"', "int main(void){"]
+    for s, cls in structs.items():
+        lines.append(f'printf("{s} %zu\\n", sizeof({s}));')
+        for f, *_ in cls._fields_:
+            lines.append(f'printf("{s}.{f} %zu\\n", offsetof({s}, {cname(f)}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for s, cls in structs.items():
+        assert int(out[s]) == C.sizeof(cls), s
+        for f, *_ in cls._fields_:
+            assert int(out[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)
+
+
+def test_train_ops_refuse_cpu_tensors():
+    from gftorf_b200 import train_ops as T
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.fused_loss(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.assemble_gaussians(make_raw(4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.FlatAdam([("xyz", torch.zeros(4, 3), 1e-3)])
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: parity through the C ABI
+# ------------------------------------------------------------------------------------------------
+ASM_CASES = [
+    dict(P=1, mask=None, iso=False, regions=("static", "dynamic")),
+    dict(P=1000, mask=None, iso=False, regions=("static", "dynamic")),
+    dict(P=777, mask=3, iso=False, regions=("static", "dynamic")),
+    dict(P=777, mask=3, iso=False, regions=("static",)),
+    dict(P=777, mask=2, iso=True, regions=("dynamic",)),
+    dict(P=5000, mask=1, iso=False, regions=("static", "dynamic")),   # every Gaussian dynamic
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ASM_CASES)
+def test_assemble_forward_backward_vs_oracle(case):
+    from gftorf_b200 import train_ops as T
+    P = case["P"]
+    raw_c = make_raw(P, isotropic=case["iso"], seed=P)
+    mask = None
+    deltas_c = None
+    if case["mask"]:
+        mask = torch.zeros(P, dtype=torch.bool)
+        mask[::case["mask"]] = True
+        deltas_c = make_deltas(int(mask.sum()), seed=P + 1)
+    # oracle with autograd
+    leaves = {k: v.clone().requires_grad_(True) for k, v in raw_c.items()}
+    dl = {k: v.clone().requires_grad_(True) for k, v in deltas_c.items()} if deltas_c else None
+    o = orc.assemble(leaves, mask, dl, case["iso"], case["regions"])
+    gouts = {k: torch.randn(v.shape, generator=torch.Generator().manual_seed(7 + i)) for i, (k, v) in enumerate(o.items())}
+    torch.autograd.backward([o[k] for k in T.OUT_NAMES], [gouts[k] for k in T.OUT_NAMES])
+    # product
+    raw_g = {k: v.cuda().requires_grad_(True) for k, v in raw_c.items()}
+    dg = {k: v.cuda().requires_grad_(True) for k, v in deltas_c.items()} if deltas_c else None
+    dyn = T.dyn_index_from_mask(mask.cuda()) if mask is not None else None
+    og = T.assemble_gaussians(raw_g, dyn, dg, case["iso"], case["regions"])
+    torch.autograd.backward([og[k] for k in T.OUT_NAMES], [gouts[k].cuda() for k in T.OUT_NAMES])
+    for k in T.OUT_NAMES:
+        assert og[k].shape == o[k].shape
+        assert rel(og[k], o[k].detach()) < 1e-6, k
+    for k in raw_c:
+        assert rel(raw_g[k].grad, leaves[k].grad) < 2e-6, k
+    if dl:
+        for k in dl:
+            assert rel(dg[k].grad, dl[k].grad) < 2e-6, k
+
+
+LOSS_CASES = [
+    dict(C=3, H=48, W=64, kind="l1", lam=1.0, ld=0.2),
+    dict(C=3, H=37, W=53, kind="l1", lam=0.7, ld=0.2),            # ragged tiles
+    dict(C=3, H=40, W=40, kind="weighted_l1", lam=1.0, ld=0.2, w=0.01),
+    dict(C=7, H=33, W=20, kind="weighted_l1", lam=2.0, ld=0.0, w=0.1, nch=2),
+    dict(C=1, H=64, W=48, kind="weighted_l2_quad", lam=1.5, ld=0.2, w=0.05),
+    dict(C=1, H=30, W=31, kind="weighted_l1_quad", lam=1.0, ld=0.1, w=0.05),
+    dict(C=1, H=16, W=16, kind="l2", lam=1.0, ld=0.0),
+    dict(C=2, H=5, W=7, kind="l2", lam=1.0, ld=0.5),              # smaller than the window
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", LOSS_CASES)
+def test_fused_loss_value_and_gradient_vs_oracle(case):
+    from gftorf_b200 import train_ops as T
+    g = torch.Generator().manual_seed(case["H"] * 100 + case["W"])
+    img = torch.rand(case["C"], case["H"], case["W"], generator=g) + 0.05
+    gt = (img + 0.2 * torch.randn(img.shape, generator=g)).clamp(0, 1.2)
+    kw = dict(kind=case["kind"], lam=case["lam"], lambda_dssim=case["ld"], w=case.get("w", 0.0), nch=case.get("nch"))
+    leaf = img.clone().requires_grad_(True)
+    ref = orc.loss_term(leaf, gt, **kw)
+    ref.backward()
+    loss, grad = T.fused_loss(img.cuda(), gt.cuda(), **kw)
+    assert abs(float(loss) - float(ref)) <= 2e-5 * max(abs(float(ref)), 1e-3)
+    assert rel(grad, leaf.grad) < 3e-5
+    # the value accumulates into a caller-supplied scalar
+    acc = torch.full((1,), 2.0, device="cuda")
+    T.fused_loss(img.cuda(), gt.cuda(), loss_out=acc, **kw)
+    assert abs(float(acc) - 2.0 - float(ref)) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_fused_loss_full_size_properties():
+    """640x480 (BASELINE configs[1]): identical images give zero loss and zero gradient; the
+    gradient of an L2-only term is exactly linear in the difference."""
+    from gftorf_b200 import train_ops as T
+    img = torch.rand(3, 480, 640, device="cuda")
+    loss, grad = T.fused_loss(img, img.clone(), kind="l1", lambda_dssim=0.2)
+    assert abs(float(loss)) < 1e-6 and float(grad.abs().max()) < 1e-9
+    gt = torch.rand_like(img)
+    _, g1 = T.fused_loss(img, gt, kind="l2", lambda_dssim=0.0)
+    assert rel(g1, 2 * (img - gt) / img.numel()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_flat_adam_vs_torch_optim_adam_and_oracle():
+    from gftorf_b200 import train_ops as T
+    torch.manual_seed(3)
+    names = ["xyz", "f_dc_color", "f_rest_color", "opacity", "scaling", "rotation", "phase_offset"]
+    shapes = [(2001, 3), (2001, 1, 3), (2001, 15, 3), (2001, 1), (2001, 3), (2001, 4), (1,)]
+    lrs = [1.6e-4, 2.5e-3, 1.25e-4, 0.05, 5e-3, 1e-3, 0.0]
+    init = [torch.randn(s) for s in shapes]
+    tp = [p.clone().requires_grad_(True) for p in init]
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(tp, lrs)], lr=0.0, eps=1e-15)
+    fa = T.FlatAdam([(n, p.cuda(), lr) for n, p, lr in zip(names, init, lrs)])
+    npp = [p.numpy().copy() for p in init]
+    m = [np.zeros_like(a) for a in npp]
+    v = [np.zeros_like(a) for a in npp]
+    for step in range(1, 7):
+        grads = [torch.randn(s) * 10.0 ** -(step % 3) for s in shapes]
+        if step == 4:                      # a learning-rate change between steps (update_learning_rate)
+            lrs[0] = 8e-5
+            opt.param_groups[0]["lr"] = lrs[0]
+            fa.set_lr("xyz", lrs[0])
+        for p, g, n in zip(tp, grads, names):
+            p.grad = g.clone()
+            fa.params[n].grad.copy_(g.cuda())
+        opt.step()
+        fa.step(zero_grad=True)
+        for a, g, mm, vv, lr in zip(npp, grads, m, v, lrs):
+            orc.adam_step(a, g.numpy(), mm, vv, lr, step)
+        assert float(fa.grad.abs().max()) == 0.0       # zero_grad fused into the step
+    for n, p, a, lr in zip(names, tp, npp, lrs):
+        ours = fa.params[n].detach().cpu()
+        assert rel(ours, p.detach()) < 3e-7, n
+        assert rel(ours, torch.from_numpy(a)) < 3e-7, n
+        if lr == 0.0:
+            assert torch.equal(ours, p.detach()), n
+
+
+@pytest.mark.gpu
+def test_flat_adam_full_size_is_a_pure_function_of_its_inputs():
+    """P = 300k, 91 floats per Gaussian (BASELINE configs[1]): two independent runs of the same
+    three steps give bit-identical parameters (no atomics, no ordering dependence)."""
+    from gftorf_b200 import train_ops as T
+    P = 300000
+    res = []
+    for _ in range(2):
+        torch.manual_seed(11)
+        groups = [("xyz", torch.randn(P, 3, device="cuda"), 1.6e-4), ("f_rest_color", torch.randn(P, 45, device="cuda"), 1e-4),
+                  ("rest", torch.randn(P, 43, device="cuda"), 1e-3)]
+        fa = T.FlatAdam(groups)
+        for s in range(3):
+            fa.grad.copy_(torch.randn(fa.grad.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(s)))
+            fa.step()
+        res.append(fa.flat.clone())
+    assert torch.equal(res[0], res[1])
