@@ -447,6 +447,7 @@ def run_gpu(args, impl):
                                      "V": Vs, "R": Rs}
             line["stage_ms_per_step"] = {k: round(v, 4) for k, v in sorted(step_share.items(), key=lambda kv: -kv[1])}
         if world == 1:
+            line["next_rows"] = next_rows_bench(P, views[0]["H"], views[0]["W"], dev, flush, peak)
             line["cpu_baseline"] = cpu_baseline(args, wl, bound_s=20.0)
     else:
         line["impl"] = "reference"
@@ -457,6 +458,101 @@ def run_gpu(args, impl):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+def next_rows_bench(P, H, W, dev, flush, peak_gbs, iters=20):
+    """SURVEY §8f rows built so far (f1 assembly, f3 loss, f4 Adam) at the bench workload's size:
+    ms per call of the fused CUDA operator (CUDA events, L2 flushed between calls), its
+    algorithmic bytes against the HBM peak, and the reference's own implementation of the same step
+    — its PyTorch operator chain (oracle/train_oracle.py restates it line for line) — on the same
+    GPU.  Reported beside the headline metric, not part of it."""
+    from gftorf_b200 import train_ops as T
+    from oracle import train_oracle as orc
+    import test_train_ops as tt
+
+    def time_ms(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    out = {}
+    # ---- f1: 25 % of the Gaussians dynamic, deformation outputs present ------------------------
+    raw = {k: v.to(dev).requires_grad_(True) for k, v in tt.make_raw(P, seed=5).items()}
+    mask = torch.zeros(P, dtype=torch.bool, device=dev)
+    mask[::4] = True
+    Nd = int(mask.sum())
+    deltas = {k: v.to(dev).requires_grad_(True) for k, v in tt.make_deltas(Nd, seed=6).items()}
+    dyn = T.dyn_index_from_mask(mask)
+    gouts = None
+
+    def asm_ours():
+        o = T.assemble_gaussians(raw, dyn, deltas)
+        nonlocal gouts
+        if gouts is None:
+            gouts = [torch.randn_like(o[k]) for k in T.OUT_NAMES]
+        torch.autograd.backward([o[k] for k in T.OUT_NAMES], gouts, inputs=list(raw.values()) + list(deltas.values()))
+
+    def asm_ref():
+        o = orc.assemble(raw, mask, deltas)
+        torch.autograd.backward([o[k] for k in T.OUT_NAMES], gouts, inputs=list(raw.values()) + list(deltas.values()))
+
+    def clear():
+        for t in list(raw.values()) + list(deltas.values()):
+            t.grad = None
+
+    t_o = time_ms(lambda: (clear(), asm_ours()))
+    t_r = time_ms(lambda: (clear(), asm_ref()))
+    byts = (91 * 4 * 2) * P + 91 * 4 * Nd + (91 * 4 * 2 + 48) * P + 91 * 4 * Nd   # fwd in+out (+deltas), bwd in+saved+out (+delta grads)
+    out["f1_assemble_fwd_bwd"] = {"ms": round(t_o, 4), "reference_torch_ms": round(t_r, 4),
+                                  "algorithmic_bytes": int(byts), "achieved_gbs": round(byts / t_o / 1e6, 1),
+                                  "hbm_frac": round(byts / t_o / 1e6 / peak_gbs, 4),
+                                  "workload": f"P={P}, 25% dynamic, sh_degree 3 (incl. autograd bookkeeping)"}
+    del raw, deltas, gouts
+    # ---- f3: colour loss (l1 + ssim) on the colour view ----------------------------------------
+    img = torch.rand(3, H, W, device=dev)
+    gt = torch.rand(3, H, W, device=dev)
+
+    def loss_ref():
+        leaf = img.detach().requires_grad_(True)
+        orc.loss_term(leaf, gt, "l1", 1.0, 0.2).backward()
+
+    t_o = time_ms(lambda: T.fused_loss(img, gt, "l1", 1.0, 0.2))
+    t_r = time_ms(loss_ref)
+    byts = 11 * 4 * img.numel()
+    out["f3_loss_l1_ssim"] = {"ms": round(t_o, 4), "reference_torch_ms": round(t_r, 4),
+                              "algorithmic_bytes": int(byts), "achieved_gbs": round(byts / t_o / 1e6, 1),
+                              "hbm_frac": round(byts / t_o / 1e6 / peak_gbs, 4),
+                              "workload": f"3x{H}x{W}, value + gradient"}
+    # ---- f4: the reference's param groups at this P ---------------------------------------------
+    shapes = [("xyz", (P, 3), 1.6e-4), ("f_dc_color", (P, 1, 3), 2.5e-3), ("f_rest_color", (P, 15, 3), 1.25e-4),
+              ("phase_f_dc", (P, 1, 1), 1e-3), ("phase_f_rest", (P, 15, 1), 5e-5), ("amp_f_dc", (P, 1, 1), 1e-3),
+              ("amp_f_rest", (P, 15, 1), 5e-5), ("opacity", (P, 1), 0.05), ("scaling", (P, 3), 5e-3),
+              ("rotation", (P, 4), 1e-3), ("f_seg_color", (P, 1), 0.0), ("phase_offset", (1,), 0.0),
+              ("dc_offset", (1,), 0.0)]
+    init = [torch.randn(sh, device=dev) for _, sh, _ in shapes]
+    fa = T.FlatAdam([(n, t, lr) for (n, _, lr), t in zip(shapes, init)])
+    fa.grad.normal_()
+    tp = [t.clone().requires_grad_(True) for t in init]
+    for t in tp:
+        t.grad = torch.randn_like(t)
+    opt = torch.optim.Adam([{"params": [t], "lr": lr} for t, (_, _, lr) in zip(tp, shapes)], lr=0.0, eps=1e-15)
+    t_o = time_ms(lambda: fa.step(zero_grad=False))
+    t_r = time_ms(opt.step)
+    byts = 28 * fa.flat.numel()
+    out["f4_adam_13_groups"] = {"ms": round(t_o, 4), "reference_torch_ms": round(t_r, 4),
+                                "algorithmic_bytes": int(byts), "achieved_gbs": round(byts / t_o / 1e6, 1),
+                                "hbm_frac": round(byts / t_o / 1e6 / peak_gbs, 4),
+                                "workload": f"P={P}, {fa.flat.numel()} parameters, 13 groups (torch.optim.Adam default = foreach)"}
+    return out
 
 
 # --------------------------------------------------------------------------------------------

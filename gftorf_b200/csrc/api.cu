@@ -299,6 +299,9 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   pp.pa = reinterpret_cast<float*>(geom + gl.pa);
   pp.ranges = reinterpret_cast<uint2*>(img + il.ranges);
   pp.scan_ticket = hdr;
+  const gft::KeyFormat kf = gft::key_format(a->near_n, a->far_n);
+  pp.key_format_out = hdr + 2;
+  pp.key_depth_bits = kf.depth_bits; pp.key_depth_base = kf.depth_base;
   pp.num_rendered = hdr + 1;
   pp.scan_state = reinterpret_cast<unsigned long long*>(hdr + 4);
   const char* nocull = std::getenv("GFT_NO_CULL");
@@ -316,7 +319,7 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
   if (e != cudaSuccess)
     return fail(-2, std::string("CUDA error reading num_rendered: ") + cudaGetErrorString(e));
 
-  const int end_bit = 32 + tile_bits((uint32_t)(gx * gy));
+  const int end_bit = kf.depth_bits + tile_bits((uint32_t)(gx * gy));
   uint2* ranges = pp.ranges;
 
   // Everything after the preprocess kernel, for a binning workspace of `cap` pairs.  With
@@ -337,7 +340,7 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
       uint32_t* vin = flip ? vals_b : vals_a; uint32_t* vout = flip ? vals_a : vals_b;
       { Stage st("duplicate_keys", stream);
         gft::launch_duplicate_keys(P, a->radii, pp.rect, pp.depths, pp.point_offsets, kin, vin, gx,
-                                   (uint32_t)cap, stream); }
+                                   (uint32_t)cap, kf, stream); }
       GFT_CUDA_OK("duplicate_keys");
       int rc;
       { Stage st("radix_sort", stream);
@@ -346,7 +349,7 @@ int gft_forward(const GftForwardArgs* a, gft_alloc_fn geom_alloc, gft_alloc_fn b
       if (rc < 0) return fail(-2, "gft_forward: radix sort failed");
       GFT_CUDA_OK("sort");
       { Stage st("identify_ranges", stream);
-        gft::launch_identify_ranges(cap, dev_count, keys_a, ranges, stream); }
+        gft::launch_identify_ranges(cap, dev_count, keys_a, ranges, kf, stream); }
       GFT_CUDA_OK("identify_ranges");
     }
     gft::BlendFwdParams bp;

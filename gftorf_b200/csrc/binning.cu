@@ -10,6 +10,9 @@
 #include "kernels.h"
 #include "radix_sort.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace gft {
 
 // One block = 256 consecutive Gaussians; the block's instances are spread evenly over its
@@ -18,7 +21,7 @@ namespace gft {
 __global__ void __launch_bounds__(GFT_BLOCK)
 duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __restrict__ depths,
                       const uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys,
-                      uint32_t* __restrict__ values, int grid_x, uint32_t capacity) {
+                      uint32_t* __restrict__ values, int grid_x, uint32_t capacity, KeyFormat kf) {
   __shared__ uint32_t s_end[GFT_BLOCK];
   const int first = blockIdx.x * GFT_BLOCK;
   const int idx = first + threadIdx.x;
@@ -43,8 +46,12 @@ duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __r
     const uint32_t w = x1 - x0;
     const uint32_t ty = y0 + k / w, tx = x0 + k % w;
     uint64_t key = (uint64_t)(ty * (uint32_t)grid_x + tx);
-    key <<= 32;
-    key |= (uint64_t)__float_as_uint(__ldg(depths + g));
+    key <<= kf.depth_bits;
+    // depth relative to the near plane, see KeyFormat (clamped: a NaN depth passes the frustum
+    // test like in the reference and must not spill into the tile bits)
+    const uint32_t zb = __float_as_uint(__ldg(depths + g));
+    const uint32_t zmax = kf.depth_bits >= 32 ? 0xffffffffu : ((1u << kf.depth_bits) - 1u);
+    key |= (uint64_t)(zb >= kf.depth_base ? min(zb - kf.depth_base, zmax) : 0u);
     if (base + i < capacity) {   // only ever false when a caller's size hint was too small
       keys[base + i] = key;
       values[base + i] = (uint32_t)g;
@@ -54,15 +61,15 @@ duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __r
 
 __global__ void identify_ranges_kernel(int R_cap, const uint32_t* __restrict__ d_R,
                                        const uint64_t* __restrict__ keys,
-                                       uint2* __restrict__ ranges) {
+                                       uint2* __restrict__ ranges, int depth_bits) {
   const int R = d_R ? (int)min(__ldg(d_R), (uint32_t)R_cap) : R_cap;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R) return;
-  const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  const uint32_t cur = (uint32_t)(keys[idx] >> depth_bits);
   if (idx == 0) {
     ranges[cur].x = 0;
   } else {
-    const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    const uint32_t prev = (uint32_t)(keys[idx - 1] >> depth_bits);
     if (cur != prev) {
       ranges[prev].y = idx;
       ranges[cur].x = idx;
@@ -73,18 +80,39 @@ __global__ void identify_ranges_kernel(int R_cap, const uint32_t* __restrict__ d
 
 void launch_duplicate_keys(int P, const int* /*radii*/, const uint16_t* rect, const float* depths,
                            const uint32_t* point_offsets, uint64_t* keys, uint32_t* values,
-                           int grid_x, uint32_t capacity, cudaStream_t stream) {
+                           int grid_x, uint32_t capacity, KeyFormat kf, cudaStream_t stream) {
   const int blocks = (P + GFT_BLOCK - 1) / GFT_BLOCK;
   duplicate_keys_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(P, rect, depths, point_offsets, keys,
-                                                          values, grid_x, capacity);
+                                                          values, grid_x, capacity, kf);
   note_launches(1);
 }
 
 void launch_identify_ranges(int R, const uint32_t* d_R, const uint64_t* keys, uint2* ranges,
-                            cudaStream_t stream) {
+                            KeyFormat kf, cudaStream_t stream) {
   if (R <= 0) return;
-  identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, d_R, keys, ranges);
+  identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, d_R, keys, ranges, kf.depth_bits);
   note_launches(1);
+}
+
+KeyFormat key_format(float near_n, float far_n) {
+  KeyFormat kf;
+  kf.depth_bits = 32;
+  kf.depth_base = 0u;
+  static const bool full = [] {   // GFT_FULL_KEYS=1: the reference's 32-bit depth field (A/B runs)
+    const char* e = std::getenv("GFT_FULL_KEYS");
+    return e && e[0] == '1';
+  }();
+  if (!full && near_n > 0.f && far_n >= near_n && far_n < 3.0e38f) {
+    uint32_t lo, hi;
+    std::memcpy(&lo, &near_n, 4);
+    std::memcpy(&hi, &far_n, 4);
+    const uint32_t span = hi - lo;
+    int b = 0;
+    while (b < 32 && (span >> b) != 0u) ++b;
+    kf.depth_bits = b == 0 ? 1 : b;
+    kf.depth_base = lo;
+  }
+  return kf;
 }
 
 bool sort_result_in_out(int end_bit) { return sort_lands_in_out(end_bit); }

@@ -126,6 +126,10 @@ preprocess_fwd_kernel(PreprocessParams p) {
   const int idx = (int)(vb * GFT_BLOCK + threadIdx.x);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
+  if (vb == 0 && threadIdx.x == 0) {
+    p.key_format_out[0] = (uint32_t)p.key_depth_bits;
+    p.key_format_out[1] = p.key_depth_base;
+  }
   // Zero tile ranges (empty tiles must read (0,0), rasterizer_impl.cu:341).
   for (int t = idx; t < p.num_tiles; t += gridDim.x * GFT_BLOCK) p.ranges[t] = make_uint2(0u, 0u);
 

@@ -41,8 +41,19 @@ def decode_buffers(geom, binning, img, P, R, W, H):
         ranges=v(img, lay.img_ranges, 8 * T, torch.int32).view(T, 2),
     )
     if R > 0:
+        # The library's sort key is (tile << depth_bits) | (float_bits(view_z) - depth_base) with
+        # the format recorded in words 2, 3 of the geometry header; `keys` is rebuilt in the
+        # reference's format (tile << 32) | float_bits(view_z) for the bit-exact comparisons,
+        # `keys_compact` is what the sort actually saw.
+        hdr = v(geom, 0, 16, torch.int32)
+        depth_bits, depth_base = int(hdr[2]), int(hdr[3]) & 0xffffffff
+        ck = v(binning, lay.bin_keys, 8 * R, torch.int64)
+        if depth_bits >= 32:
+            keys = ck
+        else:
+            keys = ((ck >> depth_bits) << 32) | ((ck & ((1 << depth_bits) - 1)) + depth_base)
         out.update(
             point_list=v(binning, lay.bin_point_list, 4 * R, torch.int32),
-            keys=v(binning, lay.bin_keys, 8 * R, torch.int64),
+            keys=keys, keys_compact=ck, key_depth_bits=depth_bits,
         )
     return out

@@ -56,6 +56,21 @@ class GftAdamArgs(C.Structure):
                 ("zero_grad", C.c_int), ("seg", GftAdamSegment * ADAM_MAX_SEGMENTS)]
 
 
+class GftDensifyPlanArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("isotropic", C.c_int), ("size_prune", C.c_int),
+                ("max_grad", C.c_float), ("min_opacity", C.c_float), ("extent", C.c_float),
+                ("percent_dense", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("grad_accum", "denom", "opacity_raw", "scaling_raw", "plan_src",
+                                          "plan_kind", "plan_noise", "split_src", "counts", "workspace")]
+
+
+class GftDensifyApplyArgs(C.Structure):
+    _fields_ = [("P_new", C.c_int), ("width", C.c_int), ("mode", C.c_int)] + \
+               [(n, C.c_void_p) for n in ("plan_src", "plan_kind", "plan_noise", "param_in", "exp_avg_in",
+                                          "exp_avg_sq_in", "param_out", "exp_avg_out", "exp_avg_sq_out",
+                                          "noise", "rotation_raw")]
+
+
 _declared = False
 
 
@@ -73,6 +88,12 @@ def _lib():
         lib.gft_fused_loss.restype = C.c_int
         lib.gft_adam_step.argtypes = [C.POINTER(GftAdamArgs), C.c_void_p]
         lib.gft_adam_step.restype = C.c_int
+        lib.gft_densify_workspace_bytes.argtypes = [C.c_int]
+        lib.gft_densify_workspace_bytes.restype = C.c_size_t
+        lib.gft_densify_plan.argtypes = [C.POINTER(GftDensifyPlanArgs), C.c_void_p]
+        lib.gft_densify_plan.restype = C.c_int
+        lib.gft_densify_apply.argtypes = [C.POINTER(GftDensifyApplyArgs), C.c_void_p]
+        lib.gft_densify_apply.restype = C.c_int
         _declared = True
     return lib
 
@@ -280,3 +301,77 @@ class FlatAdam:
         dev = self.flat.device
         with torch.cuda.device(dev):
             _check(_lib().gft_adam_step(C.byref(a), _stream(dev)), "gft_adam_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# f2 — densification
+# ------------------------------------------------------------------------------------------------
+DENSIFY_GROUPS = ("xyz", "f_dc_color", "f_rest_color", "phase_f_dc", "phase_f_rest", "amp_f_dc",
+                  "amp_f_rest", "opacity", "scaling", "rotation", "f_seg_color")
+
+
+def densify_and_prune(params: Dict[str, torch.Tensor], exp_avg: Optional[Dict[str, torch.Tensor]],
+                      exp_avg_sq: Optional[Dict[str, torch.Tensor]], grad_accum: torch.Tensor,
+                      denom: torch.Tensor, max_grad: float, min_opacity: float, extent: float,
+                      percent_dense: float, size_prune: bool = True, isotropic: bool = False,
+                      generator: Optional[torch.Generator] = None):
+    """GaussianModel.densify_and_prune (scene/gaussian_model.py:631-646) on the parameter groups of
+    the optimizer (names of :247-266) and their Adam moments.  Returns (params, exp_avg,
+    exp_avg_sq, info) for the new Gaussian set, in the reference's order; the caller restarts the
+    densification statistics from zero, as the reference does (:564-566).  The normal samples of
+    the split (:579-581) are drawn here with torch.normal on `generator`, exactly the call the
+    reference makes, so seeded runs reproduce it."""
+    lib = _lib()
+    xyz = _cuda_f32(params["xyz"], "xyz")
+    dev = xyz.device
+    P = int(xyz.shape[0])
+    if P == 0:
+        raise RuntimeError("densify_and_prune: empty Gaussian set")
+    if not (max_grad > 0.0):
+        raise RuntimeError("densify_and_prune: max_grad must be positive")
+    src = {g: _cuda_f32(params[g], g) for g in params}
+    i32 = dict(dtype=torch.int32, device=dev)
+    plan_src, plan_kind = torch.empty(2 * P, **i32), torch.empty(2 * P, **i32)
+    plan_noise, split_src = torch.empty(2 * P, **i32), torch.empty(P, **i32)
+    counts = torch.zeros(5, **i32)
+    ws = torch.empty(lib.gft_densify_workspace_bytes(P), dtype=torch.uint8, device=dev)
+    ga, dn = _cuda_f32(grad_accum, "grad_accum"), _cuda_f32(denom, "denom")
+    a = GftDensifyPlanArgs()
+    a.P, a.isotropic, a.size_prune = P, int(bool(isotropic)), int(bool(size_prune))
+    a.max_grad, a.min_opacity, a.extent, a.percent_dense = float(max_grad), float(min_opacity), float(extent), float(percent_dense)
+    a.grad_accum, a.denom = ga.data_ptr(), dn.data_ptr()
+    a.opacity_raw, a.scaling_raw = src["opacity"].data_ptr(), src["scaling"].data_ptr()
+    a.plan_src, a.plan_kind, a.plan_noise = plan_src.data_ptr(), plan_kind.data_ptr(), plan_noise.data_ptr()
+    a.split_src, a.counts, a.workspace = split_src.data_ptr(), counts.data_ptr(), ws.data_ptr()
+    with torch.cuda.device(dev):
+        _check(lib.gft_densify_plan(C.byref(a), _stream(dev)), "gft_densify_plan")
+    n_keep, n_clone, n_split, n_child, P_new = (int(x) for x in counts.tolist())   # the one host sync
+    # samples of :579-581 — torch.normal(mean=0, std=get_scaling[selected].repeat(2, 1))
+    sel = split_src[:n_split].long()
+    sc = src["scaling"][sel]
+    stds = torch.exp(sc.repeat(1, 3) if isotropic else sc).repeat(2, 1)
+    noise = torch.normal(mean=torch.zeros_like(stds), std=stds, generator=generator) if n_split else \
+        torch.zeros((0, 3), dtype=torch.float32, device=dev)
+    out_p, out_m, out_v = {}, {}, {}
+    for g in params:
+        t = src[g]
+        width = int(t.numel() // P)
+        shape = (P_new,) + tuple(t.shape[1:])
+        b = GftDensifyApplyArgs()
+        b.P_new, b.width = P_new, width
+        b.mode = 1 if g == "xyz" else (2 if g == "scaling" else 0)
+        b.plan_src, b.plan_kind, b.plan_noise = plan_src.data_ptr(), plan_kind.data_ptr(), plan_noise.data_ptr()
+        b.param_in = t.data_ptr()
+        out_p[g] = torch.empty(shape, dtype=torch.float32, device=dev)
+        b.param_out = _ptr(out_p[g])
+        if exp_avg is not None and g in exp_avg:
+            mi, vi = _cuda_f32(exp_avg[g], g), _cuda_f32(exp_avg_sq[g], g)
+            out_m[g], out_v[g] = torch.empty_like(out_p[g]), torch.empty_like(out_p[g])
+            b.exp_avg_in, b.exp_avg_sq_in = mi.data_ptr(), vi.data_ptr()
+            b.exp_avg_out, b.exp_avg_sq_out = _ptr(out_m[g]), _ptr(out_v[g])
+        if b.mode == 1:
+            b.noise, b.rotation_raw = _ptr(noise), src["rotation"].data_ptr()
+        with torch.cuda.device(dev):
+            _check(lib.gft_densify_apply(C.byref(b), _stream(dev)), "gft_densify_apply")
+    info = dict(kept=n_keep, clones=n_clone, split=n_split, children_per_copy=n_child, P_new=P_new)
+    return out_p, out_m, out_v, info

@@ -153,6 +153,61 @@ typedef struct GftAdamArgs {
 
 int gft_adam_step(const GftAdamArgs* args, gft_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2 — adaptive density control: GaussianModel.densify_and_prune (scene/gaussian_model.py:631-646)
+ * with densify_and_clone (:607-629), densify_and_split (:568-605, N = 2), prune_points (:493-513)
+ * and the optimizer-state surgery (:473-536), as a plan + one gather per parameter group.
+ *
+ * gft_densify_plan decides, per original Gaussian, what the whole sequence does to it and lays
+ * out the new Gaussian set in the reference's final order:
+ *     [ kept originals | clones | split children, copy 0 | split children, copy 1 ]
+ * counts[0..4] = kept, clones, Gaussians selected for splitting, children kept per copy, new P.
+ * plan_* need room for 2*P entries (the new set never exceeds 2*P).  plan_noise[k] is the row of
+ * the caller's normal samples a child uses: copy * counts[2] + rank among the selected — the rows
+ * of torch.normal(mean = 0, std = scaling[selected].repeat(2, 1)) (:579-581).  split_src
+ * (optional, P entries) lists the selected Gaussians so the caller can draw those samples.
+ * max_grad must be > 0 (clones carry a zero gradient into the split test, :572-573).
+ * size_prune: the world-size criteria of :640-643 (`if max_screen_size`); the screen-size criterion
+ * of :639 is always false in the reference because max_radii2D is reset by the appends (:566).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct GftDensifyPlanArgs {
+  int P;
+  int isotropic;
+  int size_prune;
+  float max_grad, min_opacity, extent, percent_dense;
+  const float* grad_accum;     /* [P,1] xyz_gradient_accum */
+  const float* denom;          /* [P,1] */
+  const float* opacity_raw;    /* [P,1] */
+  const float* scaling_raw;    /* [P,3] or [P,1] */
+  int32_t* plan_src;           /* [2P] out */
+  int32_t* plan_kind;          /* [2P] out: 0 kept original, 1 clone, 2 split child */
+  int32_t* plan_noise;         /* [2P] out: sample row for children, -1 otherwise */
+  int32_t* split_src;          /* [P]  out, optional */
+  int32_t* counts;             /* [5]  out */
+  char* workspace;             /* gft_densify_workspace_bytes(P) */
+} GftDensifyPlanArgs;
+
+size_t gft_densify_workspace_bytes(int P);
+int gft_densify_plan(const GftDensifyPlanArgs* args, gft_stream_t stream);
+
+/* Gathers ONE parameter group (row width `width` floats) and its two Adam moments into the new
+ * set: kept originals carry their moments, new Gaussians start from zero moments (:527-528).
+ * mode 0: rows are copied; mode 1 (xyz, width 3): a child's position is
+ * R(rotation_raw / |rotation_raw|) * (noise row) + xyz, noise = the caller's samples (already
+ * scaled by the standard deviations); mode 2 (scaling): a child's row is log(exp(s) / (0.8 * 2)). */
+typedef struct GftDensifyApplyArgs {
+  int P_new;
+  int width;
+  int mode;
+  const int32_t* plan_src; const int32_t* plan_kind; const int32_t* plan_noise;
+  const float* param_in; const float* exp_avg_in; const float* exp_avg_sq_in;
+  float* param_out; float* exp_avg_out; float* exp_avg_sq_out;   /* moment pointers may be NULL */
+  const float* noise;          /* [2*counts[2], 3], mode 1 */
+  const float* rotation_raw;   /* [P,4] of the OLD set, mode 1 */
+} GftDensifyApplyArgs;
+
+int gft_densify_apply(const GftDensifyApplyArgs* args, gft_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,73 @@ def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-15):
     bc2 = 1.0 - beta2 ** step
     denom = np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)
     p += f(-(lr / bc1)) * (m / denom)
+
+
+# ---- f2 -----------------------------------------------------------------------------------------
+GROUPS = ("xyz", "f_dc_color", "f_rest_color", "phase_f_dc", "phase_f_rest", "amp_f_dc", "amp_f_rest",
+          "opacity", "scaling", "rotation", "f_seg_color")
+
+
+def _rotation_matrix(r):
+    """utils/general_utils.py:91-112 (normalises the quaternion first)."""
+    q = r / torch.sqrt((r * r).sum(dim=1))[:, None]
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.zeros((q.shape[0], 3, 3), dtype=r.dtype, device=r.device)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def densify_and_prune(params, exp_avg, exp_avg_sq, grad_accum, denom, max_grad, min_opacity, extent,
+                      percent_dense, size_prune=True, isotropic=False, normal_fn=None):
+    """scene/gaussian_model.py:631-646 (densify_and_prune) with the clone (:607-629), split
+    (:568-605), prune (:493-513) and optimizer-state surgery (:473-536) it calls, on plain tensors.
+    `params`, `exp_avg`, `exp_avg_sq`: dicts over GROUPS.  `normal_fn(std)` stands for
+    torch.normal(mean=0, std=std) (:581).  Returns the three dicts for the new Gaussian set; the
+    densification statistics and max_radii2D restart from zero (:564-566), which also makes the
+    screen-size criterion of :639 vacuous."""
+    get_scaling = lambda p: torch.exp(p["scaling"].repeat(1, 3) if isotropic else p["scaling"])
+    P = params["xyz"].shape[0]
+    grads = grad_accum / denom
+    grads[grads.isnan()] = 0.0
+    p, m, v = dict(params), dict(exp_avg), dict(exp_avg_sq)
+
+    def append(new):
+        for g in GROUPS:
+            p[g] = torch.cat((p[g], new[g]), dim=0)
+            m[g] = torch.cat((m[g], torch.zeros_like(new[g])), dim=0)
+            v[g] = torch.cat((v[g], torch.zeros_like(new[g])), dim=0)
+
+    def prune(mask):
+        keep = ~mask
+        for g in GROUPS:
+            p[g], m[g], v[g] = p[g][keep], m[g][keep], v[g][keep]
+
+    # clone (:607-629)
+    sel = torch.norm(grads, dim=-1) >= max_grad
+    sel = sel & (get_scaling(p).max(dim=1).values <= percent_dense * extent)
+    append({g: p[g][sel] for g in GROUPS})
+    # split (:568-605), N = 2
+    n_now = p["xyz"].shape[0]
+    padded = torch.zeros(n_now, dtype=grads.dtype, device=grads.device)
+    padded[:P] = grads.squeeze(-1)
+    sel = (padded >= max_grad) & (get_scaling(p).max(dim=1).values > percent_dense * extent)
+    stds = get_scaling(p)[sel].repeat(2, 1)
+    samples = normal_fn(stds)
+    rots = _rotation_matrix(p["rotation"][sel]).repeat(2, 1, 1)
+    new = {g: p[g][sel].repeat(2, *([1] * (p[g].dim() - 1))) for g in GROUPS}
+    new["xyz"] = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + p["xyz"][sel].repeat(2, 1)
+    if isotropic:
+        new["scaling"] = torch.log(torch.exp(p["scaling"][sel]).repeat(2, 1) / (0.8 * 2))
+    else:
+        new["scaling"] = torch.log(get_scaling(p)[sel].repeat(2, 1) / (0.8 * 2))
+    append(new)
+    prune(torch.cat((sel, torch.zeros(2 * int(sel.sum()), dtype=torch.bool, device=sel.device))))
+    # prune (:636-644); max_radii2D was reset to zero by the two appends, so the screen-size term is False
+    mask = (torch.sigmoid(p["opacity"]) < min_opacity).squeeze(-1)
+    if size_prune:
+        ws = get_scaling(p).max(dim=1).values
+        mask = mask | (ws > 0.05 * extent) | (ws < 0.001 * extent)
+    prune(mask)
+    return p, m, v

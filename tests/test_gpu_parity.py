@@ -299,6 +299,25 @@ def test_constant_background_is_not_materialised_and_matches():
     assert harness.rel_l2(ob[3], rb[3]) <= harness.GRAD_REL_L2
 
 
+def test_compact_sort_keys_are_the_reference_keys_rebased():
+    """The sort sees (tile << depth_bits) | (float_bits(z) - float_bits(near)); rebuilt in the
+    reference's format the keys must carry exactly the Gaussians' depth bits and tile ids."""
+    inp = harness.build_inputs(device="cuda", **CASES["c1"])
+    f = harness.call_forward(rasterizer._C, inp)
+    d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
+    assert 1 <= d["key_depth_bits"] <= 28          # [znear, zfar] of the F-ToRF camera spans < 2^28 ulps
+    ck = d["keys_compact"]
+    assert bool((ck[1:] >= ck[:-1]).all())
+    g = d["point_list"].long()
+    zbits = d["depths"].view(torch.int32).long()[g]
+    assert torch.equal(d["keys"] & 0xffffffff, zbits)
+    rng = d["ranges"].long()
+    tiles = d["keys"] >> 32
+    nz = (rng[:, 1] - rng[:, 0]) > 0
+    T = rng.shape[0]
+    assert bool((tiles[rng[nz, 0]] == torch.arange(T, device="cuda")[nz]).all())
+
+
 @needs_ref
 def test_sort_backends_agree_bitwise():
     spec = CASES["c1"]

@@ -95,7 +95,8 @@ def test_train_header_symbols_are_exported():
     src = open(os.path.join(ROOT, "include", "gftorf_train.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(gft_[a-z0-9_]+)\s*\(", src)))
-    assert names == ["gft_adam_step", "gft_assemble_backward", "gft_assemble_forward", "gft_fused_loss",
+    assert names == ["gft_adam_step", "gft_assemble_backward", "gft_assemble_forward", "gft_densify_apply",
+                     "gft_densify_plan", "gft_densify_workspace_bytes", "gft_fused_loss",
                      "gft_fused_loss_scratch_bytes"]
     from gftorf_b200 import _capi
     lib = C.CDLL(_capi.LIB_PATH)
@@ -107,7 +108,8 @@ def test_train_ctypes_structs_match_the_c_layout(tmp_path):
     import subprocess
     from gftorf_b200 import train_ops as T
     structs = {"GftAssembleArgs": T.GftAssembleArgs, "GftAssembleGrads": T.GftAssembleGrads,
-               "GftLossArgs": T.GftLossArgs, "GftAdamArgs": T.GftAdamArgs, "GftAdamSegment": T.GftAdamSegment}
+               "GftLossArgs": T.GftLossArgs, "GftAdamArgs": T.GftAdamArgs, "GftAdamSegment": T.GftAdamSegment,
+               "GftDensifyPlanArgs": T.GftDensifyPlanArgs, "GftDensifyApplyArgs": T.GftDensifyApplyArgs}
     cname = lambda f: "lambda" if f == "lambda_" else f
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gftorf_train.h"', "int main(void){"]
     for s, cls in structs.items():
@@ -281,3 +283,77 @@ def test_flat_adam_full_size_is_a_pure_function_of_its_inputs():
             fa.step()
         res.append(fa.flat.clone())
     assert torch.equal(res[0], res[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# f2 — densification
+# ------------------------------------------------------------------------------------------------
+def make_model(P, isotropic=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    params = dict(xyz=r(P, 3), f_dc_color=r(P, 1, 3), f_rest_color=r(P, 15, 3) * 0.1, phase_f_dc=r(P, 1, 1),
+                  phase_f_rest=r(P, 15, 1) * 0.1, amp_f_dc=r(P, 1, 1), amp_f_rest=r(P, 15, 1) * 0.1,
+                  opacity=r(P, 1) * 2, scaling=r(P, 1 if isotropic else 3) * 1.2 - 3.0, rotation=r(P, 4),
+                  f_seg_color=torch.rand(P, 1, generator=g))
+    m = {k: r(*v.shape) * 0.01 for k, v in params.items()}
+    v = {k: torch.rand(v_.shape, generator=g) * 1e-4 for k, v_ in params.items()}
+    acc = torch.rand(P, 1, generator=g)
+    den = torch.randint(0, 4, (P, 1), generator=g).float()      # zeros -> NaN gradients -> 0
+    return params, m, v, acc, den
+
+
+def test_densify_restatement_counts_and_order():
+    """CPU pin of the oracle: sizes add up, survivors keep their relative order, new Gaussians get
+    zero moments, statistics of the three parts match a by-hand classification."""
+    P = 400
+    params, m, v, acc, den = make_model(P, seed=3)
+    kw = dict(max_grad=0.3, min_opacity=0.2, extent=4.0, percent_dense=0.01)
+    z = lambda s: torch.normal(mean=torch.zeros_like(s), std=s, generator=torch.Generator().manual_seed(9))
+    p2, m2, v2 = orc.densify_and_prune(params, m, v, acc.clone(), den, normal_fn=z, **kw)
+    g = torch.nan_to_num(acc / den, nan=0.0).squeeze(-1)
+    ms = torch.exp(params["scaling"]).max(dim=1).values
+    op = torch.sigmoid(params["opacity"]).squeeze(-1)
+    pr = (op < 0.2) | (ms > 0.05 * 4.0) | (ms < 0.001 * 4.0)
+    s = (g >= 0.3) & (ms > 0.04)
+    c = (g.abs() >= 0.3) & (ms <= 0.04)
+    n_keep, n_clone = int((~s & ~pr).sum()), int((c & ~pr).sum())
+    assert p2["xyz"].shape[0] >= n_keep + n_clone
+    assert torch.equal(p2["f_dc_color"][:n_keep], params["f_dc_color"][~s & ~pr])
+    assert torch.equal(m2["xyz"][:n_keep], m["xyz"][~s & ~pr])
+    assert torch.equal(p2["rotation"][n_keep:n_keep + n_clone], params["rotation"][c & ~pr])
+    assert float(m2["xyz"][n_keep:].abs().max()) == 0.0 and float(v2["opacity"][n_keep:].abs().max()) == 0.0
+    assert (p2["xyz"].shape[0] - n_keep - n_clone) % 2 == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [dict(P=1, iso=False, size=True), dict(P=999, iso=False, size=True),
+                                  dict(P=5000, iso=False, size=False), dict(P=3001, iso=True, size=True),
+                                  dict(P=70000, iso=False, size=True)])
+def test_densify_and_prune_vs_oracle(case):
+    """Same inputs, same torch.normal stream: the new Gaussian set must come out in the
+    reference's order with identical rows (children's positions to 1e-6: bmm vs explicit dot)."""
+    from gftorf_b200 import train_ops as T
+    P = case["P"]
+    params, m, v, acc, den = make_model(P, isotropic=case["iso"], seed=P)
+    kw = dict(max_grad=0.3, min_opacity=0.2, extent=4.0, percent_dense=0.01)
+    cu = lambda d: {k: t.cuda() for k, t in d.items()}
+    gen_o = torch.Generator("cuda").manual_seed(5)
+    gen_p = torch.Generator("cuda").manual_seed(5)
+    z = lambda s: torch.normal(mean=torch.zeros_like(s), std=s, generator=gen_o)
+    # the oracle on GPU tensors, so exp / log / sigmoid are the same device functions
+    p2, m2, v2 = orc.densify_and_prune(cu(params), cu(m), cu(v), acc.cuda(), den.cuda(), size_prune=case["size"],
+                                       isotropic=case["iso"], normal_fn=z, **kw)
+    q2, n2, w2, info = T.densify_and_prune(cu(params), cu(m), cu(v), acc.cuda(), den.cuda(), size_prune=case["size"],
+                                           isotropic=case["iso"], generator=gen_p, **kw)
+    assert info["P_new"] == p2["xyz"].shape[0]
+    for g in orc.GROUPS:
+        assert q2[g].shape == p2[g].shape, g
+        if g == "xyz":
+            assert torch.equal(q2[g][:info["kept"] + info["clones"]], p2[g][:info["kept"] + info["clones"]])
+            if q2[g].numel():
+                assert float((q2[g] - p2[g]).abs().max()) <= 1e-5 * max(1.0, float(p2[g].abs().max()))
+        elif g == "scaling":
+            assert float((q2[g] - p2[g]).abs().max() if q2[g].numel() else 0.0) <= 1e-6
+        else:
+            assert torch.equal(q2[g], p2[g]), g
+        assert torch.equal(n2[g], m2[g]) and torch.equal(w2[g], v2[g]), g
