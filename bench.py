@@ -207,13 +207,16 @@ def run_gpu(args, impl):
         return f
 
     def step_resident():
-        bucket.zero()
+        if impl != "ours":
+            bucket.zero()
         stats = []
-        for v in views:
+        for vi, v in enumerate(views):
             f = fwd(v)
             if impl == "ours":
+                # the first view overwrites the bucket (no zero fill), the others add into it
                 mod.rasterize_gaussians_backward(
-                    *bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]), grad_out=grad_out)
+                    *bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]), grad_out=grad_out,
+                    accumulate=vi > 0)
             else:
                 # the reference's gradients of the two views add in autograd's AccumulateGrad
                 b = mod.rasterize_gaussians_backward(*bwd_args(params, v, f, empty, zero3[id(v)], zero1[id(v)]))

@@ -14,18 +14,25 @@
 #include "radix_sort.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace gft {
 
 namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                         // pairs per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 pairs per tile
+// pairs per thread: 16 (4096-pair tiles).  An 8-pair variant (2048-pair tiles, 64 registers, four
+// resident blocks per SM) is kept behind GFT_SORT_ITEMS=8: measured on B200 it is 5 % SLOWER at
+// R ~ 1e6 and equal at R ~ 1e7 — a pass there is bound by its fixed costs (launch, ramp, the
+// load -> rank -> prefix -> reorder -> store dependency chain), not by resident warps.
+constexpr int RS_ITEMS_MAX = 16;
+constexpr int RS_ITEMS_MIN = 8;
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 
 constexpr int RS_LOOKBACK = 8;
+constexpr uint32_t RS_GROUP = 16;   // tiles per look-back group
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PRE = 2u << 30;
 constexpr uint32_t VAL_MASK = (1u << 30) - 1;
@@ -87,7 +94,8 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_bins_kernel(uint32_t* __restr
   h[threadIdx.x] = base + incl - v;
 }
 
-struct RsSmem {
+template <int RS_TILE>
+struct RsSmemT {
   uint64_t keys[RS_TILE];
   uint32_t vals[RS_TILE];
   uint32_t warp_hist[RS_WARPS][RS_BINS];  // per-warp digit counts -> exclusive warp prefixes
@@ -96,12 +104,15 @@ struct RsSmem {
   uint32_t tile_id;
 };
 
-__global__ void __launch_bounds__(RS_THREADS)
+template <int RS_ITEMS, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
 rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int R_cap,
                    const uint32_t* __restrict__ d_R, int shift, int nbits,
                    const uint32_t* __restrict__ digit_base, uint32_t* __restrict__ ticket,
-                   uint32_t* __restrict__ state) {
+                   uint32_t* __restrict__ state, uint32_t* __restrict__ gstate) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+  using RsSmem = RsSmemT<RS_TILE>;
   extern __shared__ __align__(16) unsigned char rs_smem_raw[];
   RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -158,35 +169,64 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
       run += c;
     }
     const uint32_t count = run;
-    uint32_t* st = state + (size_t)tile * RS_BINS + d;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      st_status_u32(st, FLAG_PRE | count);
-    } else {
-      st_status_u32(st, FLAG_AGG | count);
-      // decoupled look-back, RS_LOOKBACK predecessor tiles per step: the polls are independent
-      // loads, so a step costs one L2 round trip.  (At R ~ 1e6 the whole grid is one wave, so a
-      // tile may have to walk back over every tile before it: the walk, not bandwidth, sets the
-      // duration of a pass.)
-      int t = (int)tile - 1;
-      bool found = false;
-      while (!found) {
-        uint32_t v[RS_LOOKBACK];
+    // ---- exclusive prefix of this tile's digit count over all earlier tiles -----------------
+    // Two levels.  A plain decoupled look-back over tiles is a serial chain here: at R ~ 1e6 every
+    // tile of the pass is resident at once, nobody owns an inclusive prefix yet, and prefixes
+    // propagate at ~16 tiles per L2 round trip (measured: 13 of the 18 us of a pass).  So tiles are
+    // grouped by RS_GROUP: inside a group a tile sums its predecessors' aggregates directly (one
+    // round trip, <= RS_GROUP-1 independent loads); the LAST tile of a group publishes the group
+    // total and runs the decoupled look-back over GROUPS (a 16x shorter chain); the other tiles
+    // of a group wait for the previous group's inclusive prefix, a single word.
+    const uint32_t tiles_real = ((uint32_t)R + RS_TILE - 1) / RS_TILE;
+    const uint32_t grp = tile / RS_GROUP, first = grp * RS_GROUP;
+    const uint32_t last = min(first + RS_GROUP - 1, tiles_real - 1);
+    st_status_u32(state + (size_t)tile * RS_BINS + d, FLAG_AGG | count);
+    uint32_t in_grp = 0;
+    {
+      uint32_t v[RS_GROUP - 1];
 #pragma unroll
-        for (int i = 0; i < RS_LOOKBACK; ++i)
-          v[i] = (t - i >= 0) ? ld_status_u32(state + (size_t)(t - i) * RS_BINS + d) : FLAG_PRE;
+      for (int i = 0; i < RS_GROUP - 1; ++i)
+        v[i] = (first + i < tile) ? ld_status_u32(state + (size_t)(first + i) * RS_BINS + d) : FLAG_AGG;
 #pragma unroll
-        for (int i = 0; i < RS_LOOKBACK; ++i) {
-          if (!found) {
-            while ((v[i] & ~VAL_MASK) == 0u) v[i] = ld_status_u32(state + (size_t)(t - i) * RS_BINS + d);
-            excl += v[i] & VAL_MASK;
-            if (v[i] & FLAG_PRE) found = true;
-          }
-        }
-        t -= RS_LOOKBACK;
+      for (int i = 0; i < RS_GROUP - 1; ++i) {
+        while ((v[i] & ~VAL_MASK) == 0u) v[i] = ld_status_u32(state + (size_t)(first + i) * RS_BINS + d);
+        in_grp += v[i] & VAL_MASK;
       }
-      st_status_u32(st, FLAG_PRE | (excl + count));
     }
+    uint32_t gexcl = 0;
+    if (tile == last) {
+      const uint32_t gtotal = in_grp + count;
+      uint32_t* gs = gstate + (size_t)grp * RS_BINS + d;
+      if (grp == 0) {
+        st_status_u32(gs, FLAG_PRE | gtotal);
+      } else {
+        st_status_u32(gs, FLAG_AGG | gtotal);
+        int t = (int)grp - 1;
+        bool found = false;
+        while (!found) {
+          uint32_t v[RS_LOOKBACK];
+#pragma unroll
+          for (int i = 0; i < RS_LOOKBACK; ++i)
+            v[i] = (t - i >= 0) ? ld_status_u32(gstate + (size_t)(t - i) * RS_BINS + d) : FLAG_PRE;
+#pragma unroll
+          for (int i = 0; i < RS_LOOKBACK; ++i) {
+            if (!found) {
+              while ((v[i] & ~VAL_MASK) == 0u) v[i] = ld_status_u32(gstate + (size_t)(t - i) * RS_BINS + d);
+              gexcl += v[i] & VAL_MASK;
+              if (v[i] & FLAG_PRE) found = true;
+            }
+          }
+          t -= RS_LOOKBACK;
+        }
+        st_status_u32(gs, FLAG_PRE | (gexcl + gtotal));
+      }
+    } else if (grp != 0) {
+      const uint32_t* gp = gstate + (size_t)(grp - 1) * RS_BINS + d;
+      uint32_t v = ld_status_u32(gp);
+      while ((v & FLAG_PRE) == 0u) v = ld_status_u32(gp);
+      gexcl = v & VAL_MASK;
+    }
+    const uint32_t excl = gexcl + in_grp;
     // exclusive scan of `count` over the 256 digits
     uint32_t incl = count;
 #pragma unroll
@@ -240,11 +280,24 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int radix_sort_passes(int end_bit) { return (end_bit + 7) / 8; }
 
+namespace {
+constexpr int RS_TILE_MIN = RS_THREADS * RS_ITEMS_MIN;
+constexpr int RS_TILE_MAX = RS_THREADS * RS_ITEMS_MAX;
+inline int pick_items(int /*R*/) {
+  static const int forced = [] {
+    const char* e = std::getenv("GFT_SORT_ITEMS");
+    return (e && e[0] == '8') ? RS_ITEMS_MIN : RS_ITEMS_MAX;
+  }();
+  return forced;
+}
+}  // namespace
+
 size_t own_sort_temp_bytes(int R) {
-  const size_t tiles = ((size_t)max(R, 1) + RS_TILE - 1) / RS_TILE;
-  // hist[8][256] + ticket[8] + state[passes][tiles][256]
+  const size_t tiles = ((size_t)max(R, 1) + RS_TILE_MIN - 1) / RS_TILE_MIN;
+  // hist[8][256] + ticket[8] + per pass: tile state [tiles][256] + group state [groups][256]
+  const size_t groups = (tiles + RS_GROUP - 1) / RS_GROUP;
   return align_up(RS_MAX_PASSES * RS_BINS * 4 + RS_MAX_PASSES * 4, 256) +
-         RS_MAX_PASSES * tiles * RS_BINS * 4;
+         RS_MAX_PASSES * (tiles + groups) * RS_BINS * 4;
 }
 
 // Sorts on bits [0,end_bit).  Ping-pongs between (a) and (b) starting from a; the result lands in
@@ -258,12 +311,15 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
   uint64_t* keys_a = const_cast<uint64_t*>(keys_a_c);
   uint32_t* vals_a = const_cast<uint32_t*>(vals_a_c);
   const int npass = radix_sort_passes(end_bit);
-  const int tiles = (R + RS_TILE - 1) / RS_TILE;
+  const int items = pick_items(R);
+  const int tiles = (R + RS_THREADS * items - 1) / (RS_THREADS * items);
   const size_t head = align_up(RS_MAX_PASSES * RS_BINS * 4 + RS_MAX_PASSES * 4, 256);
   uint32_t* hist = reinterpret_cast<uint32_t*>(d_temp);
   uint32_t* ticket = hist + RS_MAX_PASSES * RS_BINS;
   uint32_t* state = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_temp) + head);
-  cudaMemsetAsync(d_temp, 0, head + (size_t)npass * tiles * RS_BINS * 4, stream);
+  const int groups = (tiles + (int)RS_GROUP - 1) / (int)RS_GROUP;
+  const size_t per_pass = (size_t)(tiles + groups) * RS_BINS;
+  cudaMemsetAsync(d_temp, 0, head + (size_t)npass * per_pass * 4, stream);
 
   int hblocks = (R + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
   hblocks = max(1, min(hblocks, 148 * 8));
@@ -271,16 +327,23 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
   rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
   note_launches(2 + npass);
 
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(rs_onesweep_kernel, (int)sizeof(RsSmem), &smem_ok);
+  static unsigned long long smem_ok_min = 0, smem_ok_max = 0;
+  if (items == RS_ITEMS_MIN)
+    ensure_dynamic_smem(rs_onesweep_kernel<RS_ITEMS_MIN, 4>, (int)sizeof(RsSmemT<RS_TILE_MIN>), &smem_ok_min);
+  else
+    ensure_dynamic_smem(rs_onesweep_kernel<RS_ITEMS_MAX, 2>, (int)sizeof(RsSmemT<RS_TILE_MAX>), &smem_ok_max);
   uint64_t* kin = keys_a; uint64_t* kout = keys_b;
   uint32_t* vin = vals_a; uint32_t* vout = vals_b;
   for (int p = 0; p < npass; ++p) {
     const int shift = 8 * p;
     const int nb = min(8, end_bit - shift);
-    rs_onesweep_kernel<<<tiles, RS_THREADS, sizeof(RsSmem), stream>>>(
-        kin, kout, vin, vout, R, d_R, shift, nb, hist + p * RS_BINS, ticket + p,
-        state + (size_t)p * tiles * RS_BINS);
+    uint32_t* st = state + (size_t)p * per_pass;
+    if (items == RS_ITEMS_MIN)
+      rs_onesweep_kernel<RS_ITEMS_MIN, 4><<<tiles, RS_THREADS, sizeof(RsSmemT<RS_TILE_MIN>), stream>>>(
+          kin, kout, vin, vout, R, d_R, shift, nb, hist + p * RS_BINS, ticket + p, st, st + (size_t)tiles * RS_BINS);
+    else
+      rs_onesweep_kernel<RS_ITEMS_MAX, 2><<<tiles, RS_THREADS, sizeof(RsSmemT<RS_TILE_MAX>), stream>>>(
+          kin, kout, vin, vout, R, d_R, shift, nb, hist + p * RS_BINS, ticket + p, st, st + (size_t)tiles * RS_BINS);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

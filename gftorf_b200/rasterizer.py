@@ -224,7 +224,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
                      grad_out_acc, grad_entropy, grad_depth_distortion, grad_amp_distortion,
                      sh, sh_p, degree, campos, geomBuffer, R, binningBuffer, imgBuffer, debug,
                      near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset,
-                     grad_out=None):
+                     grad_out=None, accumulate=True):
     """Same argument order and 12-tuple result as `_C.rasterize_gaussians_backward`
     (rasterize_points.cu:167-281).  grad_out_normal / grad_entropy / grad_amp_distortion are
     accepted and ignored, as in the reference (backward.cu never reads them).
@@ -233,7 +233,9 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     `shs [P,M,3]`, `shs_p [P,M_p,2]`, `opacities [P,1]`, `scales [P,3]`, `rotations [P,4]`,
     `phase_offset [1]`, `dc_offset [1]` that the parameter gradients are ADDED INTO
     (GftBackwardArgs.accumulate) — the slices of a `parallel.GradBucket`, so the views of a batch
-    accumulate in the buffer the collective runs on."""
+    accumulate in the buffer the collective runs on.  `accumulate=False` makes this call OVERWRITE
+    the `grad_out` tensors instead (every row is written, zeros for culled Gaussians): the first
+    view of an iteration then needs no zero fill of the bucket."""
     lib = _capi.lib()
     dev = means3D.device
     P = int(means3D.shape[0])
@@ -291,6 +293,9 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
                   dL_dphase_offset, dL_ddc_offset):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
                 raise RuntimeError("grad_out tensors must be contiguous fp32 tensors on the input's device")
+        if not accumulate and not have_scales and P > 0:   # rows the library will not touch
+            dL_dscales.zero_()
+            dL_drotations.zero_()
 
     means3D = _f32c(means3D)
     sh, sh_p = _f32c(sh), _f32c(sh_p)
@@ -328,7 +333,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     a.near_n, a.far_n, a.depth_range = float(near_n), float(far_n), float(depth_range)
     a.use_view_dependent_phase = int(bool(use_view_dependent_phase))
     a.phase_offset, a.dc_offset = _as_float(phase_offset), _as_float(dc_offset)
-    a.accumulate = 0 if grad_out is None else 1
+    a.accumulate = 1 if (grad_out is not None and accumulate) else 0
 
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):

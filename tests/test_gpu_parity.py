@@ -557,6 +557,16 @@ def test_accumulate_mode_adds_views_into_the_bucket():
     assert harness.rel_l2(go["phase_offset"], plain[0][10] + plain[1][10]) <= harness.GRAD_REL_L2
     assert harness.rel_l2(go["dc_offset"], plain[0][11] + plain[1][11]) <= harness.GRAD_REL_L2
     assert bucket.flat.data_ptr() == go["means3D"].data_ptr()
+    # accumulate=False on the first view overwrites whatever the bucket held: no zero fill needed
+    summed = bucket.flat.clone()
+    bucket.flat.fill_(float("nan"))
+    for vi, inp in enumerate((inp_a, inp_b)):
+        f = harness.call_forward(rasterizer._C, inp)
+        harness.call_backward(rasterizer._C, inp, f, grad_out=go, accumulate=vi > 0)
+    for name, t in go.items():        # (the alignment padding between slices is never touched)
+        assert bool(torch.isfinite(t).all()), name
+    bucket.flat.nan_to_num_(nan=0.0)
+    assert harness.rel_l2(bucket.flat, summed) <= harness.GRAD_REL_L2
 
 
 def test_hinted_forward_is_identical_and_survives_a_bad_hint():
