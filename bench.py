@@ -555,6 +555,19 @@ def next_rows_bench(P, H, W, dev, flush, peak_gbs, iters=20):
                                 "algorithmic_bytes": int(byts), "achieved_gbs": round(byts / t_o / 1e6, 1),
                                 "hbm_frac": round(byts / t_o / 1e6 / peak_gbs, 4),
                                 "workload": f"P={P}, {fa.flat.numel()} parameters, 13 groups (torch.optim.Adam default = foreach)"}
+    # ---- a18: distCUDA2 (initialisation) on a uniform cloud of the workload's size ---------------
+    from gftorf_b200 import distCUDA2
+    pts = torch.rand(P, 3, device=dev) * 4.0 - 2.0
+    t_o = time_ms(lambda: distCUDA2(pts))
+    entry = {"ms": round(t_o, 4), "algorithmic_bytes": 32 * P, "achieved_gbs": round(32 * P / t_o / 1e6, 1),
+             "workload": f"P={P} uniform points"}
+    try:
+        from oracle import ref_driver
+        if ref_driver.available():
+            entry["reference_kernels_ms"] = round(time_ms(lambda: ref_driver.distCUDA2(pts)), 4)
+    except Exception as e:          # the reference library did not travel: report ours alone
+        entry["reference_kernels_ms"] = None
+    out["a18_distCUDA2"] = entry
     return out
 
 
