@@ -157,7 +157,7 @@ def stage_bytes(stage, P, V, R, N, T):
         "radix_sort": 24 * R,
         "identify_ranges": 8 * R + 8 * T,
         "blend_fwd": 76 * R + 128 * N,
-        "zero_grad_records": 80 * P,
+        "zero_grad_records": 64 * P,
         "blend_bwd": 76 * R + 96 * N + 80 * V,
         "preprocess_bwd": 388 * P + 472 * V,
     }.get(stage, 0)
