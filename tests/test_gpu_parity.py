@@ -27,6 +27,11 @@ CASES = {
     "c1": dict(P=20000, W=320, H=240, kind="trained", seed=0),
     "c1_init": dict(P=20000, W=320, H=240, kind="init", seed=1),
     "c1_dense": dict(P=20000, W=320, H=240, kind="trained", seed=2, sigma_px=6.0),
+    # active SH degree below the stored one: training starts at 0 and adds a degree per 1000
+    # iterations (train.py:152-153); coefficients above the active degree must get zero gradients
+    "deg0": dict(P=3000, W=160, H=120, kind="trained", seed=6, pose="orbit", sh_degree=0),
+    "deg1": dict(P=3000, W=160, H=120, kind="trained", seed=7, pose="orbit", sh_degree=1),
+    "deg2": dict(P=3000, W=160, H=120, kind="trained", seed=8, pose="orbit", sh_degree=2),
     "c2": dict(P=300000, W=640, H=480, kind="trained", seed=0),
     "c2_vdp": dict(P=300000, W=640, H=480, kind="trained", seed=3, pose="orbit",
                    view_dependent_phase=True, phase_offset=0.3, dc_offset=0.1),
@@ -61,8 +66,8 @@ def test_forward_vs_reference_kernels(name):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["tiny", "ragged", "small_orbit", "init_small", "c1", "c1_dense",
-                                  "c2", "c2_vdp", "c3_tof"])
+@pytest.mark.parametrize("name", ["tiny", "ragged", "small_orbit", "init_small", "deg0", "deg1", "deg2",
+                                  "c1", "c1_dense", "c2", "c2_vdp", "c3_tof"])
 def test_backward_vs_reference_kernels(name):
     # zero higher-order phase/amp SH keeps the reference's undefined dL_dPA out of
     # dL_dmeans3D; dL_dsh_p is compared on the one row the reference defines (Gaussian 0).
@@ -316,6 +321,32 @@ def test_compact_sort_keys_are_the_reference_keys_rebased():
     nz = (rng[:, 1] - rng[:, 0]) > 0
     T = rng.shape[0]
     assert bool((tiles[rng[nz, 0]] == torch.arange(T, device="cuda")[nz]).all())
+
+
+@needs_ref
+@pytest.mark.parametrize("deg,M", [(0, 1), (1, 4), (2, 9), (1, 16)])
+def test_truncated_sh_tensors_vs_reference_kernels(deg, M):
+    """max_sh_degree < 3: the SH tensors hold only (deg+1)^2 coefficients (M != 16 takes the
+    unstaged path of both preprocess kernels).  Forward bit-exact, gradients within tolerance."""
+    inp = harness.build_inputs(device="cuda", P=2500, W=128, H=96, kind="trained", seed=10 + M, pose="orbit",
+                               sh_degree=deg, zero_shp_rest=True)
+    inp["shs"] = inp["shs"][:, :M, :].contiguous()
+    inp["shs_p"] = inp["shs_p"][:, :M, :].contiguous()
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    assert ours[0] == ref[0]
+    for i in range(1, 12):
+        assert torch.equal(ours[i], ref[i]), harness.FWD_NAMES[i]
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    rb = harness.call_backward(ref_driver.RefModule, inp, ref)
+    scale = float(rb[8].double().norm())
+    for i, k in enumerate(harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+            continue
+        a, b = (ob[i][0], rb[i][0]) if k == "sh_p" else (ob[i], rb[i])
+        assert a.shape == b.shape, k
+        err = float((a.double() - b.double()).norm())
+        assert err <= harness.GRAD_REL_L2 * max(float(b.double().norm()), 1e-3 * scale), (k, err)
 
 
 @needs_ref
