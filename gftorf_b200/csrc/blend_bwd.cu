@@ -67,17 +67,23 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 }  // namespace
 
 // WARPS warps = WARPS 8x4 patches of one tile per block (see blend_fwd.cu), BATCH = 32*WARPS.
-template <int WARPS, int MINB, bool SMEM_REDUCE>
+// WARP_MODE: no block-wide barrier — every warp gathers the tile list for itself, 32 Gaussians at a
+// time (one per lane) into a warp-private double buffer, only as far as its own furthest
+// contributor, and walks it at its own pace.  (In the block-synchronous mode 19 % of the warp
+// samples sit at the per-batch barrier, waiting for the busiest warp of the tile; ncu r1_d.)
+template <int WARPS, int MINB, bool SMEM_REDUCE, bool WARP_MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 blend_bwd_kernel(BlendBwdParams p) {
-  constexpr int BATCH = WARPS * 32;
+  constexpr int BATCH = WARP_MODE ? 32 : WARPS * 32;
   constexpr uint32_t SUBS = 8 / WARPS;
   using BwdBuf = BwdBufT<BATCH>;
   extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
-  BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw);
+  // the staging area is 2 x 256 records either way: one double buffer for the block, or a
+  // 2 x 32 double buffer per warp
+  BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw) + (WARP_MODE ? (threadIdx.x >> 5) * 2 : 0);
   __shared__ uint32_t s_wmax[WARPS];
   // SMEM_REDUCE: per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
-  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
+  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBufT<WARPS * 32>)) + (threadIdx.x >> 5) * RED_FLOATS;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const uint32_t warp = (blockIdx.x % SUBS) * WARPS + wib;   // patch index within the tile
@@ -146,12 +152,17 @@ blend_bwd_kernel(BlendBwdParams p) {
   uint32_t wmax = last_contributor;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s_wmax[wib] = wmax;
-  __syncthreads();
-  uint32_t bmax = 0;
+  int n_eff;
+  if (WARP_MODE) {
+    n_eff = min(n, (int)wmax);          // positions >= wmax contribute nothing for this warp
+  } else {
+    if (lane == 0) s_wmax[wib] = wmax;
+    __syncthreads();
+    uint32_t bmax = 0;
 #pragma unroll
-  for (int w = 0; w < WARPS; ++w) bmax = max(bmax, s_wmax[w]);
-  const int n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
+    for (int w = 0; w < WARPS; ++w) bmax = max(bmax, s_wmax[w]);
+    n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
+  }
 
   float T = T_final;
   float X = 0.f;     // contracted alpha*T-family recurrence
@@ -162,16 +173,17 @@ blend_bwd_kernel(BlendBwdParams p) {
   auto stage = [&](int b, int which) {
     const int base = b * BATCH;
     const int m = min(BATCH, n_eff - base);
-    if ((int)tid < m) {
-      const int g = (int)__ldg(p.point_list + range.x + base + tid);
+    const int slot = WARP_MODE ? (int)lane : (int)tid;
+    if (slot < m) {
+      const int g = (int)__ldg(p.point_list + range.x + base + slot);
       const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
       BwdBuf& d = buf[which];
-      d.id[tid] = g;
-      cp_async16(&d.r0[tid], r + 0);
-      cp_async16(&d.r1[tid], r + 1);
-      cp_async16(&d.r2[tid], r + 2);
-      cp_async16(&d.r3[tid], r + 3);
-      cp_async16(&d.r4[tid], r + 4);
+      d.id[slot] = g;
+      cp_async16(&d.r0[slot], r + 0);
+      cp_async16(&d.r1[slot], r + 1);
+      cp_async16(&d.r2[slot], r + 2);
+      cp_async16(&d.r3[slot], r + 3);
+      cp_async16(&d.r4[slot], r + 4);
     }
     cp_async_commit();
   };
@@ -299,7 +311,8 @@ blend_bwd_kernel(BlendBwdParams p) {
   if (nb > 0) stage(nb - 1, cur);
   for (int b = nb - 1; b >= 0; --b) {
     cp_async_wait_all();
-    __syncthreads();                       // batch b is in buf[cur]; everyone left buf[cur^1]
+    // batch b is in buf[cur]; everyone (block, or warp in WARP_MODE) left buf[cur^1]
+    if (WARP_MODE) __syncwarp(); else __syncthreads();
     if (b > 0) stage(b - 1, cur ^ 1);      // gather the next (nearer) batch while this one is used
     const BwdBuf& s = buf[cur];
     const int base = b * BATCH;
@@ -335,12 +348,12 @@ blend_bwd_kernel(BlendBwdParams p) {
 }
 
 namespace {
-template <int WARPS, int MINB, bool SMEM_REDUCE>
+template <int WARPS, int MINB, bool SMEM_REDUCE, bool WARP_MODE = false>
 void launch_bwd_variant(const BlendBwdParams& p, int tiles, cudaStream_t stream) {
   const int smem = 2 * (int)sizeof(BwdBufT<WARPS * 32>) + (SMEM_REDUCE ? WARPS * RED_FLOATS * 4 : 0);
   static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE>, smem, &smem_ok);
-  blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
+  ensure_dynamic_smem(blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE, WARP_MODE>, smem, &smem_ok);
+  blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE, WARP_MODE><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
 }
 }  // namespace
 
@@ -367,7 +380,13 @@ void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
     const char* e = std::getenv("GFT_BWD_SMEM_REDUCE");
     return !(e && e[0] == '0');
   }();
-  if (smem_reduce) {
+  static const bool warp_mode = [] {
+    const char* e = std::getenv("GFT_BWD_WARP");
+    return e && e[0] == '1';
+  }();
+  if (warp_mode) {
+    launch_bwd_variant<8, 3, true, true>(p, tiles, stream);
+  } else if (smem_reduce) {
     if (blend_block_warps(tiles) == 8) launch_bwd_variant<8, 3, true>(p, tiles, stream);
     else launch_bwd_variant<4, 6, true>(p, tiles, stream);
   } else {

@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace gft {
 
 namespace {
@@ -266,6 +268,199 @@ blend_fwd_kernel(BlendFwdParams p) {
   }
 }
 
+// ---- warp-autonomous variant ------------------------------------------------------------------
+// Same arithmetic, no block-wide barrier: every warp gathers the tile's Gaussian list for itself,
+// 32 Gaussians (one per lane) at a time, with cp.async into a warp-private ring of WSTAGES slots,
+// and walks it at its own pace.  In the block-synchronous kernel above 25 % of the warp samples sit
+// at the per-batch barrier (warps whose patch sees few Gaussians wait for the busiest warp of the
+// tile, ncu r1_d); here a warp only ever waits for its own copies.  The price is that the 8 warps
+// of a tile each read the records (L1/L2 hits after the first) and flush their own `pixels`
+// counts (one atomic per (warp, Gaussian) with a contribution instead of one per (tile, Gaussian)).
+constexpr int WSTAGES = 2;
+struct WarpStage {
+  float4 r0[32], r1[32], r2[32], r3[32], r4[32];
+  int id[32];
+};
+
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(GFT_BLOCK, 4)
+blend_fwd_warp_kernel(BlendFwdParams p) {
+  extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpStage* ring = reinterpret_cast<WarpStage*>(fwd_smem_raw) + warp * WSTAGES;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
+  const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
+  const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
+  const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
+  const bool inside = pix_x < (uint32_t)p.W && pix_y < (uint32_t)p.H;
+  const uint32_t pix_id = (uint32_t)p.W * pix_y + pix_x;
+  const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+  const float patch_x0 = (float)px0, patch_x1 = (float)(px0 + 7u);
+  const float patch_y0 = (float)py0, patch_y1 = (float)(py0 + 3u);
+
+  const uint2 range = p.ranges[tile];
+  const int n = (int)(range.y - range.x);
+  const int nb = (n + 31) >> 5;
+
+  bool done = !inside;
+  float T = 1.0f;
+  uint32_t last_contributor = 0;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, P4 = 0.f, P5 = 0.f, P6 = 0.f;
+  float D = 0.f, A = 0.f, DD = 0.f, DD_D = 0.f, DD_D2 = 0.f;
+  float WD0 = 0.f, WD1 = 0.f, WD2 = 0.f;
+  bool first_hit = true;
+
+  auto issue = [&](int b) {
+    if (b < nb) {
+      const int j = b * 32 + (int)lane;
+      if (j < n) {
+        const int g = (int)__ldg(p.point_list + range.x + j);
+        const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
+        WarpStage& d = ring[b % WSTAGES];
+        d.id[lane] = g;
+        cp_async16_ca(&d.r0[lane], r + 0);
+        cp_async16_ca(&d.r1[lane], r + 1);
+        cp_async16_ca(&d.r2[lane], r + 2);
+        cp_async16_ca(&d.r3[lane], r + 3);
+        cp_async16_ca(&d.r4[lane], r + 4);
+      }
+    }
+    cp_async_commit();     // one group per batch slot, empty or not, so the group count stays uniform
+  };
+
+  if (!__all_sync(0xffffffffu, done)) {
+#pragma unroll
+    for (int b = 0; b < WSTAGES - 1; ++b) issue(b);
+    for (int b = 0; b < nb; ++b) {
+      issue(b + WSTAGES - 1);
+      cp_async_wait_group<WSTAGES - 1>();   // this lane's copies of batch b have landed ...
+      __syncwarp();                         // ... and so have the other lanes'
+      const WarpStage& s = ring[b % WSTAGES];
+      const int base = b * 32;
+      const int m = min(32, n - base);
+      bool hit = false;
+      if ((int)lane < m) {
+        const float4 g0 = s.r0[lane];
+        hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
+                g0.y - g0.w > patch_y1);
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      int mycnt = 0;
+      auto eval_alpha = [&](int k, float& alpha) -> bool {
+        const float4 g0 = s.r0[k];
+        const float4 g1 = s.r1[k];
+        const float dx = __fsub_rn(g0.x, pixfx);
+        const float dy = __fsub_rn(g0.y, pixfy);
+        const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
+        const bool neg = !(power > 0.0f);
+        alpha = fminf(0.99f, __fmul_rn(g1.w, expf(neg ? power : 0.0f)));
+        return neg && !(alpha < 1.0f / 255.0f);
+      };
+      auto apply = [&](int k, float alpha, bool pass) {
+        bool contrib = !done && pass;
+        float test_T = 0.f;
+        if (contrib) {
+          test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+          if (test_T < 0.0001f) { done = true; contrib = false; }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
+        if ((int)lane == k) mycnt = __popc(bal);
+        if (contrib) {
+          const float4 g2 = s.r2[k];
+          const float4 g3 = s.r3[k];
+          const float4 g4 = s.r4[k];
+          const float w = __fmul_rn(T, alpha);
+          const float wp = __fmul_rn(T, w);
+          C0 = __fmaf_rn(w, g2.x, C0);
+          C1 = __fmaf_rn(w, g2.y, C1);
+          C2 = __fmaf_rn(w, g2.z, C2);
+          P0 = __fmaf_rn(wp, g3.x, P0);
+          P1 = __fmaf_rn(wp, g3.y, P1);
+          P2 = __fmaf_rn(wp, g3.z, P2);
+          P3 = __fmaf_rn(wp, g3.w, P3);
+          P4 = __fmaf_rn(wp, g4.x, P4);
+          P5 = __fmaf_rn(wp, g4.y, P5);
+          P6 = __fmaf_rn(wp, g4.z, P6);
+          if (first_hit) { WD0 = alpha; WD1 = g2.w; WD2 = g3.z; first_hit = false; }
+          const float z = g4.w;
+          const float z2 = __fmul_rn(z, z);
+          const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
+          float t2 = __fmaf_rn(A, z2, -t1);
+          const float wz = __fmul_rn(w, z);
+          t2 = __fadd_rn(DD_D2, t2);
+          DD_D = __fadd_rn(DD_D, wz);
+          DD_D2 = __fmaf_rn(z, wz, DD_D2);
+          D = __fmaf_rn(w, g2.w, D);
+          DD = __fmaf_rn(w, t2, DD);
+          A = __fadd_rn(A, w);
+          T = test_T;
+          last_contributor = (uint32_t)(base + k + 1);
+        }
+      };
+      while (mask) {
+        const int b1 = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const bool two = mask != 0u;
+        const int b2 = two ? (__ffs(mask) - 1) : b1;
+        if (two) mask &= mask - 1;
+        float alpha1, alpha2;
+        const bool pass1 = eval_alpha(b1, alpha1);
+        const bool pass2 = eval_alpha(b2, alpha2);
+        apply(b1, alpha1, pass1);
+        if (two) apply(b2, alpha2, pass2);
+      }
+      if (mycnt) atomicAdd(p.pixels + s.id[lane], (float)mycnt);
+      const bool all_done = __all_sync(0xffffffffu, done);   // also orders this batch's reads before the next issue
+      if (all_done) break;
+    }
+    cp_async_wait_group<0>();
+  }
+
+  if (inside) {
+    const size_t HW = (size_t)p.H * (size_t)p.W;
+    p.img_state[pix_id] = make_float4(T, DD_D, DD_D2, __uint_as_float(last_contributor));
+    float bgv[7];
+    if (p.bg_mode == 0) {
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch * HW + pix_id);
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
+    }
+    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C0);
+    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C1);
+    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2);
+    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P0);
+    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P1);
+    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P2);
+    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P3);
+    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P4);
+    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P5);
+    p.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
+    p.out_depth[pix_id] = D;
+    p.out_acc[pix_id] = A;
+    p.out_depth_distortion[pix_id] = DD;
+    p.out_distribution[0 * HW + pix_id] = WD0;
+    p.out_distribution[1 * HW + pix_id] = WD1;
+    p.out_distribution[2 * HW + pix_id] = WD2;
+    if (p.out_normal) {
+      p.out_normal[0 * HW + pix_id] = 0.f;
+      p.out_normal[1 * HW + pix_id] = 0.f;
+      p.out_normal[2 * HW + pix_id] = 0.f;
+    }
+    if (p.out_entropy) p.out_entropy[pix_id] = 0.f;
+    if (p.out_amp_distortion) p.out_amp_distortion[pix_id] = 0.f;
+  }
+}
+
 namespace {
 template <int WARPS, int MINB>
 void launch_fwd_variant(const BlendFwdParams& p, int tiles, cudaStream_t stream) {
@@ -279,6 +474,20 @@ void launch_fwd_variant(const BlendFwdParams& p, int tiles, cudaStream_t stream)
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   const int tiles = p.grid_x * p.grid_y;
   if (tiles <= 0) return;
+  // default: the warp-autonomous kernel (4 % faster at 640x480, 2 % at 1080p on B200);
+  // GFT_FWD_WARP=0 selects the block-synchronous one for A/B runs
+  static const bool warp_mode = [] {
+    const char* e = std::getenv("GFT_FWD_WARP");
+    return !(e && e[0] == '0');
+  }();
+  if (warp_mode) {
+    const int smem = (GFT_BLOCK / 32) * WSTAGES * (int)sizeof(WarpStage);
+    static unsigned long long smem_ok = 0;
+    ensure_dynamic_smem(blend_fwd_warp_kernel, smem, &smem_ok);
+    blend_fwd_warp_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
+    note_launches(1);
+    return;
+  }
   switch (blend_block_warps(tiles)) {
     case 8: launch_fwd_variant<8, 4>(p, tiles, stream); break;
     default: launch_fwd_variant<4, 8>(p, tiles, stream); break;
