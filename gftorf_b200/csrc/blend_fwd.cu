@@ -289,7 +289,8 @@ __device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(GFT_BLOCK, 4)
+template <int MINB>
+__global__ void __launch_bounds__(GFT_BLOCK, MINB)
 blend_fwd_warp_kernel(BlendFwdParams p) {
   extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -482,9 +483,11 @@ void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   }();
   if (warp_mode) {
     const int smem = (GFT_BLOCK / 32) * WSTAGES * (int)sizeof(WarpStage);
+    // 4 resident blocks per SM (55 registers): 3 (67 registers) is 4-7 % slower, 5 (48 registers,
+    // 8 B spilled) 10-15 % slower on B200
     static unsigned long long smem_ok = 0;
-    ensure_dynamic_smem(blend_fwd_warp_kernel, smem, &smem_ok);
-    blend_fwd_warp_kernel<<<tiles, GFT_BLOCK, smem, stream>>>(p);
+    ensure_dynamic_smem(blend_fwd_warp_kernel<4>, smem, &smem_ok);
+    blend_fwd_warp_kernel<4><<<tiles, GFT_BLOCK, smem, stream>>>(p);
     note_launches(1);
     return;
   }
