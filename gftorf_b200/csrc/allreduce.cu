@@ -1,0 +1,83 @@
+// allreduce.cu — sum-allreduce of the flat gradient bucket through the NVSwitch (NVLS), for
+// sm_100a.  C ABI: include/gftorf_train.h.
+//
+// The one exchange step of a data-parallel iteration: every rank holds the
+// [P, 91] fp32 gradient bucket in SYMMETRIC memory (same allocation on every GPU, mapped through
+// an NVLink multicast object; the host side obtains it from torch.distributed._symmetric_memory).
+// Rank r owns the r-th slice of the bucket: it reads the slice through the multicast address with
+// `multimem.ld_reduce` — the switch fetches the element from every GPU and returns the SUM, so the
+// link carries one reduced copy — and writes the result back with `multimem.st`, which the switch
+// replicates into every GPU's buffer.  Per GPU and direction the links carry ~S bytes in total,
+// the lower bound for an allreduce; no staging buffers, no ring steps.  The caller brackets the
+// launch with two cross-GPU barriers (data complete before, results visible after).
+#include <cuda_runtime.h>
+#include <cstdlib>
+
+#include "../../include/gftorf_train.h"
+#include "kernels.h"
+
+namespace gft {
+namespace {
+
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float4* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int AR_UNROLL>
+__global__ void __launch_bounds__(256) nvls_allreduce_kernel(float4* __restrict__ mc, long long begin, long long end) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // AR_UNROLL independent reductions in flight per thread
+  for (; i + (AR_UNROLL - 1) * stride < end; i += AR_UNROLL * stride) {
+    float4 v[AR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) v[u] = mc_ld_reduce_add(mc + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) mc_st(mc + i + u * stride, v[u]);
+  }
+  for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce_add(mc + i));
+}
+
+}  // namespace
+}  // namespace gft
+
+extern "C" {
+
+int gft_nvls_allreduce_sum(float* multicast_ptr, long long n_floats, int rank, int world,
+                           gft_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!multicast_ptr) return gft::set_error(-1, "gft_nvls_allreduce_sum: null multicast pointer");
+  if (world <= 0 || rank < 0 || rank >= world) return gft::set_error(-1, "gft_nvls_allreduce_sum: bad rank / world");
+  if (n_floats < 0 || (n_floats & 3) || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
+    return gft::set_error(-1, "gft_nvls_allreduce_sum: length must be a multiple of 4 floats, pointer 16-byte aligned");
+  const long long total = n_floats >> 2;
+  const long long per = (total + world - 1) / world;
+  const long long begin = per * rank, end = begin + per < total ? begin + per : total;
+  if (begin >= end) return 0;
+  static const int env_blocks = [] { const char* e = std::getenv("GFT_NVLS_BLOCKS"); return e ? std::atoi(e) : 0; }();
+  static const int env_unroll = [] { const char* e = std::getenv("GFT_NVLS_UNROLL"); return e ? std::atoi(e) : 0; }();
+  const int unroll = env_unroll == 8 ? 8 : (env_unroll == 2 ? 2 : 4);
+  long long blocks = (end - begin + 256 * unroll - 1) / (256 * unroll);
+  const long long cap = env_blocks > 0 ? env_blocks : 148 * 8;
+  if (blocks > cap) blocks = cap;
+  float4* mc = reinterpret_cast<float4*>(multicast_ptr);
+  if (unroll == 8) gft::nvls_allreduce_kernel<8><<<(int)blocks, 256, 0, stream>>>(mc, begin, end);
+  else if (unroll == 2) gft::nvls_allreduce_kernel<2><<<(int)blocks, 256, 0, stream>>>(mc, begin, end);
+  else gft::nvls_allreduce_kernel<4><<<(int)blocks, 256, 0, stream>>>(mc, begin, end);
+  gft::note_launches(1);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

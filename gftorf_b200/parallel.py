@@ -40,7 +40,8 @@ class GradBucket:
     the gradients of all local views in place and the collective runs on the buffer as it stands —
     no pack or copy step between the last backward and the allreduce."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], scalars: Sequence[torch.Tensor] = ()):
+    def __init__(self, params: Dict[str, torch.Tensor], scalars: Sequence[torch.Tensor] = (),
+                 symmetric: bool = False, group=None):
         self.names = [n for n, _ in PARAM_LAYOUT if n in params]
         self.params = params
         self.scalars = list(scalars)
@@ -50,8 +51,30 @@ class GradBucket:
         for n in sizes:
             self.offsets.append(cur)
             cur += (n + 3) // 4 * 4  # 16-byte aligned slices
-        self.flat = torch.zeros(cur, dtype=torch.float32, device=ref.device)
         self.sizes = sizes
+        self._symm = None
+        if symmetric:
+            self.flat = self._alloc_symmetric(cur, ref.device, group)
+        else:
+            self.flat = torch.zeros(cur, dtype=torch.float32, device=ref.device)
+
+    def _alloc_symmetric(self, n, device, group):
+        """The bucket in symmetric memory bound to an NVLink multicast object, so the exchange can
+        run through the switch (`gft_nvls_allreduce_sum`).  Collective: every rank of `group` must
+        construct its bucket at the same point.  Falls back to an ordinary tensor (and NCCL) when
+        the platform offers no multicast."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g = group if group is not None else dist.group.WORLD
+            flat = symm.empty(n, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(flat, g.group_name)
+            flat.zero_()
+            if int(hdl.multicast_ptr) != 0:
+                self._symm = hdl
+            return flat
+        except Exception:
+            self._symm = None
+            return torch.zeros(n, dtype=torch.float32, device=device)
 
     def views(self):
         tensors = [self.params[n] for n in self.names] + self.scalars
@@ -82,6 +105,24 @@ class GradBucket:
     def allreduce(self, group=None, average: bool = False, async_op: bool = False):
         """Sum (or mean) over ranks.  No-op in a single process."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if self._symm is not None and not async_op:
+            # through the NVSwitch: barrier, one kernel (multimem.ld_reduce + multimem.st on this
+            # rank's slice), barrier — all on the current stream
+            import ctypes as C
+            from . import train_ops
+            hdl = self._symm
+            lib = train_ops._lib()
+            hdl.barrier(channel=0)
+            mc = int(hdl.multicast_ptr) + int(self.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])
+            stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            with torch.cuda.device(self.flat.device):
+                rc = lib.gft_nvls_allreduce_sum(C.c_void_p(mc), C.c_longlong(self.flat.numel()), hdl.rank,
+                                                hdl.world_size, stream)
+            train_ops._check(rc, "gft_nvls_allreduce_sum")
+            hdl.barrier(channel=1)
+            if average:
+                self.flat.div_(hdl.world_size)
             return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if average:

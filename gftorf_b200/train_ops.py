@@ -94,6 +94,8 @@ def _lib():
         lib.gft_densify_plan.restype = C.c_int
         lib.gft_densify_apply.argtypes = [C.POINTER(GftDensifyApplyArgs), C.c_void_p]
         lib.gft_densify_apply.restype = C.c_int
+        lib.gft_nvls_allreduce_sum.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+        lib.gft_nvls_allreduce_sum.restype = C.c_int
         _declared = True
     return lib
 

@@ -208,6 +208,21 @@ typedef struct GftDensifyApplyArgs {
 
 int gft_densify_apply(const GftDensifyApplyArgs* args, gft_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * e — the exchange step of a data-parallel iteration: in-place sum-allreduce of
+ * the flat gradient bucket over the GPUs of one NVSwitch domain, through the switch's multicast /
+ * in-network reduction (NVLS).  The reference has no multi-GPU code; this stands where an
+ * ncclAllReduce(sum, fp32) would.
+ *
+ * `multicast_ptr` is the MULTICAST address of the bucket: the same symmetric allocation on every
+ * rank, bound to an NVLink multicast object (the Python side gets it from
+ * torch.distributed._symmetric_memory: rendezvous(t).multicast_ptr + offset).  Rank r reduces and
+ * re-broadcasts the r-th 1/world slice.  The caller must run a cross-GPU barrier on the stream
+ * before the call (every rank's bucket complete) and after it (results visible everywhere).
+ * ---------------------------------------------------------------------------------------- */
+int gft_nvls_allreduce_sum(float* multicast_ptr, long long n_floats, int rank, int world,
+                           gft_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
