@@ -200,15 +200,23 @@ __device__ __forceinline__ void warp_stage_in(const float* __restrict__ gbase, i
     sbuf[r * (ROW + 1) + c] = __ldg(gbase + e);
   }
 }
-template <int ROW, bool ACC = false>
+// Gradient store modes of the backward: 0 overwrite, 1 add (plain read-modify-write: one view at
+// a time per buffer), 2 atomic add (several views may run concurrently into one bucket).
+template <int ACC>
+__device__ __forceinline__ void acc_store(float* p, float v) {
+  if (ACC == 0) *p = v;
+  else if (ACC == 1) *p += v;
+  else atomicAdd(p, v);
+}
+
+template <int ROW, int ACC = 0>
 __device__ __forceinline__ void warp_stage_out(float* __restrict__ gbase, int nrows,
                                                const float* sbuf, uint32_t lane) {
   const int total = nrows * ROW;
 #pragma unroll 4
   for (int e = (int)lane; e < total; e += 32) {
     const int r = e / ROW, c = e - r * ROW;
-    if (ACC) gbase[e] += sbuf[r * (ROW + 1) + c];
-    else gbase[e] = sbuf[r * (ROW + 1) + c];
+    acc_store<ACC>(gbase + e, sbuf[r * (ROW + 1) + c]);
   }
 }
 #define GFT_STAGE_FLOATS_PER_WARP (32 * 49)

@@ -147,7 +147,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 //      the warp's 32 Gaussians are one contiguous chunk, staged through shared memory (coalesced
 //      in), differentiated in place, and streamed out coalesced as dL_dsh / dL_dsh_p;
 //   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation.
-template <bool ACC>
+template <int ACC>
 __global__ void __launch_bounds__(GFT_BLOCK)
 preprocess_bwd_kernel(PreprocessBwdParams p) {
   // ACC: add into the six parameter-gradient outputs (means3D, sh, sh_p, opacity, scales,
@@ -241,7 +241,7 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
         float tmp[48];
         dL_ddir = sh_backward<3>(p.D, min(p.M, 16), dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g, tmp);
         const int ncf = 3 * (p.D + 1) * (p.D + 1);
-        for (int k = 0; k < ncf; ++k) p.dL_dsh[(size_t)idx * p.M * 3 + k] += tmp[k];
+        for (int k = 0; k < ncf; ++k) acc_store<ACC>(p.dL_dsh + (size_t)idx * p.M * 3 + k, tmp[k]);
       }
       const V3 dm = dnormvdv3(dir_orig, dL_ddir);
       dmx += dm.x; dmy += dm.y; dmz += dm.z;
@@ -318,7 +318,7 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
         float tmp[32];
         dL_ddir = sh_backward<2>(p.D, min(p.M_p, 16), dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2, gpa, tmp);
         const int ncf = 2 * (p.D + 1) * (p.D + 1);
-        for (int k = 0; k < ncf; ++k) p.dL_dsh_p[(size_t)idx * p.M_p * 2 + k] += tmp[k];
+        for (int k = 0; k < ncf; ++k) acc_store<ACC>(p.dL_dsh_p + (size_t)idx * p.M_p * 2 + k, tmp[k]);
       }
       const V3 dm = dnormvdv3(dir_orig, dL_ddir);
       dmx += dm.x; dmy += dm.y; dmz += dm.z;
@@ -353,7 +353,7 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     p.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
     p.dL_dmeans2D[3 * (size_t)idx + 1] = dm2y;
     p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    if (ACC) p.dL_dopacity[idx] += dopac; else p.dL_dopacity[idx] = dopac;
+    acc_store<ACC>(p.dL_dopacity + idx, dopac);
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol[k];
     if (p.dL_dconic) {
       reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
@@ -458,15 +458,9 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dmz += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
     }
 
-    if (ACC) {
-      p.dL_dmeans3D[3 * (size_t)idx + 0] += dmx;
-      p.dL_dmeans3D[3 * (size_t)idx + 1] += dmy;
-      p.dL_dmeans3D[3 * (size_t)idx + 2] += dmz;
-    } else {
-      p.dL_dmeans3D[3 * (size_t)idx + 0] = dmx;
-      p.dL_dmeans3D[3 * (size_t)idx + 1] = dmy;
-      p.dL_dmeans3D[3 * (size_t)idx + 2] = dmz;
-    }
+    acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 0, dmx);
+    acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 1, dmy);
+    acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 2, dmz);
 
     // ---------------- cov3D -> scale, rotation (backward.cu:399-462) -------------------------
     if (p.scales != nullptr) {
@@ -500,15 +494,9 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       const float ds_x = R00 * D00 + R10 * D10 + R20 * D20;
       const float ds_y = R01 * D01 + R11 * D11 + R21 * D21;
       const float ds_z = R02 * D02 + R12 * D12 + R22 * D22;
-      if (ACC) {
-        p.dL_dscales[3 * (size_t)idx + 0] += ds_x;
-        p.dL_dscales[3 * (size_t)idx + 1] += ds_y;
-        p.dL_dscales[3 * (size_t)idx + 2] += ds_z;
-      } else {
-        p.dL_dscales[3 * (size_t)idx + 0] = ds_x;
-        p.dL_dscales[3 * (size_t)idx + 1] = ds_y;
-        p.dL_dscales[3 * (size_t)idx + 2] = ds_z;
-      }
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 0, ds_x);
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 1, ds_y);
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 2, ds_z);
       // dL_dMt[i] *= s_i ; Mt[i][j] = D[j][i] * s_i
       const float t00 = D00 * sx, t01 = D10 * sx, t02 = D20 * sx;
       const float t10 = D01 * sy, t11 = D11 * sy, t12 = D21 * sy;
@@ -519,11 +507,15 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dq.z = 2 * x * (t10 + t01) + 2 * r * (t20 - t02) + 2 * z * (t12 + t21) - 4 * y * (t22 + t00);
       dq.w = 2 * r * (t01 - t10) + 2 * x * (t20 + t02) + 2 * y * (t12 + t21) - 4 * z * (t11 + t00);
       float4* dq_out = reinterpret_cast<float4*>(p.dL_drotations) + idx;
-      if (ACC) {
-        const float4 o = *dq_out;
-        dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+      if (ACC == 2) {
+        atomicAdd(dq_out, dq);          // RED.E.ADD.F32x4
+      } else {
+        if (ACC == 1) {
+          const float4 o = *dq_out;
+          dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+        }
+        *dq_out = dq;
       }
-      *dq_out = dq;
     }
   }
 
@@ -551,13 +543,16 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
-  static unsigned long long smem_ok0 = 0, smem_ok1 = 0;
-  if (p.accumulate) {
-    ensure_dynamic_smem(preprocess_bwd_kernel<true>, smem, &smem_ok1);
-    preprocess_bwd_kernel<true><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  static unsigned long long smem_ok0 = 0, smem_ok1 = 0, smem_ok2 = 0;
+  if (p.accumulate == 2) {          // atomic adds: several views may target the same bucket at once
+    ensure_dynamic_smem(preprocess_bwd_kernel<2>, smem, &smem_ok2);
+    preprocess_bwd_kernel<2><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  } else if (p.accumulate) {
+    ensure_dynamic_smem(preprocess_bwd_kernel<1>, smem, &smem_ok1);
+    preprocess_bwd_kernel<1><<<blocks, GFT_BLOCK, smem, stream>>>(p);
   } else {
-    ensure_dynamic_smem(preprocess_bwd_kernel<false>, smem, &smem_ok0);
-    preprocess_bwd_kernel<false><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+    ensure_dynamic_smem(preprocess_bwd_kernel<0>, smem, &smem_ok0);
+    preprocess_bwd_kernel<0><<<blocks, GFT_BLOCK, smem, stream>>>(p);
   }
   note_launches(1);
 }

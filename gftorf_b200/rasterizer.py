@@ -235,7 +235,9 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     (GftBackwardArgs.accumulate) — the slices of a `parallel.GradBucket`, so the views of a batch
     accumulate in the buffer the collective runs on.  `accumulate=False` makes this call OVERWRITE
     the `grad_out` tensors instead (every row is written, zeros for culled Gaussians): the first
-    view of an iteration then needs no zero fill of the bucket."""
+    view of an iteration then needs no zero fill of the bucket.  `accumulate="atomic"` adds with
+    atomics, so the backward calls of several views may run concurrently on different streams
+    into one (zero-filled) bucket (`parallel.ViewRunner`)."""
     lib = _capi.lib()
     dev = means3D.device
     P = int(means3D.shape[0])
@@ -333,7 +335,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
     a.near_n, a.far_n, a.depth_range = float(near_n), float(far_n), float(depth_range)
     a.use_view_dependent_phase = int(bool(use_view_dependent_phase))
     a.phase_offset, a.dc_offset = _as_float(phase_offset), _as_float(dc_offset)
-    a.accumulate = 1 if (grad_out is not None and accumulate) else 0
+    a.accumulate = 0 if (grad_out is None or not accumulate) else (2 if accumulate == "atomic" else 1)
 
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):

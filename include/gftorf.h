@@ -188,7 +188,9 @@ typedef struct GftBackwardArgs {
    * dL_dopacity, dL_dscales, dL_drotations, dL_dphase_offset and dL_ddc_offset are ADDED TO
    * (rows of culled Gaussians untouched), so the views of a multi-camera batch accumulate
    * straight into one gradient bucket (the reference gets the same sum from autograd's
-   * AccumulateGrad, train.py:279).  dL_dmeans2D and the optional intermediates stay per view. */
+   * AccumulateGrad, train.py:279).  dL_dmeans2D and the optional intermediates stay per view.
+   * 2: as 1 with ATOMIC adds, so backward calls of different views may run concurrently (on
+   * different streams) into the same bucket; the bucket must have been zero-filled. */
   int accumulate;
 } GftBackwardArgs;
 

@@ -600,6 +600,49 @@ def test_accumulate_mode_adds_views_into_the_bucket():
     assert harness.rel_l2(bucket.flat, summed) <= harness.GRAD_REL_L2
 
 
+def test_concurrent_views_with_atomic_accumulation():
+    """parallel.ViewRunner: the two views of an iteration on two streams / host threads, gradients
+    added into one zero-filled bucket with atomics.  Same images as the sequential calls (bit for
+    bit), same gradient sums within the gradient tolerance; errors in a view reach the caller."""
+    from gftorf_b200 import parallel
+    inp_a = harness.build_inputs(device="cuda", P=20000, W=320, H=240, kind="trained", seed=41)
+    inp_b = harness.build_inputs(device="cuda", P=20000, W=256, H=192, kind="trained", seed=41, pose="orbit")
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p"):
+        inp_b[k] = inp_a[k]
+    params = {k: inp_a[k] for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p")}
+    bucket = parallel.GradBucket(params, [torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")])
+    go = bucket.grad_out()
+    seq = []
+    for inp in (inp_a, inp_b):
+        f = harness.call_forward(rasterizer._C, inp)
+        seq.append((f, harness.call_backward(rasterizer._C, inp, f)))
+    runner = parallel.ViewRunner(2)
+
+    def view(inp):
+        f = harness.call_forward(rasterizer._C, inp)
+        b = harness.call_backward(rasterizer._C, inp, f, grad_out=go, accumulate="atomic")
+        return f, b
+
+    for _ in range(3):                       # repeated: a race would not show every time
+        bucket.zero()
+        res = runner.run([lambda: view(inp_a), lambda: view(inp_b)])
+        torch.cuda.synchronize()
+        for (f, b), (fs, bs) in zip(res, seq):
+            assert f[0] == fs[0]
+            for i in range(1, 12):
+                assert torch.equal(f[i], fs[i]), harness.FWD_NAMES[i]
+            assert harness.rel_l2(b[0], bs[0]) <= harness.GRAD_REL_L2      # means2D, per view
+        for name, i in dict(means3D=4, shs=6, shs_p=7, opacities=3, scales=8, rotations=9).items():
+            assert harness.rel_l2(go[name], seq[0][1][i] + seq[1][1][i]) <= harness.GRAD_REL_L2, name
+
+    def boom():
+        raise ValueError("view failed")
+    with pytest.raises(ValueError, match="view failed"):
+        runner.run([lambda: view(inp_a), boom])
+    torch.cuda.synchronize()
+    runner.close()
+
+
 def test_hinted_forward_is_identical_and_survives_a_bad_hint():
     """GftForwardArgs.R_hint: same bits as the exact mode for a generous hint, an exact hint, and a
     hint that is too small (overflow -> the tail of the pipeline re-runs with the right size)."""
