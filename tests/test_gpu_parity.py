@@ -600,6 +600,50 @@ def test_accumulate_mode_adds_views_into_the_bucket():
     assert harness.rel_l2(bucket.flat, summed) <= harness.GRAD_REL_L2
 
 
+def test_concurrent_views_through_the_autograd_surface():
+    """Two views of one iteration issued through parallel.ViewRunner with the PUBLIC surface
+    (GaussianRasterizer + autograd.backward from the two host threads): the leaves' accumulated
+    gradients equal those of the two views run one after the other."""
+    from gftorf_b200 import parallel
+    inp_a = harness.build_inputs(device="cuda", P=8000, W=160, H=120, kind="trained", seed=51)
+    inp_b = harness.build_inputs(device="cuda", P=8000, W=128, H=96, kind="trained", seed=51, pose="orbit")
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+
+    def run(concurrent):
+        leaves = {k: inp_a[k].clone().requires_grad_(True) for k in names}
+        m2d = torch.zeros_like(inp_a["means3D"], requires_grad=True)
+
+        def view(inp):
+            s = rasterizer.GaussianRasterizationSettings(
+                image_height=inp["H"], image_width=inp["W"], tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"],
+                bg=inp["bg"], scale_modifier=1.0, viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+                sh_degree=3, campos=inp["campos"], prefiltered=False, debug=False, near_n=inp["near_n"],
+                far_n=inp["far_n"], depth_range=inp["depth_range"])
+            out = rasterizer.GaussianRasterizer(s)(
+                means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], shs=leaves["shs"],
+                shs_p=leaves["shs_p"], scales=leaves["scales"], rotations=leaves["rotations"])
+            g = inp["grads"]
+            torch.autograd.backward([out[0], out[1], out[2], out[4], out[6]],
+                                    [g["color"], g["phasor"], g["depth"], g["acc"], g["depth_distortion"]])
+            return out[0].clone()
+
+        if concurrent:
+            runner = parallel.ViewRunner(2)
+            imgs = runner.run([lambda: view(inp_a), lambda: view(inp_b)])
+            runner.close()
+        else:
+            imgs = [view(inp_a), view(inp_b)]
+        torch.cuda.synchronize()
+        return imgs, {k: leaves[k].grad.clone() for k in names}
+
+    imgs_s, grads_s = run(False)
+    imgs_c, grads_c = run(True)
+    for a, b in zip(imgs_s, imgs_c):
+        assert torch.equal(a, b)
+    for k in names:
+        assert harness.rel_l2(grads_c[k], grads_s[k]) <= harness.GRAD_REL_L2, k
+
+
 def test_concurrent_views_with_atomic_accumulation():
     """parallel.ViewRunner: the two views of an iteration on two streams / host threads, gradients
     added into one zero-filled bucket with atomics.  Same images as the sequential calls (bit for
