@@ -12,11 +12,17 @@ step ends with the NCCL sum-allreduce of the flat per-Gaussian gradient bucket (
 
   value  : Mpix/s of pixels taken through forward+backward, whole job, inputs resident in HBM,
            called through the C-ABI entry points (gftorf_b200.rasterizer._C);
-           ms_per_step is BASELINE's "fwd+bwd ms/iter".
-  e2e    : the same metric through the public autograd surface (GaussianRasterizer + backward())
-           with HOST buffers: pinned-host -> device copies of all Gaussian parameters, cameras,
-           background and pixel gradients, and device -> host reads of the parameter gradients
-           and the rendered images, all inside the timed region.
+           ms_per_step is BASELINE's "fwd+bwd ms/iter".  The two views of a step are in flight
+           concurrently (parallel.ViewRunner: one stream + host thread per view, gradients added
+           into the zero-filled bucket with atomics); --sequential-views runs them back to back.
+           Per-kernel times (stage_ms_per_step, roofline) come from a second, sequential pass of
+           the same steps, because concurrent kernels share the SMs.
+  e2e    : the same metric through the public autograd surface (GaussianRasterizer + backward(),
+           the two views through ViewRunner) with HOST buffers: pinned-host -> device copies of
+           all Gaussian parameters, cameras, background and pixel gradients, and device -> host
+           reads of the parameter gradients and the rendered images, all inside the timed region.
+  next_rows : the SURVEY §8f operators (assembly, loss, Adam) and distCUDA2 at the workload's
+           size, each beside the reference's implementation of the same step on the same GPU.
   --impl reference : the UNMODIFIED reference kernels (oracle/_ref/libgftorf_ref.so, built from
            /root/reference by oracle/Makefile) driven the way the reference's torch binding drives
            them (oracle/ref_driver.py) — same workload, same metric, on the GPU.  The reference has
