@@ -505,14 +505,17 @@ def run_gpu(args, impl):
             Ts = [((v["W"] + 15) // 16) * ((v["H"] + 15) // 16) for v in views]
             byts = float(np.mean([stage_bytes(dom, P, Vs[i], Rs[i], Ns[i], Ts[i]) for i in range(len(views))]))
             ach = byts / (mean_ms[dom] * 1e-3) / 1e9
-            traffic = None
+            traffic = issue_busy = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tj.get(dom)
+                issue_busy = tj.get("_issue_slots_busy_per_active_cycle", {}).get(dom)
             except Exception:
                 pass
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 2),
                                 "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
                                 "traffic": traffic,
+                                "issue_slots_busy": issue_busy,   # ncu smsp__issue_active per active cycle (profiles/)
                                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                                 "algorithmic_bytes_per_launch": int(byts),
                                 "kernel_ms_per_launch": round(mean_ms[dom], 4),

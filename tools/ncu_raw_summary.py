@@ -34,6 +34,7 @@ def main():
     ki = H.index("Kernel Name")
     cols = [m for m in METRICS if m in H]
     traffic = {}
+    issue = {}
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel"] + [f"{m} [{U[H.index(m)]}]" for m in cols])
@@ -43,12 +44,20 @@ def main():
             try:
                 b = sum(float(r[H.index(m)].replace(",", "")) * UNIT[U[H.index(m)]]
                         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                traffic.setdefault(name.split("<")[0].replace("_kernel", ""), []).append(b)
+                traffic.setdefault(name.split("<")[0].replace("_kernel", "").replace("_warp", ""), []).append(b)
+            except Exception:
+                pass
+            try:
+                key = name.split("<")[0].replace("_kernel", "").replace("_warp", "")
+                issue.setdefault(key, []).append(float(r[H.index("smsp__issue_active.avg.per_cycle_active")]))
             except Exception:
                 pass
     print(f"{out}: {len(data)} launches, {len(cols)} metrics")
     if len(sys.argv) > 3:
-        json.dump({k: int(sum(v) / len(v)) for k, v in traffic.items()}, open(sys.argv[3], "w"), indent=1)
+        doc = {k: int(sum(v) / len(v)) for k, v in traffic.items()}
+        doc["_issue_slots_busy_per_active_cycle"] = {k: round(sum(v) / len(v), 3) for k, v in issue.items()}
+        doc["_source"] = src
+        json.dump(doc, open(sys.argv[3], "w"), indent=1)
         print(sys.argv[3], {k: int(sum(v) / len(v)) for k, v in traffic.items()})
 
 
