@@ -219,32 +219,38 @@ blend_bwd_kernel(BlendBwdParams p) {
       const float wp = w * T;         // weight of the phasor family, alpha*T*T
 
       const float z = g4.w;
-      const float kappa = g2.x * gc0 + g2.y * gc1 + g2.z * gc2;
-      const float x_tot = kappa + g2.w * gd + (z * (z * k2 - k1) + k0);
-      const float pi = g3.x * gp0 + g3.y * gp1 + g3.z * gp2 + g3.w * gp3 + g4.x * gp4 +
-                       g4.y * gp5 + g4.z * gp6;
+      // the two dot products with packed fp32x2 FMAs (pairs = halves of the 128-bit record loads)
+      const float2 kd = fma2(make_float2(g2.z, g2.w), make_float2(gc2, gd),
+                             mul2(make_float2(g2.x, g2.y), make_float2(gc0, gc1)));
+      const float x_tot = (kd.x + kd.y) + (z * (z * k2 - k1) + k0);
+      const float2 pd = fma2(make_float2(g4.x, g4.y), make_float2(gp4, gp5),
+                             fma2(make_float2(g3.z, g3.w), make_float2(gp2, gp3),
+                                  mul2(make_float2(g3.x, g3.y), make_float2(gp0, gp1))));
+      const float pi = (pd.x + pd.y) + g4.z * gp6;
       const float dL_dalpha = (x_tot - X) * T + (pi - 2.f * om * Bp) * (T * T) -
                               (T_final * inv_om) * bgdot;
-      X = alpha * x_tot + om * X;
-      Bp = alpha * pi + (om * om) * Bp;
+      // X <- alpha x + om X ;  Bp <- alpha pi + om^2 Bp
+      const float2 rec = fma2(make_float2(alpha, alpha), make_float2(x_tot, pi),
+                              mul2(make_float2(om, om * om), make_float2(X, Bp)));
+      X = rec.x;
+      Bp = rec.y;
 
       const float h = g1.w * dL_dalpha * G;   // dL_dG * G
-      const float hx = h * dx, hy = h * dy;
-      v[0] = hx;
-      v[1] = hy;
-      v[2] = hx * dx;
-      v[3] = hx * dy;
-      v[4] = hy * dy;
+      const float2 dxy = make_float2(dx, dy);
+      const float2 hxy = mul2(make_float2(h, h), dxy);            // h dx, h dy
+      const float2 hxx = mul2(make_float2(hxy.x, hxy.x), dxy);    // h dx dx, h dx dy
+      v[0] = hxy.x;
+      v[1] = hxy.y;
+      v[2] = hxx.x;
+      v[3] = hxx.y;
+      v[4] = hxy.y * dy;
       v[5] = G * dL_dalpha;
-      v[6] = w * gc0;
-      v[7] = w * gc1;
-      v[8] = w * gc2;
-      v[9] = w * gd;
+      const float2 w2 = make_float2(w, w), wp2 = make_float2(wp, wp);
+      const float2 v67 = mul2(w2, make_float2(gc0, gc1)), v89 = mul2(w2, make_float2(gc2, gd));
+      const float2 vAB = mul2(wp2, make_float2(gA, gB)), vCS = mul2(wp2, make_float2(gp2, gS));
+      v[6] = v67.x; v[7] = v67.y; v[8] = v89.x; v[9] = v89.y;
       v[10] = w * (2.f * z * k2 - k1);
-      v[11] = wp * gA;
-      v[12] = wp * gB;
-      v[13] = wp * gp2;
-      v[14] = wp * gS;
+      v[11] = vAB.x; v[12] = vAB.y; v[13] = vCS.x; v[14] = vCS.y;
     }
 
     if (SMEM_REDUCE) {
@@ -256,8 +262,13 @@ blend_bwd_kernel(BlendBwdParams p) {
       __syncwarp();
       const float4* rp = reinterpret_cast<const float4*>(red + (lane >> 1) * RED_STRIDE + (lane & 1u) * 16u);
       const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
-      float sum = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
-                  (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+      // 16 -> 1 with packed adds: 7 FADD2 + 1 FADD instead of 15 FADD
+      const float2 s0 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
+      const float2 s1 = add2(make_float2(q1.x, q1.y), make_float2(q1.z, q1.w));
+      const float2 s2 = add2(make_float2(q2.x, q2.y), make_float2(q2.z, q2.w));
+      const float2 s3 = add2(make_float2(q3.x, q3.y), make_float2(q3.z, q3.w));
+      const float2 st = add2(add2(s0, s1), add2(s2, s3));
+      float sum = st.x + st.y;
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       __syncwarp();
       if ((lane & 1u) == 0u && lane != 30u)

@@ -313,9 +313,11 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
   bool done = !inside;
   float T = 1.0f;
   uint32_t last_contributor = 0;
-  float C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, P4 = 0.f, P5 = 0.f, P6 = 0.f;
-  float D = 0.f, A = 0.f, DD = 0.f, DD_D = 0.f, DD_D2 = 0.f;
+  // accumulators in pairs for the packed FFMA2: (C0,C1) (C2,D) use weight w, (P0,P1) (P2,P3)
+  // (P4,P5) use weight w*T — the pairs are the halves of the 128-bit record loads
+  float2 C01 = make_float2(0.f, 0.f), C2D = C01, P01 = C01, P23 = C01, P45 = C01;
+  float P6 = 0.f;
+  float A = 0.f, DD = 0.f, DD_D = 0.f, DD_D2 = 0.f;
   float WD0 = 0.f, WD1 = 0.f, WD2 = 0.f;
   bool first_hit = true;
 
@@ -380,15 +382,12 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
           const float4 g4 = s.r4[k];
           const float w = __fmul_rn(T, alpha);
           const float wp = __fmul_rn(T, w);
-          C0 = __fmaf_rn(w, g2.x, C0);
-          C1 = __fmaf_rn(w, g2.y, C1);
-          C2 = __fmaf_rn(w, g2.z, C2);
-          P0 = __fmaf_rn(wp, g3.x, P0);
-          P1 = __fmaf_rn(wp, g3.y, P1);
-          P2 = __fmaf_rn(wp, g3.z, P2);
-          P3 = __fmaf_rn(wp, g3.w, P3);
-          P4 = __fmaf_rn(wp, g4.x, P4);
-          P5 = __fmaf_rn(wp, g4.y, P5);
+          const float2 w2 = make_float2(w, w), wp2 = make_float2(wp, wp);
+          C01 = fma2(w2, make_float2(g2.x, g2.y), C01);
+          C2D = fma2(w2, make_float2(g2.z, g2.w), C2D);    // .y is the depth accumulator D
+          P01 = fma2(wp2, make_float2(g3.x, g3.y), P01);
+          P23 = fma2(wp2, make_float2(g3.z, g3.w), P23);
+          P45 = fma2(wp2, make_float2(g4.x, g4.y), P45);
           P6 = __fmaf_rn(wp, g4.z, P6);
           if (first_hit) { WD0 = alpha; WD1 = g2.w; WD2 = g3.z; first_hit = false; }
           const float z = g4.w;
@@ -399,7 +398,6 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
           t2 = __fadd_rn(DD_D2, t2);
           DD_D = __fadd_rn(DD_D, wz);
           DD_D2 = __fmaf_rn(z, wz, DD_D2);
-          D = __fmaf_rn(w, g2.w, D);
           DD = __fmaf_rn(w, t2, DD);
           A = __fadd_rn(A, w);
           T = test_T;
@@ -436,17 +434,17 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
 #pragma unroll
       for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
     }
-    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C0);
-    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C1);
-    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2);
-    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P0);
-    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P1);
-    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P2);
-    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P3);
-    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P4);
-    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P5);
+    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C01.x);
+    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C01.y);
+    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2D.x);
+    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P01.x);
+    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P01.y);
+    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P23.x);
+    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P23.y);
+    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P45.x);
+    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P45.y);
     p.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
-    p.out_depth[pix_id] = D;
+    p.out_depth[pix_id] = C2D.y;
     p.out_acc[pix_id] = A;
     p.out_depth_distortion[pix_id] = DD;
     p.out_distribution[0 * HW + pix_id] = WD0;
