@@ -28,10 +28,13 @@ constexpr int ASM_BLOCK = 256;
 // (position, opacity, scale, rotation).  Phase B/C: the block's SH rows are contiguous chunks of
 // the output (256 x 3M and 256 x 2M floats): all threads walk them element by element, so stores
 // are fully coalesced and the gathers from the dc / rest / deformation arrays are contiguous runs.
+// MC: compile-time SH coefficient count (16 = the reference's sh_degree 3, the row lengths become
+// constants and the per-element divisions multiplications), 0 = take it from the arguments
+template <int MC>
 __global__ void __launch_bounds__(ASM_BLOCK) assemble_fwd_kernel(GftAssembleArgs a) {
   const int first = blockIdx.x * ASM_BLOCK;
   const int i = first + (int)threadIdx.x;
-  const int M = a.M;
+  const int M = MC ? MC : a.M;
   __shared__ int s_dyn[ASM_BLOCK];    // deformation row, -1: static, -2: excluded region / out of range
   int code = -2;
   if (i < a.P) {
@@ -113,10 +116,11 @@ __global__ void __launch_bounds__(ASM_BLOCK) assemble_fwd_kernel(GftAssembleArgs
   }
 }
 
+template <int MC>
 __global__ void __launch_bounds__(ASM_BLOCK) assemble_bwd_kernel(GftAssembleArgs a, GftAssembleGrads g) {
   const int first = blockIdx.x * ASM_BLOCK;
   const int i = first + (int)threadIdx.x;
-  const int M = a.M;
+  const int M = MC ? MC : a.M;
   __shared__ int s_dyn[ASM_BLOCK];
   int code = -2;
   if (i < a.P) {
@@ -272,7 +276,9 @@ int gft_assemble_forward(const GftAssembleArgs* a, gft_stream_t stream_) {
     return gft::set_error(-1, "gft_assemble_forward: required parameter pointer is null");
   if (!a->means3D || !a->opacities || !a->scales || !a->rotations || !a->shs || !a->shs_p)
     return gft::set_error(-1, "gft_assemble_forward: required output pointer is null");
-  gft::assemble_fwd_kernel<<<(a->P + gft::ASM_BLOCK - 1) / gft::ASM_BLOCK, gft::ASM_BLOCK, 0, stream>>>(*a);
+  const int blocks = (a->P + gft::ASM_BLOCK - 1) / gft::ASM_BLOCK;
+  if (a->M == 16) gft::assemble_fwd_kernel<16><<<blocks, gft::ASM_BLOCK, 0, stream>>>(*a);
+  else gft::assemble_fwd_kernel<0><<<blocks, gft::ASM_BLOCK, 0, stream>>>(*a);
   gft::note_launches(1);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(e));
@@ -292,7 +298,9 @@ int gft_assemble_backward(const GftAssembleArgs* a, const GftAssembleGrads* g, g
       !g->g_f_dc_phase || !g->g_f_dc_amp ||
       (a->M > 1 && (!g->g_f_rest_color || !g->g_f_rest_phase || !g->g_f_rest_amp)))
     return gft::set_error(-1, "gft_assemble_backward: outgoing gradient pointer is null");
-  gft::assemble_bwd_kernel<<<(a->P + gft::ASM_BLOCK - 1) / gft::ASM_BLOCK, gft::ASM_BLOCK, 0, stream>>>(*a, *g);
+  const int blocks = (a->P + gft::ASM_BLOCK - 1) / gft::ASM_BLOCK;
+  if (a->M == 16) gft::assemble_bwd_kernel<16><<<blocks, gft::ASM_BLOCK, 0, stream>>>(*a, *g);
+  else gft::assemble_bwd_kernel<0><<<blocks, gft::ASM_BLOCK, 0, stream>>>(*a, *g);
   gft::note_launches(1);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(e));
