@@ -220,7 +220,7 @@ template <int ROW>
 __device__ __forceinline__ void warp_stage_in(const float* __restrict__ gbase, int nrows,
                                               float* sbuf, uint32_t lane) {
   const int total = nrows * ROW;
-#pragma unroll 4
+#pragma unroll 12
   for (int e = (int)lane; e < total; e += 32) {
     const int r = e / ROW, c = e - r * ROW;
     sbuf[r * (ROW + 1) + c] = __ldg(gbase + e);
