@@ -148,7 +148,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 //      in), differentiated in place, and streamed out coalesced as dL_dsh / dL_dsh_p;
 //   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation.
 template <int ACC>
-__global__ void __launch_bounds__(GFT_BLOCK)
+__global__ void __launch_bounds__(GFT_BLOCK, 4)
 preprocess_bwd_kernel(PreprocessBwdParams p) {
   // ACC: add into the six parameter-gradient outputs (means3D, sh, sh_p, opacity, scales,
   // rotations) and the two scalar offsets instead of overwriting them — several views then
