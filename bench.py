@@ -292,14 +292,22 @@ def run_gpu(args, impl):
             dev_params[k].requires_grad_(True)
         dev_m2d = torch.zeros_like(params["means3D"], requires_grad=True)
 
+    side = {id(v): (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)) for v in views}
+
     def e2e_view_job(v, hv, dv, himg):
-        # one view through the public surface on the runner's stream: its own H2D copies, forward,
-        # autograd backward (gradients accumulate into the shared leaves), D2H of its images
+        # one view through the public surface on the runner's stream: forward, autograd backward
+        # (gradients accumulate into the shared leaves).  Its host copies ride on two side streams:
+        # the pixel gradients come up while the forward runs, the images go down while the
+        # backward runs.
+        cur = torch.cuda.current_stream()
+        up, down = side[id(v)]
         with torch.no_grad():
             for k in ("viewmatrix", "projmatrix", "campos"):
                 dv[k].copy_(hv[k], non_blocking=True)
-            for k, t in hv["grads"].items():
-                dv["grads"][k].copy_(t, non_blocking=True)
+            up.wait_stream(cur)
+            with torch.cuda.stream(up):
+                for k, t in hv["grads"].items():
+                    dv["grads"][k].copy_(t, non_blocking=True)
         g = dv["grads"]
         s = Settings(image_height=v["H"], image_width=v["W"], tanfovx=v["tanfovx"], tanfovy=v["tanfovy"],
                      bg=dev_bg, scale_modifier=1.0, viewmatrix=dv["viewmatrix"], projmatrix=dv["projmatrix"],
@@ -308,11 +316,15 @@ def run_gpu(args, impl):
         out = Raster(s)(means3D=dev_params["means3D"], means2D=dev_m2d, opacities=dev_params["opacities"],
                         shs=dev_params["shs"], shs_p=dev_params["shs_p"], scales=dev_params["scales"],
                         rotations=dev_params["rotations"])
+        down.wait_stream(cur)
+        with torch.cuda.stream(down), torch.no_grad():
+            himg[0:3].copy_(out[0], non_blocking=True)
+            himg[3:10].copy_(out[1], non_blocking=True)
+            himg[10:11].copy_(out[2], non_blocking=True)
+        cur.wait_stream(up)
         torch.autograd.backward([out[0], out[1], out[2], out[4], out[6]],
                                 [g["color"], g["phasor"], g["depth"], g["acc"], g["depth_distortion"]])
-        himg[0:3].copy_(out[0], non_blocking=True)
-        himg[3:10].copy_(out[1], non_blocking=True)
-        himg[10:11].copy_(out[2], non_blocking=True)
+        cur.wait_stream(down)
 
     def step_e2e_concurrent():
         with torch.no_grad():
