@@ -61,15 +61,18 @@ WORKLOADS = {
     # configs[3] per-view shape: 2M Gaussians, 1080p RGB + 640x480 ToF
     "c4": dict(P=2000000, color=(1920, 1080), tof=(640, 480), depth_range=15.0, kind="trained",
                desc="BASELINE configs[3] per-view shape: 2M Gaussians, 1080p colour + 640x480 ToF"),
+    # configs[4] upper end: 8M Gaussians (screen-space sigma 1 px), two 1080p frames per step
+    "c5": dict(P=8000000, color=(1920, 1080), tof=(1920, 1080), depth_range=15.0, kind="trained", sigma_px=1.0,
+               desc="BASELINE configs[4] upper end: 8M Gaussians, two 1920x1080 frames"),
 }
 
 
 # --------------------------------------------------------------------------------------------
-def make_view(P, wh, depth_range, kind, seed, device, cloud=None, bg_hw=None):
+def make_view(P, wh, depth_range, kind, seed, device, cloud=None, bg_hw=None, sigma_px=1.5):
     W, H = wh
     cam = scenes.make_camera(W, H, depth_range=depth_range, seed=seed)
     if cloud is None:
-        cloud = scenes.make_cloud(P, cam, kind=kind, seed=seed)
+        cloud = scenes.make_cloud(P, cam, kind=kind, seed=seed, sigma_px=sigma_px)
     bh, bw = bg_hw if bg_hw else (H, W)
     bg = scenes.make_background(bh, bw, seed=seed)
     grads = scenes.make_pixel_grads(H, W, seed=seed)
@@ -82,7 +85,8 @@ def make_view(P, wh, depth_range, kind, seed, device, cloud=None, bg_hw=None):
 
 
 def build_scene(wl, seed, device):
-    color, cloud = make_view(wl["P"], wl["color"], wl["depth_range"], wl["kind"], seed, device)
+    color, cloud = make_view(wl["P"], wl["color"], wl["depth_range"], wl["kind"], seed, device,
+                             sigma_px=wl.get("sigma_px", 1.5))
     # the bg map is sized from the colour camera and reused for the ToF view (train.py:121-128)
     tof, _ = make_view(wl["P"], wl["tof"], wl["depth_range"], wl["kind"], seed, device, cloud=cloud,
                        bg_hw=(wl["color"][1], wl["color"][0]))
