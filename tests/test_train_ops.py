@@ -91,6 +91,42 @@ def test_assemble_restatement_semantics():
     assert torch.equal(iso["scales"][:, 0], iso["scales"][:, 2])
 
 
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_loss_cases():
+    z = np.load(os.path.join(GOLDEN, "train_loss.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    out = []
+    for n in names:
+        lam, ld, w, nch = (float(x) for x in z[n + "/meta"])
+        out.append(dict(name=n, img=torch.from_numpy(z[n + "/img"]), gt=torch.from_numpy(z[n + "/gt"]),
+                        loss=float(z[n + "/loss"]), grad=torch.from_numpy(z[n + "/grad"]), ssim=float(z[n + "/ssim"]),
+                        kw=dict(kind=str(z[n + "/kind"]), lam=lam, lambda_dssim=ld, w=w, nch=int(nch))))
+    return out
+
+
+def test_loss_restatement_matches_the_reference_functions():
+    """tests/golden/train_loss.npz was produced by the reference's OWN utils/loss_utils.py
+    (tests/golden/make_train_golden.py imports it from /root/reference): values and gradients."""
+    for c in golden_loss_cases():
+        leaf = c["img"].clone().requires_grad_(True)
+        val = orc.loss_term(leaf, c["gt"], **c["kw"])
+        val.backward()
+        assert abs(float(val) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"])), c["name"]
+        assert rel(leaf.grad, c["grad"]) < 1e-5, c["name"]
+        assert abs(float(orc.ssim(c["img"], c["gt"])) - c["ssim"]) < 1e-6, c["name"]
+
+
+def test_rotation_restatement_matches_the_reference_function():
+    """build_rotation / inverse_sigmoid of the reference's utils/general_utils.py (fixture)."""
+    z = np.load(os.path.join(GOLDEN, "train_misc.npz"))
+    R = orc._rotation_matrix(torch.from_numpy(z["q"]))
+    assert float((R - torch.from_numpy(z["R"])).abs().max()) < 1e-6
+    x = torch.from_numpy(z["x"])
+    assert float((torch.log(x / (1 - x)) - torch.from_numpy(z["inv_sigmoid"])).abs().max()) < 1e-6
+
+
 def test_train_header_symbols_are_exported():
     src = open(os.path.join(ROOT, "include", "gftorf_train.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
@@ -215,6 +251,16 @@ def test_fused_loss_value_and_gradient_vs_oracle(case):
     acc = torch.full((1,), 2.0, device="cuda")
     T.fused_loss(img.cuda(), gt.cuda(), loss_out=acc, **kw)
     assert abs(float(acc) - 2.0 - float(ref)) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_fused_loss_vs_reference_generated_golden():
+    """The CUDA loss against values and gradients computed by the reference's own loss_utils.py."""
+    from gftorf_b200 import train_ops as T
+    for c in golden_loss_cases():
+        loss, grad = T.fused_loss(c["img"].cuda(), c["gt"].cuda(), **c["kw"])
+        assert abs(float(loss) - c["loss"]) <= 2e-5 * max(abs(c["loss"]), 1e-3), c["name"]
+        assert rel(grad, c["grad"]) < 3e-5, c["name"]
 
 
 @pytest.mark.gpu
