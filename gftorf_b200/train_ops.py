@@ -316,13 +316,14 @@ def densify_and_prune(params: Dict[str, torch.Tensor], exp_avg: Optional[Dict[st
                       exp_avg_sq: Optional[Dict[str, torch.Tensor]], grad_accum: torch.Tensor,
                       denom: torch.Tensor, max_grad: float, min_opacity: float, extent: float,
                       percent_dense: float, size_prune: bool = True, isotropic: bool = False,
-                      generator: Optional[torch.Generator] = None):
+                      generator: Optional[torch.Generator] = None, samples: Optional[torch.Tensor] = None):
     """GaussianModel.densify_and_prune (scene/gaussian_model.py:631-646) on the parameter groups of
     the optimizer (names of :247-266) and their Adam moments.  Returns (params, exp_avg,
     exp_avg_sq, info) for the new Gaussian set, in the reference's order; the caller restarts the
     densification statistics from zero, as the reference does (:564-566).  The normal samples of
     the split (:579-581) are drawn here with torch.normal on `generator`, exactly the call the
-    reference makes, so seeded runs reproduce it."""
+    reference makes, so seeded runs reproduce it; `samples` ([2 * split, 3], already scaled by the
+    standard deviations) replaces the draw (used to replay recorded noise)."""
     lib = _lib()
     xyz = _cuda_f32(params["xyz"], "xyz")
     dev = xyz.device
@@ -352,8 +353,13 @@ def densify_and_prune(params: Dict[str, torch.Tensor], exp_avg: Optional[Dict[st
     sel = split_src[:n_split].long()
     sc = src["scaling"][sel]
     stds = torch.exp(sc.repeat(1, 3) if isotropic else sc).repeat(2, 1)
-    noise = torch.normal(mean=torch.zeros_like(stds), std=stds, generator=generator) if n_split else \
-        torch.zeros((0, 3), dtype=torch.float32, device=dev)
+    if samples is not None:
+        noise = _cuda_f32(samples, "samples")
+        if tuple(noise.shape) != (2 * n_split, 3):
+            raise RuntimeError(f"samples must be [{2 * n_split}, 3] for this plan, got {tuple(noise.shape)}")
+    else:
+        noise = torch.normal(mean=torch.zeros_like(stds), std=stds, generator=generator) if n_split else \
+            torch.zeros((0, 3), dtype=torch.float32, device=dev)
     out_p, out_m, out_v = {}, {}, {}
     for g in params:
         t = src[g]

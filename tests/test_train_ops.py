@@ -371,6 +371,49 @@ def test_densify_restatement_counts_and_order():
     assert (p2["xyz"].shape[0] - n_keep - n_clone) % 2 == 0
 
 
+def golden_densify_cases():
+    z = np.load(os.path.join(GOLDEN, "train_densify.npz"))
+    out = []
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        t = lambda key: torch.from_numpy(z[n + "/" + key])
+        max_grad, min_op, extent, pd, size, iso = (float(x) for x in z[n + "/meta"])
+        c = dict(name=n, acc=t("acc"), den=t("den"), samples=t("samples"),
+                 kw=dict(max_grad=max_grad, min_opacity=min_op, extent=extent, percent_dense=pd,
+                         size_prune=bool(size), isotropic=bool(iso)))
+        for pre in ("in", "in_m", "in_v", "out", "out_m", "out_v"):
+            c[pre] = {g: t(pre + "/" + g) for g in orc.GROUPS}
+        out.append(c)
+    return out
+
+
+def test_densify_restatement_matches_the_reference_method():
+    """tests/golden/train_densify.npz: inputs, recorded split noise and results of the reference's
+    OWN GaussianModel.densify_and_prune run on CPU (tests/golden/make_densify_golden.py).  The
+    restatement must reproduce the new Gaussian set — order, rows and Adam moments — exactly."""
+    for c in golden_densify_cases():
+        p, m, v = orc.densify_and_prune(c["in"], c["in_m"], c["in_v"], c["acc"].clone(), c["den"],
+                                        normal_fn=lambda s, c=c: c["samples"], **c["kw"])
+        for g in orc.GROUPS:
+            assert p[g].shape == c["out"][g].shape, (c["name"], g)
+            assert float((p[g] - c["out"][g]).abs().max() if p[g].numel() else 0.0) <= 1e-6, (c["name"], g)
+            assert torch.equal(m[g], c["out_m"][g]) and torch.equal(v[g], c["out_v"][g]), (c["name"], g)
+
+
+@pytest.mark.gpu
+def test_densify_vs_reference_generated_golden():
+    """The CUDA densification against the reference's own densify_and_prune (recorded noise replayed)."""
+    from gftorf_b200 import train_ops as T
+    cu = lambda d: {k: t.cuda() for k, t in d.items()}
+    for c in golden_densify_cases():
+        p, m, v, info = T.densify_and_prune(cu(c["in"]), cu(c["in_m"]), cu(c["in_v"]), c["acc"].cuda(), c["den"].cuda(),
+                                            samples=c["samples"].cuda(), **c["kw"])
+        assert info["P_new"] == c["out"]["xyz"].shape[0], c["name"]
+        for g in orc.GROUPS:
+            assert p[g].shape == c["out"][g].shape, (c["name"], g)
+            assert float((p[g].cpu() - c["out"][g]).abs().max() if p[g].numel() else 0.0) <= 2e-6, (c["name"], g)
+            assert torch.equal(m[g].cpu(), c["out_m"][g]) and torch.equal(v[g].cpu(), c["out_v"][g]), (c["name"], g)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [dict(P=1, iso=False, size=True), dict(P=999, iso=False, size=True),
                                   dict(P=5000, iso=False, size=False), dict(P=3001, iso=True, size=True),
