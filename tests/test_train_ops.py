@@ -371,6 +371,65 @@ def test_densify_restatement_counts_and_order():
     assert (p2["xyz"].shape[0] - n_keep - n_clone) % 2 == 0
 
 
+def golden_assemble_cases():
+    z = np.load(os.path.join(GOLDEN, "train_assemble.npz"))
+    out = []
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        t = lambda key: torch.from_numpy(z[n + "/" + key])
+        iso, st, dy = (bool(x) for x in z[n + "/meta"])
+        c = dict(name=n, mask=t("mask"), iso=iso, regions=tuple(r for r, on in (("static", st), ("dynamic", dy)) if on))
+        for pre, names in (("raw", tuple(RAW_KEYS)), ("graw", tuple(RAW_KEYS)), ("delta", DELTA_KEYS), ("gdelta", DELTA_KEYS),
+                           ("out", OUT_KEYS), ("gout", OUT_KEYS)):
+            c[pre] = {k: t(pre + "/" + k) for k in names}
+        out.append(c)
+    return out
+
+
+RAW_KEYS = ("xyz", "opacity_raw", "scaling_raw", "rotation_raw", "f_dc_color", "f_rest_color", "f_dc_phase",
+            "f_rest_phase", "f_dc_amp", "f_rest_amp")
+DELTA_KEYS = ("d_xyz", "d_rot", "d_sh", "d_sh_p")
+OUT_KEYS = ("means3D", "opacities", "scales", "rotations", "shs", "shs_p")
+
+
+def test_assemble_restatement_matches_the_reference_render():
+    """tests/golden/train_assemble.npz: the reference's OWN render() (gaussian_renderer/__init__.py)
+    and model getters run on CPU with the rasterizer replaced by a recorder
+    (tests/golden/make_assemble_golden.py): the six tensors it hands to the rasterizer, and the
+    raw-parameter / deformation gradients autograd derives for a known gradient of those tensors."""
+    for c in golden_assemble_cases():
+        leaves = {k: v.clone().requires_grad_(True) for k, v in c["raw"].items()}
+        dl = {k: v.clone().requires_grad_(True) for k, v in c["delta"].items()}
+        o = orc.assemble(leaves, c["mask"], dl, c["iso"], c["regions"])
+        for k in OUT_KEYS:
+            assert float((o[k] - c["out"][k]).abs().max()) <= 1e-6, (c["name"], k)
+        torch.autograd.backward([o[k] for k in OUT_KEYS], [c["gout"][k] for k in OUT_KEYS])
+        for k in RAW_KEYS:
+            assert rel(leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k]), c["graw"][k]) < 1e-5 \
+                or float(c["graw"][k].abs().max()) == 0.0, (c["name"], k)
+        for k in DELTA_KEYS:
+            got = dl[k].grad if dl[k].grad is not None else torch.zeros_like(dl[k])
+            assert float((got - c["gdelta"][k]).abs().max() if got.numel() else 0.0) <= 1e-6, (c["name"], k)
+
+
+@pytest.mark.gpu
+def test_assemble_vs_reference_generated_golden():
+    """The CUDA assembly (forward and backward) against the reference's own render() + getters."""
+    from gftorf_b200 import train_ops as T
+    for c in golden_assemble_cases():
+        raw = {k: v.cuda().requires_grad_(True) for k, v in c["raw"].items()}
+        dl = {k: v.cuda().requires_grad_(True) for k, v in c["delta"].items()}
+        dyn = T.dyn_index_from_mask(c["mask"].cuda())
+        o = T.assemble_gaussians(raw, dyn, dl, c["iso"], c["regions"])
+        for k in OUT_KEYS:
+            assert float((o[k].cpu() - c["out"][k]).abs().max()) <= 2e-6, (c["name"], k)
+        torch.autograd.backward([o[k] for k in OUT_KEYS], [c["gout"][k].cuda() for k in OUT_KEYS])
+        for k in RAW_KEYS:
+            assert float((raw[k].grad.cpu() - c["graw"][k]).abs().max()) <= 2e-5 * max(1.0, float(c["graw"][k].abs().max())), (c["name"], k)
+        for k in DELTA_KEYS:
+            if dl[k].numel():
+                assert float((dl[k].grad.cpu() - c["gdelta"][k]).abs().max()) <= 2e-5 * max(1.0, float(c["gdelta"][k].abs().max())), (c["name"], k)
+
+
 def golden_densify_cases():
     z = np.load(os.path.join(GOLDEN, "train_densify.npz"))
     out = []
