@@ -52,6 +52,10 @@ WORKLOADS = {
     # configs[1] of BASELINE.json: F-TöRF synthetic-shaped scene, 300k Gaussians, 640x480 RGB + ToF
     "c2": dict(P=300000, color=(640, 480), tof=(640, 480), depth_range=15.0, kind="trained",
                desc="BASELINE configs[1]: 300k Gaussians, 640x480 RGB view + 640x480 ToF view, SH degree 3"),
+    # the same shape at INITIALISATION (dataset_readers.py:891-903): uniform cloud, isotropic scale from
+    # distCUDA2, opacity 0.1 — huge splats (median radius ~50 px), R/V ~ 25
+    "c2_init": dict(P=300000, color=(640, 480), tof=(640, 480), depth_range=15.0, kind="init",
+                    desc="configs[1] shape at initialisation: 300k init-like Gaussians, 640x480 x2"),
     # configs[0]: the CPU-runnable case
     "c1": dict(P=20000, color=(320, 240), tof=(320, 240), depth_range=15.0, kind="trained",
                desc="BASELINE configs[0]: 20k Gaussians, 320x240"),
