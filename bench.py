@@ -100,6 +100,13 @@ def build_scene(wl, seed, device):
     return params, [color, tof]
 
 
+def view_spec(v):
+    """A bench view as the batched API's ViewSpec."""
+    from gftorf_b200 import views as V
+    return V.ViewSpec(v["H"], v["W"], v["tanfovx"], v["tanfovy"], v["bg"], v["viewmatrix"], v["projmatrix"],
+                      v["campos"], v["near_n"], v["far_n"], v["depth_range"])
+
+
 def fwd_args(params, v, empty):
     return (v["bg"], params["means3D"], empty, empty, params["opacities"], params["scales"],
             params["rotations"], 1.0, empty, v["viewmatrix"], v["projmatrix"], v["tanfovx"],

@@ -68,7 +68,7 @@ int gft_nvls_allreduce_sum(float* multicast_ptr, long long n_floats, int rank, i
   static const int env_unroll = [] { const char* e = std::getenv("GFT_NVLS_UNROLL"); return e ? std::atoi(e) : 0; }();
   const int unroll = env_unroll == 8 ? 8 : (env_unroll == 2 ? 2 : 4);
   long long blocks = (end - begin + 256 * unroll - 1) / (256 * unroll);
-  const long long cap = env_blocks > 0 ? env_blocks : 148 * 8;
+  const long long cap = env_blocks > 0 ? env_blocks : (long long)gft::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   float4* mc = reinterpret_cast<float4*>(multicast_ptr);
   if (unroll == 8) gft::nvls_allreduce_kernel<8><<<(int)blocks, 256, 0, stream>>>(mc, begin, end);

@@ -1,119 +1,259 @@
-// binning.cu — key duplication, tile|depth sort and tile-range identification.
+// binning.cu — tile-segmented binning: per-tile instance counts -> tile ranges -> scatter of the
+// (depth, Gaussian) entries into their tile's segment -> one in-shared-memory sort per segment.
 //
 // Replaces duplicateWithKeys (cuda_rasterizer/rasterizer_impl.cu:72-113), the
-// cub::DeviceRadixSort::SortPairs call (rasterizer_impl.cu:334-339) and identifyTileRanges
-// (rasterizer_impl.cu:118-140).  All of it is integer work and is bit-exact with the reference:
-//   key   = (tile_id << 32) | float_bits(view_z)       value = Gaussian index
-// emitted per Gaussian in (y outer, x inner) order at offset point_offsets[idx-1], then sorted
-// stably on bits [0, 32 + ceil_log2-ish(T)) so equal keys keep ascending Gaussian index.
+// cub::DeviceRadixSort::SortPairs call over all R instances (rasterizer_impl.cu:334-339: 6 global
+// passes of 24 B/instance + histogram) and identifyTileRanges + its memset
+// (rasterizer_impl.cu:118-140,341).  All of it is integer work and bit-exact with the reference:
+// the reference sorts keys (tile << 32) | float_bits(view_z) with a STABLE radix sort over
+// instances emitted in ascending Gaussian order, so inside a tile the list is ordered by
+// (float_bits(view_z), Gaussian index).  Here
+//   1. the preprocess kernel counts the instances of every tile (tile_counts, one RED each),
+//   2. tile_scan_kernel turns the counts into `ranges` (an exclusive scan over tiles IS the
+//      reference's ranges array) and the instance count R,
+//   3. scatter_entries_kernel writes every instance's 64-bit entry (depth bits << 32 | index)
+//      into its tile's segment at a slot taken from an atomic cursor (arbitrary order),
+//   4. tile_sort_kernel sorts each segment on the whole 64-bit entry — a total order, so the
+//      arbitrary slot order of step 3 does not matter and the result is the reference's list.
+// HBM traffic: 8 B written + 8 B read + 12 B written per instance (28 B) instead of
+// 12 + 8 + 6 x 24 + 8 = 172 B for emit + histogram + radix passes + ranges.
 #include "common.cuh"
 #include "kernels.h"
-#include "radix_sort.cuh"
 
 #include <cstdlib>
-#include <cstring>
 
 namespace gft {
 
-// One block = 256 consecutive Gaussians; the block's instances are spread evenly over its
-// threads (a Gaussian covering thousands of tiles is emitted by all 256 threads, with coalesced
-// stores), instead of one thread looping over all tiles of its Gaussian.
-__global__ void __launch_bounds__(GFT_BLOCK)
-duplicate_keys_kernel(int P, const uint16_t* __restrict__ rect, const float* __restrict__ depths,
-                      const uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys,
-                      uint32_t* __restrict__ values, int grid_x, uint32_t capacity, KeyFormat kf) {
-  __shared__ uint32_t s_end[GFT_BLOCK];
-  const int first = blockIdx.x * GFT_BLOCK;
-  const int idx = first + threadIdx.x;
-  const uint32_t base = first == 0 ? 0u : __ldg(point_offsets + first - 1);
-  const int last = min(P, first + GFT_BLOCK) - 1;
-  s_end[threadIdx.x] = __ldg(point_offsets + min(idx, last)) - base;
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int SCAN_THREADS = 1024;
+
+// One block scans all tile counters (T_total <= 16 views x 8160 tiles at 1080p).
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(const uint32_t* __restrict__ counts, int T, uint32_t capacity,
+                 uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
+                 uint32_t* __restrict__ hdr) {
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  __shared__ uint32_t s_carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  const uint32_t total = s_end[GFT_BLOCK - 1];
-  for (uint32_t i = threadIdx.x; i < total; i += GFT_BLOCK) {
-    // smallest t with s_end[t] > i
-    int lo = 0, hi = GFT_BLOCK - 1;
+  // chunks of SCAN_THREADS*4 counters: every thread owns 4 consecutive ones (one 16-byte load)
+  for (int base = 0; base < T; base += SCAN_THREADS * 4) {
+    const int i0 = base + (int)tid * 4;
+    uint32_t c[4];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int mid = (lo + hi) >> 1;
-      if (s_end[mid] > i) hi = mid; else lo = mid + 1;
+    for (int k = 0; k < 4; ++k) c[k] = (i0 + k < T) ? counts[i0 + k] : 0u;
+    const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += n;
     }
-    const int t = lo;
-    const uint32_t k = i - (t > 0 ? s_end[t - 1] : 0u);
-    const int g = first + t;
-    const uint2 r = __ldg(reinterpret_cast<const uint2*>(rect) + g);
-    const uint32_t x0 = r.x & 0xffffu, y0 = r.x >> 16, x1 = r.y & 0xffffu;
-    const uint32_t w = x1 - x0;
-    const uint32_t ty = y0 + k / w, tx = x0 + k % w;
-    uint64_t key = (uint64_t)(ty * (uint32_t)grid_x + tx);
-    key <<= kf.depth_bits;
-    // depth relative to the near plane, see KeyFormat (clamped: a NaN depth passes the frustum
-    // test like in the reference and must not spill into the tile bits)
-    const uint32_t zb = __float_as_uint(__ldg(depths + g));
-    const uint32_t zmax = kf.depth_bits >= 32 ? 0xffffffffu : ((1u << kf.depth_bits) - 1u);
-    key |= (uint64_t)(zb >= kf.depth_base ? min(zb - kf.depth_base, zmax) : 0u);
-    if (base + i < capacity) {   // only ever false when a caller's size hint was too small
-      keys[base + i] = key;
-      values[base + i] = (uint32_t)g;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+      const uint32_t t = s_warp[w];
+      if ((uint32_t)w < warp) wbase += t;
+      total += t;
     }
+    uint32_t x = s_carry + wbase + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < T) {
+        const uint32_t y = x + c[k];
+        // empty tiles read (0,0): the reference's memset + identifyTileRanges never touch them
+        ranges[i0 + k] = c[k] ? make_uint2(min(x, capacity), min(y, capacity)) : make_uint2(0u, 0u);
+        cursors[i0 + k] = 0u;
+        x = y;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) hdr[1] = s_carry;   // num_rendered
+}
+
+// grid: (ceil(P/256), nviews).  Same tile enumeration as the counting in the preprocess kernel.
+__global__ void __launch_bounds__(GFT_BLOCK)
+scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint2* __restrict__ ranges,
+                       uint32_t* __restrict__ cursors, u64* __restrict__ entries) {
+  const int v = blockIdx.y;
+  const ViewCam& vc = p.views[v];
+  const int idx = (int)(blockIdx.x * GFT_BLOCK + threadIdx.x);
+  const uint32_t lane = threadIdx.x & 31;
+  const size_t P = (size_t)p.P;
+  uint32_t rx0 = 0, ry0 = 0, rx1 = 0, tiles = 0;
+  if (idx < p.P && vc.radii[idx] > 0) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p.g.rect) + v * P + idx);
+    rx0 = r.x & 0xffffu; ry0 = r.x >> 16; rx1 = r.y & 0xffffu;
+    const uint32_t ry1 = r.y >> 16;
+    tiles = (rx1 - rx0) * (ry1 - ry0);
+  }
+  const uint32_t gx = (uint32_t)vc.grid_x, tb = (uint32_t)vc.tile_base;
+  const float* __restrict__ depths = p.g.depths + v * P;
+  for_each_tile(rx0, ry0, rx1, tiles, (uint32_t)idx, lane, [&](uint32_t tx, uint32_t ty, uint32_t g) {
+    const uint32_t t = tb + ty * gx + tx;
+    const uint2 rg = __ldg(ranges + t);
+    const uint32_t slot = rg.x + atomicAdd(cursors + t, 1u);
+    if (slot < rg.y)   // only ever false when a caller's size hint was too small
+      entries[slot] = ((u64)__float_as_uint(__ldg(depths + g)) << 32) | (u64)g;
+  });
+}
+
+// ---- per-segment sort ----------------------------------------------------------------------
+// Bitonic sorting network in its "flip" form: level k first compares i with its mirror inside the
+// k-block (i ^ (k-1)), then runs half-cleaners of distance k/4, k/8, ..., 1.  Every comparison
+// puts the smaller key at the lower index, so a segment of arbitrary length n needs no padding:
+// elements past n behave as +infinity and a comparison whose upper index is >= n is a no-op.
+// Segments of up to `cap` entries (a power of two, the dynamic shared memory size / 8) are sorted
+// entirely in shared memory; longer ones (initialisation-like clouds: thousands of large splats
+// per tile) sort cap-sized chunks in shared memory and run the stages of distance >= cap on the
+// segment in global memory (L2-resident), one block per segment either way.
+constexpr int SORT_THREADS = 256;
+
+__device__ __forceinline__ void ce_shared(u64* s, uint32_t a, uint32_t b) {
+  const u64 x = s[a], y = s[b];
+  if (x > y) { s[a] = y; s[b] = x; }
+}
+
+// all stages of distance < min(cap, k) of level k on the shared chunk s[0, len)
+__device__ __forceinline__ void level_in_shared(u64* s, uint32_t len, uint32_t k, bool with_flip,
+                                                uint32_t pairs) {
+  if (with_flip) {
+    const uint32_t half = k >> 1;
+    for (uint32_t t = threadIdx.x; t < pairs; t += SORT_THREADS) {
+      const uint32_t lo = t & (half - 1), blk = t / half;
+      const uint32_t a = blk * k + lo, b = blk * k + (k - 1u - lo);
+      if (b < len) ce_shared(s, a, b);
+    }
+    __syncthreads();
+  }
+  for (uint32_t j = with_flip ? (k >> 2) : (k >> 1); j > 0; j >>= 1) {
+    for (uint32_t t = threadIdx.x; t < pairs; t += SORT_THREADS) {
+      const uint32_t a = ((t / j) * (j << 1)) + (t & (j - 1)), b = a + j;
+      if (b < len) ce_shared(s, a, b);
+    }
+    __syncthreads();
   }
 }
 
-__global__ void identify_ranges_kernel(int R_cap, const uint32_t* __restrict__ d_R,
-                                       const uint64_t* __restrict__ keys,
-                                       uint2* __restrict__ ranges, int depth_bits) {
-  const int R = d_R ? (int)min(__ldg(d_R), (uint32_t)R_cap) : R_cap;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= R) return;
-  const uint32_t cur = (uint32_t)(keys[idx] >> depth_bits);
-  if (idx == 0) {
-    ranges[cur].x = 0;
-  } else {
-    const uint32_t prev = (uint32_t)(keys[idx - 1] >> depth_bits);
-    if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
-    }
-  }
-  if (idx == R - 1) ranges[cur].y = R;
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
+  return n <= 1u ? 1u : (1u << (32 - __clz(n - 1u)));
 }
 
-void launch_duplicate_keys(int P, const int* /*radii*/, const uint16_t* rect, const float* depths,
-                           const uint32_t* point_offsets, uint64_t* keys, uint32_t* values,
-                           int grid_x, uint32_t capacity, KeyFormat kf, cudaStream_t stream) {
-  const int blocks = (P + GFT_BLOCK - 1) / GFT_BLOCK;
-  duplicate_keys_kernel<<<blocks, GFT_BLOCK, 0, stream>>>(P, rect, depths, point_offsets, keys,
-                                                          values, grid_x, capacity, kf);
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
+                 uint32_t* __restrict__ point_list, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+  u64* s = reinterpret_cast<u64*>(sort_smem_raw);
+  const uint2 rg = ranges[blockIdx.x];
+  const uint32_t n = rg.y - rg.x;
+  if (n == 0u) return;
+  u64* g = entries + rg.x;
+  uint32_t* pl = point_list + rg.x;
+  const uint32_t tid = threadIdx.x;
+
+  if (n <= cap) {
+    for (uint32_t i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
+    __syncthreads();
+    const uint32_t m = next_pow2(n);
+    for (uint32_t k = 2; k <= m; k <<= 1) level_in_shared(s, n, k, true, m >> 1);
+    for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+      const u64 e = s[i];
+      g[i] = e;
+      pl[i] = (uint32_t)e;
+    }
+    return;
+  }
+
+  // ---- long segment: chunks in shared memory, wide stages in global memory --------------------
+  const uint32_t m = next_pow2(n);
+  for (uint32_t c0 = 0; c0 < n; c0 += cap) {
+    const uint32_t len = min(cap, n - c0);
+    for (uint32_t i = tid; i < len; i += SORT_THREADS) s[i] = __ldcg(g + c0 + i);
+    __syncthreads();
+    for (uint32_t k = 2; k <= cap; k <<= 1) level_in_shared(s, len, k, true, cap >> 1);
+    for (uint32_t i = tid; i < len; i += SORT_THREADS) g[c0 + i] = s[i];
+    __syncthreads();
+  }
+  for (uint32_t k = cap << 1; k <= m; k <<= 1) {
+    const uint32_t half = k >> 1;
+    for (uint32_t t = tid; t < (m >> 1); t += SORT_THREADS) {       // flip, distance up to k-1
+      const uint32_t lo = t & (half - 1), blk = t / half;
+      const uint32_t a = blk * k + lo, b = blk * k + (k - 1u - lo);
+      if (b < n) {
+        const u64 x = __ldcg(g + a), y = __ldcg(g + b);
+        if (x > y) { g[a] = y; g[b] = x; }
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = k >> 2; j >= cap; j >>= 1) {                    // half-cleaners across chunks
+      for (uint32_t t = tid; t < (m >> 1); t += SORT_THREADS) {
+        const uint32_t a = ((t / j) * (j << 1)) + (t & (j - 1)), b = a + j;
+        if (b < n) {
+          const u64 x = __ldcg(g + a), y = __ldcg(g + b);
+          if (x > y) { g[a] = y; g[b] = x; }
+        }
+      }
+      __syncthreads();
+    }
+    for (uint32_t c0 = 0; c0 < n; c0 += cap) {                        // distances < cap: per chunk
+      const uint32_t len = min(cap, n - c0);
+      for (uint32_t i = tid; i < len; i += SORT_THREADS) s[i] = __ldcg(g + c0 + i);
+      __syncthreads();
+      level_in_shared(s, len, cap, false, cap >> 1);
+      for (uint32_t i = tid; i < len; i += SORT_THREADS) g[c0 + i] = s[i];
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = tid; i < n; i += SORT_THREADS) pl[i] = (uint32_t)__ldcg(g + i);
+}
+
+}  // namespace
+
+void launch_tile_scan(const uint32_t* tile_counts, int T_total, uint32_t capacity, uint2* ranges,
+                      uint32_t* cursors, uint32_t* hdr, cudaStream_t stream) {
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_counts, T_total, capacity, ranges, cursors, hdr);
   note_launches(1);
 }
 
-void launch_identify_ranges(int R, const uint32_t* d_R, const uint64_t* keys, uint2* ranges,
-                            KeyFormat kf, cudaStream_t stream) {
-  if (R <= 0) return;
-  identify_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, d_R, keys, ranges, kf.depth_bits);
+void launch_scatter_entries(const PreprocessParams& pp, const uint2* ranges, uint32_t* cursors,
+                            unsigned long long* entries, cudaStream_t stream) {
+  if (pp.P <= 0) return;
+  const dim3 grid((pp.P + GFT_BLOCK - 1) / GFT_BLOCK, pp.nviews);
+  scatter_entries_kernel<<<grid, GFT_BLOCK, 0, stream>>>(pp, ranges, cursors, entries);
   note_launches(1);
 }
 
-KeyFormat key_format(float near_n, float far_n) {
-  KeyFormat kf;
-  kf.depth_bits = 32;
-  kf.depth_base = 0u;
-  static const bool full = [] {   // GFT_FULL_KEYS=1: the reference's 32-bit depth field (A/B runs)
-    const char* e = std::getenv("GFT_FULL_KEYS");
-    return e && e[0] == '1';
-  }();
-  if (!full && near_n > 0.f && far_n >= near_n && far_n < 3.0e38f) {
-    uint32_t lo, hi;
-    std::memcpy(&lo, &near_n, 4);
-    std::memcpy(&hi, &far_n, 4);
-    const uint32_t span = hi - lo;
-    int b = 0;
-    while (b < 32 && (span >> b) != 0u) ++b;
-    kf.depth_bits = b == 0 ? 1 : b;
-    kf.depth_base = lo;
-  }
-  return kf;
+void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entries,
+                      uint32_t* point_list, int mean_len_hint, cudaStream_t stream) {
+  if (T_total <= 0) return;
+  // shared-memory capacity per block: 4096 entries (32 KB, 7 blocks/SM) for ordinary scenes, 8192
+  // (64 KB, 3 blocks/SM) when the tile lists are long on average (initialisation-like clouds)
+  const int forced = option(OPT_SORT_CAP);
+  uint32_t cap = mean_len_hint > 1500 ? 8192u : 4096u;
+  if (forced == 256 || forced == 1024 || forced == 2048 || forced == 4096 || forced == 8192 || forced == 16384)
+    cap = (uint32_t)forced;
+  const int smem = (int)cap * 8;
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(tile_sort_kernel, 16384 * 8, &smem_ok);
+  tile_sort_kernel<<<T_total, SORT_THREADS, smem, stream>>>(ranges, entries, point_list, cap);
+  note_launches(1);
 }
+
+// ---- radix sort pass-throughs (knn, A/B hooks) -------------------------------------------------
+}  // namespace gft
+
+#include "radix_sort.cuh"
+
+namespace gft {
 
 bool sort_result_in_out(int end_bit) { return sort_lands_in_out(end_bit); }
 

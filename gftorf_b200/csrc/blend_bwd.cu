@@ -20,13 +20,17 @@
 //        sum G*dL/dalpha | sum w*g_c[3] | sum w*g_d | sum w*(2z*k2-k1) | sum wp*(gA,gB,gC,gS)
 //     where (gA,gB,gC,gS) are the four linear combinations of the 7 phasor pixel gradients that the
 //     phasor backward consumes (backward.cu:551-577).  15 values instead of 18.
-//   * Warp reduction of the 15 partials.  Default: a transpose through a warp-private shared
-//     buffer — every lane stores its 15 values down one column (15 STS, conflict-free), lane j sums
-//     half a row with four 128-bit loads + 15 adds, one shuffle joins the halves: ~38 instructions.
-//     Alternative kept for A/B (GFT_BWD_SMEM_REDUCE=0): a halving butterfly 16 -> 8 -> 4 -> 2 -> 1
-//     values per lane (16 shuffles + 32 selects + 16 adds, ~64 instructions; 18*5 = 90 shuffles
-//     for a plain per-value reduction).  Either way value i ends in lanes 2i, 2i+1 and the even
-//     lanes issue ONE reduction instruction onto the Gaussian's 64-byte record.
+//   * Warp reduction of the 15 partials: a transpose through a warp-private shared buffer — every
+//     lane stores its 15 values down one column (15 STS, conflict-free), lane j sums half a row
+//     with four 128-bit loads + packed adds, one shuffle joins the halves: ~38 instructions (the
+//     halving shuffle butterfly it replaced cost ~64 and was 30 % of the kernel's instructions).
+//     Value i ends in lanes 2i, 2i+1 and the even lanes issue ONE reduction instruction onto the
+//     Gaussian's 64-byte record.
+//   * No divergent region in the replay (PRED): a pair that does not contribute is replayed with
+//     alpha = G = 0, for which every partial is exactly 0 and the recurrences leave the pixel's
+//     state untouched (T/1, 0*x + 1*X), so the `if (contributes)` of the reference
+//     (backward.cu:744-754) needs no branch, no re-convergence barrier and no zero fill of the 15
+//     partials.
 //   * a 16x16 tile is walked by 8 warps of 8x4 pixels, 32 Gaussians at a time; a warp skips
 //     Gaussians whose conservative alpha>=1/255 box misses its patch (exact, see blend_fwd.cu);
 //     batches behind the tile's furthest last-contributor are never loaded; the next batch is
@@ -66,40 +70,41 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 }  // namespace
 
-// WARPS warps = WARPS 8x4 patches of one tile per block (see blend_fwd.cu), BATCH = 32*WARPS.
-// WARP_MODE: no block-wide barrier — every warp gathers the tile list for itself, 32 Gaussians at a
-// time (one per lane) into a warp-private double buffer, only as far as its own furthest
-// contributor, and walks it at its own pace.  (In the block-synchronous mode 19 % of the warp
-// samples sit at the per-batch barrier, waiting for the busiest warp of the tile; ncu r1_d.)
-template <int WARPS, int MINB, bool SMEM_REDUCE, bool WARP_MODE>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-blend_bwd_kernel(BlendBwdParams p) {
-  constexpr int BATCH = WARP_MODE ? 32 : WARPS * 32;
-  constexpr uint32_t SUBS = 8 / WARPS;
+// 8 warps = the eight 8x4 patches of one 16x16 tile (see blend_fwd.cu), BATCH = 256 Gaussians
+// staged per step (one per thread) into a double buffer.  One launch covers the tiles of all
+// views of the batch (global tile index = blockIdx.x).
+template <int MINB, bool PRED>
+__global__ void __launch_bounds__(GFT_BLOCK, MINB)
+blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
+  constexpr int WARPS = GFT_BLOCK / 32;
+  constexpr int BATCH = GFT_BLOCK;
   using BwdBuf = BwdBufT<BATCH>;
   extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
-  // the staging area is 2 x 256 records either way: one double buffer for the block, or a
-  // 2 x 32 double buffer per warp
-  BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw) + (WARP_MODE ? (threadIdx.x >> 5) * 2 : 0);
+  BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw);
   __shared__ uint32_t s_wmax[WARPS];
-  // SMEM_REDUCE: per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
-  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBufT<WARPS * 32>)) + (threadIdx.x >> 5) * RED_FLOATS;
+  // per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
+  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  const uint32_t warp = (blockIdx.x % SUBS) * WARPS + wib;   // patch index within the tile
-  const uint32_t tile = blockIdx.x / SUBS;
-  const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int vi = 0;
+  for (int v = 1; v < p.nviews; ++v) vi = ((int)blockIdx.x >= p.views[v].tile_base) ? v : vi;
+  const BlendViewBwd& vw = p.views[vi];
+  const uint32_t tile = blockIdx.x - (uint32_t)vw.tile_base;
+  const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
   const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
-  const bool inside = pix_x < (uint32_t)p.W && pix_y < (uint32_t)p.H;
-  const uint32_t pix_id = (uint32_t)p.W * pix_y + pix_x;
+  const int W = vw.W, H = vw.H;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
   const float pixfx = (float)pix_x, pixfy = (float)pix_y;
   const float patch_x0 = (float)px0, patch_x1 = (float)(px0 + 7u);
   const float patch_y0 = (float)py0, patch_y1 = (float)(py0 + 3u);
-  const size_t HW = (size_t)p.H * (size_t)p.W;
+  const size_t HW = (size_t)H * (size_t)W;
+  const float4* __restrict__ recs = vw.rec;
+  float* __restrict__ grad_rec = vw.grad_rec;
 
-  const uint2 range = p.ranges[tile];
+  const uint2 range = p.ranges[blockIdx.x];
   const int n = (int)(range.y - range.x);
 
   // ---- per-pixel forward state, incoming gradients and the constants derived from them ----
@@ -109,34 +114,34 @@ blend_bwd_kernel(BlendBwdParams p) {
   float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f, gp3 = 0.f, gp4 = 0.f, gp5 = 0.f, gp6 = 0.f;
   float gd = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, bgdot = 0.f;
   if (inside) {
-    const float4 st = __ldg(p.img_state + pix_id);
+    const float4 st = __ldg(p.img_state + vw.pix_base + pix_id);
     T_final = st.x;
     const float w_z_total = st.y, w_z2_total = st.z;
     last_contributor = __float_as_uint(st.w);
-    gc0 = __ldg(p.dL_dcolor + 0 * HW + pix_id);
-    gc1 = __ldg(p.dL_dcolor + 1 * HW + pix_id);
-    gc2 = __ldg(p.dL_dcolor + 2 * HW + pix_id);
-    gp0 = __ldg(p.dL_dphasor + 0 * HW + pix_id);
-    gp1 = __ldg(p.dL_dphasor + 1 * HW + pix_id);
-    gp2 = __ldg(p.dL_dphasor + 2 * HW + pix_id);
-    gp3 = __ldg(p.dL_dphasor + 3 * HW + pix_id);
-    gp4 = __ldg(p.dL_dphasor + 4 * HW + pix_id);
-    gp5 = __ldg(p.dL_dphasor + 5 * HW + pix_id);
-    gp6 = __ldg(p.dL_dphasor + 6 * HW + pix_id);
-    gd = __ldg(p.dL_ddepth + pix_id);
-    const float ga = __ldg(p.dL_dacc + pix_id);
-    const float gdd = __ldg(p.dL_ddd + pix_id);
+    gc0 = __ldg(vw.dL_dcolor + 0 * HW + pix_id);
+    gc1 = __ldg(vw.dL_dcolor + 1 * HW + pix_id);
+    gc2 = __ldg(vw.dL_dcolor + 2 * HW + pix_id);
+    gp0 = __ldg(vw.dL_dphasor + 0 * HW + pix_id);
+    gp1 = __ldg(vw.dL_dphasor + 1 * HW + pix_id);
+    gp2 = __ldg(vw.dL_dphasor + 2 * HW + pix_id);
+    gp3 = __ldg(vw.dL_dphasor + 3 * HW + pix_id);
+    gp4 = __ldg(vw.dL_dphasor + 4 * HW + pix_id);
+    gp5 = __ldg(vw.dL_dphasor + 5 * HW + pix_id);
+    gp6 = __ldg(vw.dL_dphasor + 6 * HW + pix_id);
+    gd = __ldg(vw.dL_ddepth + pix_id);
+    const float ga = __ldg(vw.dL_dacc + pix_id);
+    const float gdd = __ldg(vw.dL_ddd + pix_id);
     // dL_dw + g_a = z^2*k2 - z*k1 + k0  (backward.cu:828 with the (1 - T_final) of quirk A.7-5)
     k2 = gdd * (1.f - T_final);
     k1 = 2.0f * gdd * w_z_total;
     k0 = gdd * w_z2_total + ga;
     float bgv[7];
-    if (p.bg_mode == 0) {
+    if (vw.bg_mode == 0) {
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch * HW + pix_id);
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(vw.bg + ch * HW + pix_id);
     } else {
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(vw.bg + ch);
     }
     // backward.cu:850-858: both background terms enter dL/dalpha with the factor -T_final/(1-alpha)
     bgdot = bgv[0] * gc0 + bgv[1] * gc1 + bgv[2] * gc2 +
@@ -152,17 +157,12 @@ blend_bwd_kernel(BlendBwdParams p) {
   uint32_t wmax = last_contributor;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  int n_eff;
-  if (WARP_MODE) {
-    n_eff = min(n, (int)wmax);          // positions >= wmax contribute nothing for this warp
-  } else {
-    if (lane == 0) s_wmax[wib] = wmax;
-    __syncthreads();
-    uint32_t bmax = 0;
+  if (lane == 0) s_wmax[warp] = wmax;
+  __syncthreads();
+  uint32_t bmax = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) bmax = max(bmax, s_wmax[w]);
-    n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
-  }
+  for (int w = 0; w < WARPS; ++w) bmax = max(bmax, s_wmax[w]);
+  const int n_eff = min(n, (int)bmax);  // positions >= bmax are skipped by every pixel of the tile
 
   float T = T_final;
   float X = 0.f;     // contracted alpha*T-family recurrence
@@ -173,17 +173,16 @@ blend_bwd_kernel(BlendBwdParams p) {
   auto stage = [&](int b, int which) {
     const int base = b * BATCH;
     const int m = min(BATCH, n_eff - base);
-    const int slot = WARP_MODE ? (int)lane : (int)tid;
-    if (slot < m) {
-      const int g = (int)__ldg(p.point_list + range.x + base + slot);
-      const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
+    if ((int)tid < m) {
+      const int g = (int)__ldg(p.point_list + range.x + base + tid);
+      const float4* r = recs + (size_t)g * (GFT_REC_FLOATS / 4);
       BwdBuf& d = buf[which];
-      d.id[slot] = g;
-      cp_async16(&d.r0[slot], r + 0);
-      cp_async16(&d.r1[slot], r + 1);
-      cp_async16(&d.r2[slot], r + 2);
-      cp_async16(&d.r3[slot], r + 3);
-      cp_async16(&d.r4[slot], r + 4);
+      d.id[tid] = g;
+      cp_async16(&d.r0[tid], r + 0);
+      cp_async16(&d.r1[tid], r + 1);
+      cp_async16(&d.r2[tid], r + 2);
+      cp_async16(&d.r3[tid], r + 3);
+      cp_async16(&d.r4[tid], r + 4);
     }
     cp_async_commit();
   };
@@ -205,9 +204,16 @@ blend_bwd_kernel(BlendBwdParams p) {
   auto replay = [&](const BwdBuf& s, int k, bool contrib, float G, float alpha, float dx, float dy) {
     if (!__any_sync(0xffffffffu, contrib)) return;
     float v[16];
+    if (PRED) {
+      // a pair that does not contribute is replayed with alpha = G = 0: every partial below is
+      // then exactly 0 and T, X, Bp keep their values (T * 1, 0 * x + 1 * X)
+      alpha = contrib ? alpha : 0.f;
+      G = contrib ? G : 0.f;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = 0.f;
-    if (contrib) {
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    if (PRED || contrib) {
       const float4 g1 = s.r1[k];
       const float4 g2 = s.r2[k];
       const float4 g3 = s.r3[k];
@@ -253,77 +259,33 @@ blend_bwd_kernel(BlendBwdParams p) {
       v[11] = vAB.x; v[12] = vAB.y; v[13] = vCS.x; v[14] = vCS.y;
     }
 
-    if (SMEM_REDUCE) {
-      // Transpose through shared memory: lane l stores its 15 partials down column l (stride 36:
-      // conflict-free), then lane j sums one half (16 lanes) of row j>>1 with four 128-bit loads
-      // (the 8 lanes of a load phase hit 8 different bank groups) and one shuffle joins the halves.
+    // Transpose through shared memory: lane l stores its 15 partials down column l (stride 36:
+    // conflict-free), then lane j sums one half (16 lanes) of row j>>1 with four 128-bit loads
+    // (the 8 lanes of a load phase hit 8 different bank groups) and one shuffle joins the halves.
 #pragma unroll
-      for (int i = 0; i < 15; ++i) red[i * RED_STRIDE + (int)lane] = v[i];
-      __syncwarp();
-      const float4* rp = reinterpret_cast<const float4*>(red + (lane >> 1) * RED_STRIDE + (lane & 1u) * 16u);
-      const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
-      // 16 -> 1 with packed adds: 7 FADD2 + 1 FADD instead of 15 FADD
-      const float2 s0 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
-      const float2 s1 = add2(make_float2(q1.x, q1.y), make_float2(q1.z, q1.w));
-      const float2 s2 = add2(make_float2(q2.x, q2.y), make_float2(q2.z, q2.w));
-      const float2 s3 = add2(make_float2(q3.x, q3.y), make_float2(q3.z, q3.w));
-      const float2 st = add2(add2(s0, s1), add2(s2, s3));
-      float sum = st.x + st.y;
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      __syncwarp();
-      if ((lane & 1u) == 0u && lane != 30u)
-        atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), sum);
-      return;
-    }
-    // ---- halving butterfly: value i ends complete in lanes 2i and 2i+1 ---------------------
-    float a8[8];
-    {
-      const bool up = (lane & 16u) != 0u;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-    }
-    float a4[4];
-    {
-      const bool up = (lane & 8u) != 0u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = up ? a8[i] : a8[i + 4];
-        const float keep = up ? a8[i + 4] : a8[i];
-        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-    }
-    float a2[2];
-    {
-      const bool up = (lane & 4u) != 0u;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float send = up ? a4[i] : a4[i + 2];
-        const float keep = up ? a4[i + 2] : a4[i];
-        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-    }
-    float a1;
-    {
-      const bool up = (lane & 2u) != 0u;
-      const float send = up ? a2[0] : a2[1];
-      const float keep = up ? a2[1] : a2[0];
-      a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-    if ((lane & 1u) == 0u && lane != 30u)   // lane 30 holds the unused slot 15
-      atomicAdd(p.grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), a1);
+    for (int i = 0; i < 15; ++i) red[i * RED_STRIDE + (int)lane] = v[i];
+    __syncwarp();
+    const float4* rp = reinterpret_cast<const float4*>(red + (lane >> 1) * RED_STRIDE + (lane & 1u) * 16u);
+    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+    // 16 -> 1 with packed adds: 7 FADD2 + 1 FADD instead of 15 FADD
+    const float2 s0 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
+    const float2 s1 = add2(make_float2(q1.x, q1.y), make_float2(q1.z, q1.w));
+    const float2 s2 = add2(make_float2(q2.x, q2.y), make_float2(q2.z, q2.w));
+    const float2 s3 = add2(make_float2(q3.x, q3.y), make_float2(q3.z, q3.w));
+    const float2 st = add2(add2(s0, s1), add2(s2, s3));
+    float sum = st.x + st.y;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    __syncwarp();
+    if ((lane & 1u) == 0u && lane != 30u)
+      atomicAdd(grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), sum);
   };
 
   int cur = 0;
   if (nb > 0) stage(nb - 1, cur);
   for (int b = nb - 1; b >= 0; --b) {
     cp_async_wait_all();
-    // batch b is in buf[cur]; everyone (block, or warp in WARP_MODE) left buf[cur^1]
-    if (WARP_MODE) __syncwarp(); else __syncthreads();
+    // batch b is in buf[cur]; everyone left buf[cur^1]
+    __syncthreads();
     if (b > 0) stage(b - 1, cur ^ 1);      // gather the next (nearer) batch while this one is used
     const BwdBuf& s = buf[cur];
     const int base = b * BATCH;
@@ -359,51 +321,26 @@ blend_bwd_kernel(BlendBwdParams p) {
 }
 
 namespace {
-template <int WARPS, int MINB, bool SMEM_REDUCE, bool WARP_MODE = false>
-void launch_bwd_variant(const BlendBwdParams& p, int tiles, cudaStream_t stream) {
-  const int smem = 2 * (int)sizeof(BwdBufT<WARPS * 32>) + (SMEM_REDUCE ? WARPS * RED_FLOATS * 4 : 0);
+template <int MINB, bool PRED>
+void launch_bwd_variant(const BlendBwdParams& p, cudaStream_t stream) {
+  const int smem = 2 * (int)sizeof(BwdBufT<GFT_BLOCK>) + (GFT_BLOCK / 32) * RED_FLOATS * 4;
   static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE, WARP_MODE>, smem, &smem_ok);
-  blend_bwd_kernel<WARPS, MINB, SMEM_REDUCE, WARP_MODE><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
+  ensure_dynamic_smem(blend_bwd_kernel<MINB, PRED>, smem, &smem_ok);
+  blend_bwd_kernel<MINB, PRED><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
 }
 }  // namespace
 
-int blend_block_warps(int tiles) {
-  static const int forced = [] {
-    const char* e = std::getenv("GFT_BLEND_WARPS");
-    const int v = e ? std::atoi(e) : 0;
-    return (v == 8 || v == 4) ? v : 0;
-  }();
-  if (forced) return forced;
-  (void)tiles;
-  return 8;   // measured: 8 / 4 / 2 warps per block within 1 % of each other at 640x480 and 1080p
-}
+int blend_block_warps(int) { return 8; }
 
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
-  const int tiles = p.grid_x * p.grid_y;
-  if (tiles <= 0) return;
+  if (p.T_total <= 0) return;
   // Measured and rejected on B200 (c2 and c4 workloads): 64-register variants for one more resident
-  // block per SM (+4 %), and sending replays with few contributing pixels straight to the record
-  // with per-lane reductions instead of the butterfly (+4 %).
-  // default: reduce through shared memory (7 % faster than the shuffle butterfly on B200, c2 and
-  // c4 workloads); GFT_BWD_SMEM_REDUCE=0 selects the butterfly for A/B runs
-  static const bool smem_reduce = [] {
-    const char* e = std::getenv("GFT_BWD_SMEM_REDUCE");
-    return !(e && e[0] == '0');
-  }();
-  static const bool warp_mode = [] {
-    const char* e = std::getenv("GFT_BWD_WARP");
-    return e && e[0] == '1';
-  }();
-  if (warp_mode) {
-    launch_bwd_variant<8, 3, true, true>(p, tiles, stream);
-  } else if (smem_reduce) {
-    if (blend_block_warps(tiles) == 8) launch_bwd_variant<8, 3, true>(p, tiles, stream);
-    else launch_bwd_variant<4, 6, true>(p, tiles, stream);
-  } else {
-    if (blend_block_warps(tiles) == 8) launch_bwd_variant<8, 3, false>(p, tiles, stream);
-    else launch_bwd_variant<4, 6, false>(p, tiles, stream);
-  }
+  // block per SM (+4 %), replays with few contributing pixels sent straight to the record with
+  // per-lane reductions (+4 %), a warp-autonomous variant like the forward's (+6 %), half-tile
+  // blocks (+-1 %), the shuffle butterfly instead of the shared-memory transpose (+7 %).
+  // Option bwd_pred = 0 (GFT_BWD_PRED=0) selects the branchy replay for A/B runs.
+  if (option(OPT_BWD_PRED) != 0) launch_bwd_variant<3, true>(p, stream);
+  else launch_bwd_variant<3, false>(p, stream);
   note_launches(1);
 }
 

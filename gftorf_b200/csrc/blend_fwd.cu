@@ -28,254 +28,17 @@ namespace gft {
 
 namespace {
 
-// A block is WARPS warps = WARPS 8x4 patches of one 16x16 tile (8 = the whole tile, 4 = a 16x8
-// half, 2 = a 16x4 quarter) and stages BATCH = 32*WARPS Gaussians at a time, one per thread.
-// Sub-tile blocks exist for load balance: at 640x480 there are only 1200 tiles for 148 SMs
-// (8.1 per SM -> the last round runs 10 % full); 2400 half tiles quantise twice as finely, and the
-// block-wide early-termination / furthest-contributor bounds get tighter.
-template <int BATCH>
-struct FwdBufT {
-  float4 r0[BATCH];  // x y ex ey
-  float4 r1[BATCH];  // conA conB conC opacity
-  float4 r2[BATCH];  // r g b dist
-  float4 r3[BATCH];  // ph0..ph3
-  float4 r4[BATCH];  // ph4 ph5 ph6 ndc
-  int id[BATCH];
-  int cnt[BATCH];
-};
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-}  // namespace
-
-template <int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-blend_fwd_kernel(BlendFwdParams p) {
-  constexpr int BATCH = WARPS * 32;
-  constexpr uint32_t SUBS = 8 / WARPS;     // blocks per tile
-  using FwdBuf = FwdBufT<BATCH>;
-  extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
-  FwdBuf* buf = reinterpret_cast<FwdBuf*>(fwd_smem_raw);
-  const uint32_t tid = threadIdx.x, lane = tid & 31;
-  const uint32_t warp = (blockIdx.x % SUBS) * WARPS + (tid >> 5);   // patch index within the tile
-  const uint32_t tile = blockIdx.x / SUBS;
-  const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
-  // warp patch: 8 wide x 4 high
-  const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
-  const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
-  const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
-  const bool inside = pix_x < (uint32_t)p.W && pix_y < (uint32_t)p.H;
-  const uint32_t pix_id = (uint32_t)p.W * pix_y + pix_x;
-  const float pixfx = (float)pix_x, pixfy = (float)pix_y;
-  const float patch_x0 = (float)px0, patch_x1 = (float)(px0 + 7u);
-  const float patch_y0 = (float)py0, patch_y1 = (float)(py0 + 3u);
-
-  const uint2 range = p.ranges[tile];
-  const int n = (int)(range.y - range.x);
-
-  bool done = !inside;
-  bool warp_done = __all_sync(0xffffffffu, done);
-  float T = 1.0f;
-  uint32_t last_contributor = 0;
-  float C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, P4 = 0.f, P5 = 0.f, P6 = 0.f;
-  float D = 0.f, A = 0.f, DD = 0.f, DD_D = 0.f, DD_D2 = 0.f;
-  float WD0 = 0.f, WD1 = 0.f, WD2 = 0.f;
-  bool first_hit = true;
-
-  // gather one batch of the tile list into a shared-memory buffer with cp.async
-  auto stage = [&](int base, int which) {
-    const int m = min(BATCH, n - base);
-    if ((int)tid < m) {
-      const int g = (int)__ldg(p.point_list + range.x + base + tid);
-      const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
-      FwdBuf& d = buf[which];
-      d.id[tid] = g;
-      d.cnt[tid] = 0;
-      cp_async16(&d.r0[tid], r + 0);
-      cp_async16(&d.r1[tid], r + 1);
-      cp_async16(&d.r2[tid], r + 2);
-      cp_async16(&d.r3[tid], r + 3);
-      cp_async16(&d.r4[tid], r + 4);
-    }
-    cp_async_commit();
-  };
-
-  // One (pixel, Gaussian) pair, after its alpha has been evaluated.  Sequential per pixel: the
-  // transmittance test and the accumulators depend on every earlier Gaussian.
-  auto apply = [&](const FwdBuf& s, int base, int k, int b, float alpha, bool pass, int& mycnt) {
-    bool contrib = !done && pass;
-    float test_T = 0.f;
-    if (contrib) {
-      test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-      if (test_T < 0.0001f) {   // forward.cu:538-543: done BEFORE applying this Gaussian
-        done = true;
-        contrib = false;
-      }
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
-    if ((int)lane == b) mycnt = __popc(bal);
-    if (contrib) {
-      const float4 g2 = s.r2[k];
-      const float4 g3 = s.r3[k];
-      const float4 g4 = s.r4[k];
-      const float w = __fmul_rn(T, alpha);
-      const float wp = __fmul_rn(T, w);
-      C0 = __fmaf_rn(w, g2.x, C0);
-      C1 = __fmaf_rn(w, g2.y, C1);
-      C2 = __fmaf_rn(w, g2.z, C2);
-      P0 = __fmaf_rn(wp, g3.x, P0);
-      P1 = __fmaf_rn(wp, g3.y, P1);
-      P2 = __fmaf_rn(wp, g3.z, P2);
-      P3 = __fmaf_rn(wp, g3.w, P3);
-      P4 = __fmaf_rn(wp, g4.x, P4);
-      P5 = __fmaf_rn(wp, g4.y, P5);
-      P6 = __fmaf_rn(wp, g4.z, P6);
-      if (first_hit) {  // first applied Gaussian (forward.cu:561-567)
-        WD0 = alpha;
-        WD1 = g2.w;
-        WD2 = g3.z;
-        first_hit = false;
-      }
-      // depth distortion, forward.cu:572-578 in the reference's evaluation order
-      const float z = g4.w;
-      const float z2 = __fmul_rn(z, z);
-      const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
-      float t2 = __fmaf_rn(A, z2, -t1);
-      const float wz = __fmul_rn(w, z);
-      t2 = __fadd_rn(DD_D2, t2);
-      DD_D = __fadd_rn(DD_D, wz);
-      DD_D2 = __fmaf_rn(z, wz, DD_D2);
-      D = __fmaf_rn(w, g2.w, D);
-      DD = __fmaf_rn(w, t2, DD);
-      A = __fadd_rn(A, w);
-      T = test_T;
-      last_contributor = (uint32_t)(base + k + 1);
-    }
-  };
-  // alpha of one pair (forward.cu:524-537), independent of the pixel's running state, so two
-  // Gaussians are evaluated side by side to overlap their expf latency chains
-  auto eval_alpha = [&](const FwdBuf& s, int k, float& alpha) -> bool {
-    const float4 g0 = s.r0[k];
-    const float4 g1 = s.r1[k];
-    const float dx = __fsub_rn(g0.x, pixfx);
-    const float dy = __fsub_rn(g0.y, pixfy);
-    const float power = pair_power(dx, dy, g1.x, g1.y, g1.z);
-    const bool neg = !(power > 0.0f);
-    alpha = fminf(0.99f, __fmul_rn(g1.w, expf(neg ? power : 0.0f)));
-    return neg && !(alpha < 1.0f / 255.0f);
-  };
-
-  int cur = 0, prev_m = 0;
-  if (n > 0) stage(0, cur);
-  for (int base = 0; base < n; base += BATCH) {
-    cp_async_wait_all();
-    // One barrier per batch: it publishes batch `base` in buf[cur], retires every reader of
-    // buf[cur^1], and carries the block-wide "everyone is done" vote (forward.cu:500-502).
-    const bool all_done = __syncthreads_and(done);
-    if ((int)tid < prev_m) {   // pixel counts of the batch all warps have just left
-      const int cnt = buf[cur ^ 1].cnt[tid];
-      if (cnt) atomicAdd(p.pixels + buf[cur ^ 1].id[tid], (float)cnt);
-    }
-    prev_m = 0;
-    if (all_done) break;
-    if (base + BATCH < n) stage(base + BATCH, cur ^ 1);   // overlaps with the work below
-    FwdBuf& s = buf[cur];
-    const int m = min(BATCH, n - base);
-
-    if (!warp_done) {
-      for (int c = 0; c < m; c += 32) {
-        const int jj = c + (int)lane;
-        bool hit = false;
-        if (jj < m) {
-          const float4 g0 = s.r0[jj];
-          // written so that NaN extents mean "not culled"
-          hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
-                  g0.y - g0.w > patch_y1);
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        int mycnt = 0;
-        while (mask) {
-          const int b1 = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const bool two = mask != 0u;
-          const int b2 = two ? (__ffs(mask) - 1) : b1;
-          if (two) mask &= mask - 1;
-          float alpha1, alpha2;
-          const bool pass1 = eval_alpha(s, c + b1, alpha1);
-          const bool pass2 = eval_alpha(s, c + b2, alpha2);
-          apply(s, base, c + b1, b1, alpha1, pass1, mycnt);
-          if (two) apply(s, base, c + b2, b2, alpha2, pass2, mycnt);
-        }
-        if (mycnt) atomicAdd(&s.cnt[jj], mycnt);
-        if (__all_sync(0xffffffffu, done)) {
-          warp_done = true;
-          break;
-        }
-      }
-    }
-    prev_m = m;
-    cur ^= 1;
-  }
-  __syncthreads();
-  if ((int)tid < prev_m) {   // the last batch that was processed
-    const int cnt = buf[cur ^ 1].cnt[tid];
-    if (cnt) atomicAdd(p.pixels + buf[cur ^ 1].id[tid], (float)cnt);
-  }
-  cp_async_wait_all();   // a prefetch may still be in flight when the tile finished early
-
-  if (inside) {
-    const size_t HW = (size_t)p.H * (size_t)p.W;
-    p.img_state[pix_id] = make_float4(T, DD_D, DD_D2, __uint_as_float(last_contributor));
-    float bgv[7];
-    if (p.bg_mode == 0) {
-#pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch * HW + pix_id);
-    } else {
-#pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
-    }
-    // colour reads bg planes 0..2, phasor planes 0..6, both weighted by T (forward.cu:644,649)
-    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C0);
-    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C1);
-    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2);
-    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P0);
-    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P1);
-    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P2);
-    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P3);
-    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P4);
-    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P5);
-    p.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
-    p.out_depth[pix_id] = D;
-    p.out_acc[pix_id] = A;
-    p.out_depth_distortion[pix_id] = DD;
-    p.out_distribution[0 * HW + pix_id] = WD0;
-    p.out_distribution[1 * HW + pix_id] = WD1;
-    p.out_distribution[2 * HW + pix_id] = WD2;
-    // outputs the reference allocates but never writes (forward.cu:655-667): defined as 0
-    if (p.out_normal) {
-      p.out_normal[0 * HW + pix_id] = 0.f;
-      p.out_normal[1 * HW + pix_id] = 0.f;
-      p.out_normal[2 * HW + pix_id] = 0.f;
-    }
-    if (p.out_entropy) p.out_entropy[pix_id] = 0.f;
-    if (p.out_amp_distortion) p.out_amp_distortion[pix_id] = 0.f;
-  }
-}
-
-// ---- warp-autonomous variant ------------------------------------------------------------------
-// Same arithmetic, no block-wide barrier: every warp gathers the tile's Gaussian list for itself,
-// 32 Gaussians (one per lane) at a time, with cp.async into a warp-private ring of WSTAGES slots,
-// and walks it at its own pace.  In the block-synchronous kernel above 25 % of the warp samples sit
-// at the per-batch barrier (warps whose patch sees few Gaussians wait for the busiest warp of the
-// tile, ncu r1_d); here a warp only ever waits for its own copies.  The price is that the 8 warps
-// of a tile each read the records (L1/L2 hits after the first) and flush their own `pixels`
-// counts (one atomic per (warp, Gaussian) with a contribution instead of one per (tile, Gaussian)).
+// Warp-autonomous blend: a 16x16 tile is covered by 8 warps of 8x4 pixels that never synchronise
+// with each other.  Every warp gathers the tile's Gaussian list for itself, 32 Gaussians (one per
+// lane) at a time, with cp.async into a warp-private ring of WSTAGES slots of 80-byte records, and
+// walks it at its own pace.  (A block-synchronous version — one shared double buffer, one
+// __syncthreads per batch of 256 — had 25 % of its warp samples parked at the barrier, waiting for
+// the busiest warp of the tile; it was 4 % slower at 640x480 and 2 % at 1080p and is gone.)  The
+// price is that the 8 warps each read the records (L1/L2 hits after the first) and flush their
+// own `pixels` counts (one atomic per (warp, Gaussian) with a contribution).
+//
+// One launch covers the tiles of ALL views of the batch: block b works on global tile b, which
+// belongs to the view v with tile_base_v <= b < tile_base_v + T_v.
 constexpr int WSTAGES = 2;
 struct WarpStage {
   float4 r0[32], r1[32], r2[32], r3[32], r4[32];
@@ -286,27 +49,37 @@ __device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+}  // namespace
+
 template <int MINB>
 __global__ void __launch_bounds__(GFT_BLOCK, MINB)
-blend_fwd_warp_kernel(BlendFwdParams p) {
+blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
   extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpStage* ring = reinterpret_cast<WarpStage*>(fwd_smem_raw) + warp * WSTAGES;
-  const uint32_t tile = blockIdx.x;
-  const uint32_t tile_x = tile % (uint32_t)p.grid_x, tile_y = tile / (uint32_t)p.grid_x;
+  // the view this tile belongs to (uniform per block)
+  int vi = 0;
+  for (int v = 1; v < p.nviews; ++v) vi = ((int)blockIdx.x >= p.views[v].tile_base) ? v : vi;
+  const BlendViewFwd& vw = p.views[vi];
+  const uint32_t tile = blockIdx.x - (uint32_t)vw.tile_base;
+  const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
   const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
-  const bool inside = pix_x < (uint32_t)p.W && pix_y < (uint32_t)p.H;
-  const uint32_t pix_id = (uint32_t)p.W * pix_y + pix_x;
+  const int W = vw.W, H = vw.H;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
   const float pixfx = (float)pix_x, pixfy = (float)pix_y;
   const float patch_x0 = (float)px0, patch_x1 = (float)(px0 + 7u);
   const float patch_y0 = (float)py0, patch_y1 = (float)(py0 + 3u);
+  const float4* __restrict__ recs = vw.rec;
+  float* __restrict__ pixels = vw.pixels;
 
-  const uint2 range = p.ranges[tile];
+  const uint2 range = p.ranges[blockIdx.x];
   const int n = (int)(range.y - range.x);
   const int nb = (n + 31) >> 5;
 
@@ -326,7 +99,7 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
       const int j = b * 32 + (int)lane;
       if (j < n) {
         const int g = (int)__ldg(p.point_list + range.x + j);
-        const float4* r = p.rec + (size_t)g * (GFT_REC_FLOATS / 4);
+        const float4* r = recs + (size_t)g * (GFT_REC_FLOATS / 4);
         WarpStage& d = ring[b % WSTAGES];
         d.id[lane] = g;
         cp_async16_ca(&d.r0[lane], r + 0);
@@ -352,11 +125,14 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
       bool hit = false;
       if ((int)lane < m) {
         const float4 g0 = s.r0[lane];
+        // written so that NaN extents mean "not culled"
         hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
                 g0.y - g0.w > patch_y1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       int mycnt = 0;
+      // alpha of one pair (forward.cu:524-537), independent of the pixel's running state, so two
+      // Gaussians are evaluated side by side to overlap their expf latency chains
       auto eval_alpha = [&](int k, float& alpha) -> bool {
         const float4 g0 = s.r0[k];
         const float4 g1 = s.r1[k];
@@ -367,12 +143,14 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
         alpha = fminf(0.99f, __fmul_rn(g1.w, expf(neg ? power : 0.0f)));
         return neg && !(alpha < 1.0f / 255.0f);
       };
+      // One (pixel, Gaussian) pair, after its alpha has been evaluated.  Sequential per pixel: the
+      // transmittance test and the accumulators depend on every earlier Gaussian.
       auto apply = [&](int k, float alpha, bool pass) {
         bool contrib = !done && pass;
         float test_T = 0.f;
         if (contrib) {
           test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-          if (test_T < 0.0001f) { done = true; contrib = false; }
+          if (test_T < 0.0001f) { done = true; contrib = false; }   // forward.cu:538-543
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
         if ((int)lane == k) mycnt = __popc(bal);
@@ -389,7 +167,8 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
           P23 = fma2(wp2, make_float2(g3.z, g3.w), P23);
           P45 = fma2(wp2, make_float2(g4.x, g4.y), P45);
           P6 = __fmaf_rn(wp, g4.z, P6);
-          if (first_hit) { WD0 = alpha; WD1 = g2.w; WD2 = g3.z; first_hit = false; }
+          if (first_hit) { WD0 = alpha; WD1 = g2.w; WD2 = g3.z; first_hit = false; }   // forward.cu:561-567
+          // depth distortion, forward.cu:572-578 in the reference's evaluation order
           const float z = g4.w;
           const float z2 = __fmul_rn(z, z);
           const float t1 = __fmul_rn(DD_D, __fadd_rn(z, z));
@@ -416,7 +195,9 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
         apply(b1, alpha1, pass1);
         if (two) apply(b2, alpha2, pass2);
       }
-      if (mycnt) atomicAdd(p.pixels + s.id[lane], (float)mycnt);
+      // `pixels` (forward.cu:629: one float atomic per contributing pair) counted by ballot and
+      // flushed once per (warp, Gaussian); integer-valued floats < 2^24, exact in any order
+      if (mycnt) atomicAdd(pixels + s.id[lane], (float)mycnt);
       const bool all_done = __all_sync(0xffffffffu, done);   // also orders this batch's reads before the next issue
       if (all_done) break;
     }
@@ -424,75 +205,52 @@ blend_fwd_warp_kernel(BlendFwdParams p) {
   }
 
   if (inside) {
-    const size_t HW = (size_t)p.H * (size_t)p.W;
-    p.img_state[pix_id] = make_float4(T, DD_D, DD_D2, __uint_as_float(last_contributor));
+    const size_t HW = (size_t)H * (size_t)W;
+    p.img_state[vw.pix_base + pix_id] = make_float4(T, DD_D, DD_D2, __uint_as_float(last_contributor));
     float bgv[7];
-    if (p.bg_mode == 0) {
+    if (vw.bg_mode == 0) {
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch * HW + pix_id);
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(vw.bg + ch * HW + pix_id);
     } else {
 #pragma unroll
-      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(p.bg + ch);
+      for (int ch = 0; ch < 7; ++ch) bgv[ch] = __ldg(vw.bg + ch);
     }
-    p.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C01.x);
-    p.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C01.y);
-    p.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2D.x);
-    p.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P01.x);
-    p.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P01.y);
-    p.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P23.x);
-    p.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P23.y);
-    p.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P45.x);
-    p.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P45.y);
-    p.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
-    p.out_depth[pix_id] = C2D.y;
-    p.out_acc[pix_id] = A;
-    p.out_depth_distortion[pix_id] = DD;
-    p.out_distribution[0 * HW + pix_id] = WD0;
-    p.out_distribution[1 * HW + pix_id] = WD1;
-    p.out_distribution[2 * HW + pix_id] = WD2;
-    if (p.out_normal) {
-      p.out_normal[0 * HW + pix_id] = 0.f;
-      p.out_normal[1 * HW + pix_id] = 0.f;
-      p.out_normal[2 * HW + pix_id] = 0.f;
+    // colour reads bg planes 0..2, phasor planes 0..6, both weighted by T (forward.cu:644,649)
+    vw.out_color[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], C01.x);
+    vw.out_color[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], C01.y);
+    vw.out_color[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], C2D.x);
+    vw.out_phasor[0 * HW + pix_id] = __fmaf_rn(T, bgv[0], P01.x);
+    vw.out_phasor[1 * HW + pix_id] = __fmaf_rn(T, bgv[1], P01.y);
+    vw.out_phasor[2 * HW + pix_id] = __fmaf_rn(T, bgv[2], P23.x);
+    vw.out_phasor[3 * HW + pix_id] = __fmaf_rn(T, bgv[3], P23.y);
+    vw.out_phasor[4 * HW + pix_id] = __fmaf_rn(T, bgv[4], P45.x);
+    vw.out_phasor[5 * HW + pix_id] = __fmaf_rn(T, bgv[5], P45.y);
+    vw.out_phasor[6 * HW + pix_id] = __fmaf_rn(T, bgv[6], P6);
+    vw.out_depth[pix_id] = C2D.y;
+    vw.out_acc[pix_id] = A;
+    vw.out_depth_distortion[pix_id] = DD;
+    vw.out_distribution[0 * HW + pix_id] = WD0;
+    vw.out_distribution[1 * HW + pix_id] = WD1;
+    vw.out_distribution[2 * HW + pix_id] = WD2;
+    // outputs the reference allocates but never writes (forward.cu:655-667): defined as 0
+    if (vw.out_normal) {
+      vw.out_normal[0 * HW + pix_id] = 0.f;
+      vw.out_normal[1 * HW + pix_id] = 0.f;
+      vw.out_normal[2 * HW + pix_id] = 0.f;
     }
-    if (p.out_entropy) p.out_entropy[pix_id] = 0.f;
-    if (p.out_amp_distortion) p.out_amp_distortion[pix_id] = 0.f;
+    if (vw.out_entropy) vw.out_entropy[pix_id] = 0.f;
+    if (vw.out_amp_distortion) vw.out_amp_distortion[pix_id] = 0.f;
   }
 }
-
-namespace {
-template <int WARPS, int MINB>
-void launch_fwd_variant(const BlendFwdParams& p, int tiles, cudaStream_t stream) {
-  const int smem = 2 * (int)sizeof(FwdBufT<WARPS * 32>);
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_fwd_kernel<WARPS, MINB>, smem, &smem_ok);
-  blend_fwd_kernel<WARPS, MINB><<<tiles * (8 / WARPS), WARPS * 32, smem, stream>>>(p);
-}
-}  // namespace
 
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
-  const int tiles = p.grid_x * p.grid_y;
-  if (tiles <= 0) return;
-  // default: the warp-autonomous kernel (4 % faster at 640x480, 2 % at 1080p on B200);
-  // GFT_FWD_WARP=0 selects the block-synchronous one for A/B runs
-  static const bool warp_mode = [] {
-    const char* e = std::getenv("GFT_FWD_WARP");
-    return !(e && e[0] == '0');
-  }();
-  if (warp_mode) {
-    const int smem = (GFT_BLOCK / 32) * WSTAGES * (int)sizeof(WarpStage);
-    // 4 resident blocks per SM (55 registers): 3 (67 registers) is 4-7 % slower, 5 (48 registers,
-    // 8 B spilled) 10-15 % slower on B200
-    static unsigned long long smem_ok = 0;
-    ensure_dynamic_smem(blend_fwd_warp_kernel<4>, smem, &smem_ok);
-    blend_fwd_warp_kernel<4><<<tiles, GFT_BLOCK, smem, stream>>>(p);
-    note_launches(1);
-    return;
-  }
-  switch (blend_block_warps(tiles)) {
-    case 8: launch_fwd_variant<8, 4>(p, tiles, stream); break;
-    default: launch_fwd_variant<4, 8>(p, tiles, stream); break;
-  }
+  if (p.T_total <= 0) return;
+  const int smem = (GFT_BLOCK / 32) * WSTAGES * (int)sizeof(WarpStage);
+  // 4 resident blocks per SM (55 registers): 3 (67 registers) is 4-7 % slower, 5 (48 registers,
+  // 8 B spilled) 10-15 % slower on B200
+  static unsigned long long smem_ok = 0;
+  ensure_dynamic_smem(blend_fwd_warp_kernel<4>, smem, &smem_ok);
+  blend_fwd_warp_kernel<4><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
   note_launches(1);
 }
 

@@ -211,6 +211,34 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Visits every tile of a Gaussian's tile rectangle [rx0,rx1) x [ry0, ry0 + tiles/(rx1-rx0)):
+// rectangles of up to 32 tiles by their own lane, larger ones by the whole warp (the reference's
+// initial splats have a median radius of ~50 px and a few cover thousands of tiles; one thread
+// looping over all of them stalls its warp, rasterizer_impl.cu:90-110).  Must be called by all 32
+// lanes; lanes with nothing to emit pass tiles = 0.  `payload` travels with the rectangle.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t tiles,
+                                              uint32_t payload, uint32_t lane, F&& f) {
+  const uint32_t w = rx1 - rx0;
+  const uint32_t big = __ballot_sync(0xffffffffu, tiles > 32u);
+  if (tiles != 0u && tiles <= 32u) {
+    uint32_t tx = rx0, ty = ry0;
+    for (uint32_t k = 0; k < tiles; ++k) {
+      f(tx, ty, payload);
+      if (++tx == rx1) { tx = rx0; ++ty; }
+    }
+  }
+  uint32_t m = big;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t bx0 = __shfl_sync(0xffffffffu, rx0, src), by0 = __shfl_sync(0xffffffffu, ry0, src);
+    const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, tiles, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, payload, src);
+    for (uint32_t k = lane; k < bn; k += 32u) f(bx0 + k % bw, by0 + k / bw, bp);
+  }
+}
+
 // ---- warp-cooperative staging of per-Gaussian rows ------------------------------------------
 // The SH tensors are [P][ROW] row-major, so the rows of a warp's 32 consecutive Gaussians are one
 // contiguous chunk of global memory.  These helpers move the chunk between global memory (fully

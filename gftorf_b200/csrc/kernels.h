@@ -1,8 +1,17 @@
 // kernels.h — internal launch interfaces between api.cu and the kernel translation units.
+//
+// Every kernel of the rasterizer works on a BATCH of views of the same Gaussian set (the colour
+// and the ToF camera of an iteration, gaussian_renderer/__init__.py:107-128; the 8 cameras of a
+// multi-view batch; the frames of a render-only sweep): one launch covers all views, the tiles of
+// all views form one global tile index space (view v owns tiles [tile_base_v, tile_base_v + T_v)),
+// and the per-Gaussian parameters are read once per launch instead of once per view.  A single
+// view (the reference's call shape) is a batch of one.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+
+#define GFT_MAX_VIEWS 16
 
 namespace gft {
 
@@ -21,16 +30,49 @@ inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_ma
   __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
 }
 
+// Number of SMs of the current device (cached per device).
+int sm_count();
+
+// Tunables / A-B switches (gft_set_option in the C ABI; defaults from the environment, read once).
+enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_COUNT };
+int option(int id);
+
 // Records the thread-local error string behind gft_last_error() and returns `code` (api.cu).
 int set_error(int code, const char* msg);
 
-// Warps per blend block (8 = a whole 16x16 tile, 4 = a 16x8 half, 2 = a 16x4 quarter); see
-// blend_fwd.cu.  GFT_BLEND_WARPS overrides the choice (for A/B measurements).
+// Warps per blend block (8 = a whole 16x16 tile, 4 = a 16x8 half); see blend_fwd.cu.
+// GFT_BLEND_WARPS overrides the choice (for A/B measurements).
 int blend_block_warps(int tiles);
 
+// ---- per-view constants ------------------------------------------------------------------------
+struct ViewCam {
+  int W, H, grid_x, grid_y;
+  int tile_base;                 // first global tile of this view
+  int use_view_dependent_phase;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  float near_n, far_n, dist2phase, phase_offset, dc_offset;
+  int pad_;
+  const float* viewmatrix;       // 16 floats, column-major
+  const float* projmatrix;       // 16 floats, full view*proj
+  const float* campos;           // 3 floats
+  int* radii;                    // [P] (forward: written; backward: read)
+  float* pixels;                 // [P] forward only
+  float* dL_dmeans2D;            // [P,3] backward only
+};
+
+// Per-view slices of the geometry workspace are laid out view-major: array[v][P][...].
+struct GeomViews {
+  float* cov3D;            // [P][6]            shared by all views (rasterizer_impl.cu:471)
+  float* rec;              // [V][P][20]        blend records
+  float* depths;           // [V][P]            view-space z (the sort key's depth bits)
+  uint32_t* tiles_touched; // [V][P]
+  uint16_t* rect;          // [V][P][4]
+  uint32_t* clamped;       // [V][P]            packed r | g<<8 | b<<16 | amp<<24
+  float* pa;               // [V][P][2]
+};
+
 struct PreprocessParams {
-  int P, D, M, M_p;
-  int W, H, grid_x, grid_y, num_tiles;
+  int P, D, M, M_p, nviews;
   const float* means3D;
   const float* scales;
   float scale_modifier;
@@ -41,75 +83,49 @@ struct PreprocessParams {
   const float* cov3D_precomp;
   const float* colors_precomp;
   const float* phasors_precomp;
-  const float* viewmatrix;
-  const float* projmatrix;
-  const float* campos;
-  float tan_fovx, tan_fovy, focal_x, focal_y;
   int prefiltered;
-  float near_n, far_n, dist2phase;
-  int use_view_dependent_phase;
-  float phase_offset, dc_offset;
-  int subtile_cull;       // 0: write infinite extents (blend kernels then test every pair)
-  // outputs
-  int* radii;
-  float* pixels;
-  float* rec;             // [P][20]
-  float* depths;          // [P]
-  uint32_t* tiles_touched;
-  uint32_t* point_offsets;
-  uint16_t* rect;         // [P][4]
-  float* cov3D;           // [P][6]
-  uint32_t* clamped;      // [P] packed r|g<<8|b<<16|amp<<24
-  float* pa;              // [P][2]
-  uint2* ranges;          // [T]
-  // scan
-  uint32_t* scan_ticket;   // header word 0 (unused since block ids are static)
-  uint32_t* key_format_out; // header words 2,3: depth_bits, depth_base (for the debug accessor)
-  int key_depth_bits; uint32_t key_depth_base;
-  unsigned long long* scan_state;
-  uint32_t* num_rendered;
+  int subtile_cull;        // 0: write infinite extents (blend kernels then test every pair)
+  GeomViews g;
+  uint32_t* tile_counts;   // [T_total] zero-filled before the launch; += 1 per (Gaussian, tile) instance
+  ViewCam views[GFT_MAX_VIEWS];
 };
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present,
                          float near_n, float far_n, cudaStream_t stream);
 
-// ---- binning ---------------------------------------------------------------------------------
-// Sort-key format.  The reference's key is (tile << 32) | float_bits(view_z).  Visible Gaussians
-// have near <= view_z <= far (the frustum test), and positive floats order like their bit
-// patterns, so (float_bits(view_z) - float_bits(near)) needs only depth_bits =
-// bit_length(float_bits(far) - float_bits(near)) bits and sorts identically: the compact key is
-// (tile << depth_bits) | (float_bits(view_z) - depth_base), typically 37-39 significant bits
-// instead of 43-45 — one radix pass fewer.  depth_bits = 32, depth_base = 0 is the reference's format.
-struct KeyFormat {
-  int depth_bits;
-  uint32_t depth_base;
-};
-KeyFormat key_format(float near_n, float far_n);
+// ---- binning: tile-segmented (binning.cu) ------------------------------------------------------
+// tile_counts -> ranges (exclusive scan over the global tile index; empty tiles read (0,0) like
+// the reference's memset + identifyTileRanges, rasterizer_impl.cu:118-140,341), the instance
+// count R in hdr[1], cursors zeroed.  Ranges are clamped to `capacity` (only ever effective when
+// a caller's size hint was too small; the forward is then repeated with the exact size).
+void launch_tile_scan(const uint32_t* tile_counts, int T_total, uint32_t capacity, uint2* ranges,
+                      uint32_t* cursors, uint32_t* hdr, cudaStream_t stream);
+// Every (view, Gaussian, tile) instance writes its entry (float_bits(view_z) << 32 | Gaussian id)
+// into its tile's segment, at a slot handed out by an atomic cursor (any order).
+void launch_scatter_entries(const PreprocessParams& pp, const uint2* ranges, uint32_t* cursors,
+                            unsigned long long* entries, cudaStream_t stream);
+// Sorts every tile segment on the 64-bit entry (depth bits, then Gaussian id): exactly the order
+// of the reference's stable radix sort of (tile << 32 | depth) keys over instances emitted in
+// ascending Gaussian order (rasterizer_impl.cu:90-110,334-339).  Writes the sorted entries back
+// and the Gaussian ids to point_list.
+void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entries,
+                      uint32_t* point_list, int mean_len_hint, cudaStream_t stream);
 
-void launch_duplicate_keys(int P, const int* radii, const uint16_t* rect, const float* depths,
-                           const uint32_t* point_offsets, uint64_t* keys, uint32_t* values,
-                           int grid_x, uint32_t capacity, KeyFormat kf, cudaStream_t stream);
-// Stable LSD radix sort of (key,value) pairs on bits [0, end_bit).  Returns temp bytes needed
-// when d_temp == nullptr.
+// ---- radix sort (knn + the A/B hooks) ----------------------------------------------------------
 size_t sort_pairs_temp_bytes(int R);
-// R: capacity (grid / temp sizing); d_R: optional device pointer to the actual count (<= R)
 int sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
                cudaStream_t stream, const uint32_t* d_R = nullptr);
 bool sort_result_in_out(int end_bit);
-void launch_identify_ranges(int R, const uint32_t* d_R, const uint64_t* keys, uint2* ranges,
-                            KeyFormat kf, cudaStream_t stream);
 
 // ---- blend -----------------------------------------------------------------------------------
-struct BlendFwdParams {
+struct BlendViewFwd {
   int W, H, grid_x, grid_y;
-  const uint2* ranges;
-  const uint32_t* point_list;
-  const float4* rec;
+  int tile_base, bg_mode;
+  size_t pix_base;          // first pixel of this view in img_state
+  const float4* rec;        // this view's blend records
   const float* bg;
-  int bg_mode;
-  float4* img_state;  // final_T, w_z_total, w_z2_total, n_contrib bits
   float* out_color;
   float* out_phasor;
   float* out_depth;
@@ -121,51 +137,53 @@ struct BlendFwdParams {
   float* out_distribution;
   float* pixels;
 };
-void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream);
-
-struct BlendBwdParams {
-  int W, H, grid_x, grid_y;
+struct BlendFwdParams {
+  int nviews, T_total;
   const uint2* ranges;
   const uint32_t* point_list;
+  float4* img_state;  // final_T, w_z_total, w_z2_total, n_contrib bits
+  BlendViewFwd views[GFT_MAX_VIEWS];
+};
+void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream);
+
+struct BlendViewBwd {
+  int W, H, grid_x, grid_y;
+  int tile_base, bg_mode;
+  size_t pix_base;
   const float4* rec;
   const float* bg;
-  int bg_mode;
-  const float4* img_state;
   const float* dL_dcolor;
   const float* dL_dphasor;
   const float* dL_ddepth;
   const float* dL_dacc;
   const float* dL_ddd;
-  float* grad_rec;  // [P][16], zero-filled before launch
+  float* grad_rec;    // [P][16] of this view, zero-filled before launch
+};
+struct BlendBwdParams {
+  int nviews, T_total;
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const float4* img_state;
+  BlendViewBwd views[GFT_MAX_VIEWS];
 };
 void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream);
 
 // ---- preprocess backward ---------------------------------------------------------------------
 struct PreprocessBwdParams {
-  int P, D, M, M_p;
-  int W, H;
+  int P, D, M, M_p, nviews;
   const float* means3D;
-  const int* radii;
   const float* shs;
   const float* shs_p;
-  const uint32_t* clamped;
   const float* scales;
   const float* rotations;
   float scale_modifier;
-  const float* cov3D;  // precomp or saved
-  const float* viewmatrix;
-  const float* projmatrix;
-  const float* campos;
-  float focal_x, focal_y, tan_fovx, tan_fovy;
-  const float* rec;       // forward blend records (dist)
-  const float* pa;        // [P][2]
-  const float* grad_rec;  // [P][16] from blend backward
-  float near_n, far_n, dist2phase;
-  int use_view_dependent_phase;
-  float phase_offset, dc_offset;
-  int accumulate;  // add into the parameter gradients instead of overwriting
-  // outputs
-  float* dL_dmeans2D;
+  const float* cov3D;      // precomp or saved, [P][6]
+  const float* rec;        // [V][P][20] forward blend records (conic, dist)
+  const uint32_t* clamped; // [V][P]
+  const float* pa;         // [V][P][2]
+  const float* grad_rec;   // [V][P][16] from blend backward
+  int accumulate;          // 0 overwrite, 1 add, 2 atomic add (see include/gftorf.h)
+  // outputs: the parameter gradients, summed over the views of the batch, each row written once
   float* dL_dopacity;
   float* dL_dmeans3D;
   float* dL_dsh;
@@ -174,11 +192,12 @@ struct PreprocessBwdParams {
   float* dL_drotations;
   float* dL_dphase_offset;
   float* dL_ddc_offset;
-  float* dL_dcolors;
-  float* dL_dcov3D;
-  float* dL_dconic;
+  float* dL_dcolors;       // optional: grad of colors_precomp (summed over views)
+  float* dL_dcov3D;        // optional: grad of cov3D_precomp (summed over views)
+  float* dL_dconic;        // optional per-view intermediates of view 0 (single-view debugging)
   float* dL_ddist;
   float* dL_dndc;
+  ViewCam views[GFT_MAX_VIEWS];
 };
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 

@@ -29,7 +29,7 @@ namespace gft {
 namespace {
 
 constexpr int KNN_BOX = 1024;  // BOX_SIZE, simple_knn.cu:18
-constexpr int MM_BLOCKS = 592; // 4 per SM
+constexpr int MM_BLOCKS = 1024; // capacity of the partial min/max array; the grid is 4 blocks per SM
 
 struct KnnWs {
   float* partial;      // [MM_BLOCKS][6]
@@ -253,7 +253,7 @@ size_t knn_workspace_bytes(int P) { return knn_layout(nullptr, P).total; }
 int knn_dist2(const float* points, int P, float* out, char* workspace, cudaStream_t stream) {
   if (P <= 0) return 0;
   KnnWs w = knn_layout(workspace, P);
-  const int mmb = min(MM_BLOCKS, (P + 255) / 256);
+  const int mmb = min(min(MM_BLOCKS, 4 * sm_count()), (P + 255) / 256);
   knn_minmax_kernel<<<mmb, 256, 0, stream>>>(P, points, w.partial);
   knn_minmax_final_kernel<<<1, 32, 0, stream>>>(mmb, w.partial, w.aabb);
   knn_morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, w.aabb, w.keys_a, w.vals_a);

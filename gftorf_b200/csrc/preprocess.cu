@@ -111,55 +111,91 @@ __device__ __forceinline__ void eval_sh_pa(int D, const float* sp, const float* 
 
 }  // namespace
 
+// One block = 256 consecutive Gaussians, ALL views of the batch.  The per-Gaussian parameters
+// (mean, scale, rotation, opacity and the 48 + 32 SH floats: 364 B) are read once; per view the
+// kernel culls, projects, evaluates colour and phasor, writes the view's blend record and counts
+// the Gaussian into every tile it touches (tile_counts, the input of the tile-segmented binning).
+//   pass A (colour SH rows of the warp staged in shared memory): geometry + colour per view
+//   pass B (phase/amplitude SH rows staged in the same buffer):   phasor per view
+// The arithmetic of every view is the single-view sequence pinned to the reference binary.
 __global__ void __launch_bounds__(GFT_BLOCK)
-preprocess_fwd_kernel(PreprocessParams p) {
+preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p) {
   extern __shared__ float fwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
-  __shared__ uint32_t s_warp_tot[GFT_BLOCK / 32];
-  __shared__ uint32_t s_prefix;
 
-  // Block id = blockIdx.x, as in cub::DeviceScan: a block publishes its aggregate right after
-  // phase 1 and only looks back at its very end, when every lower-numbered block has long been
-  // dispatched (blocks are dispatched in index order), so the look-back practically never waits.
-  // (A ticket counter would make the order explicit, but its atomic round trip stalls the whole
-  // block before any work can start: ncu showed 8.5 warps per issue waiting at barriers.)
-  const uint32_t vb = blockIdx.x;
-  const int idx = (int)(vb * GFT_BLOCK + threadIdx.x);
+  const int idx = (int)(blockIdx.x * GFT_BLOCK + threadIdx.x);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-
-  if (vb == 0 && threadIdx.x == 0) {
-    p.key_format_out[0] = (uint32_t)p.key_depth_bits;
-    p.key_format_out[1] = p.key_depth_base;
-  }
-  // Zero tile ranges (empty tiles must read (0,0), rasterizer_impl.cu:341).
-  for (int t = idx; t < p.num_tiles; t += gridDim.x * GFT_BLOCK) p.ranges[t] = make_uint2(0u, 0u);
-
-  uint32_t tiles = 0;
   const bool in_range = idx < p.P;
-  int radius_i = 0;
-  uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
-  float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, pix_x = 0.f, pix_y = 0.f;
-  float3 cov = make_float3(0.f, 0.f, 0.f);
-  float det = 0.f;
-  bool alive = false;
-  const float* __restrict__ V = p.viewmatrix;
-  const float* __restrict__ PM = p.projmatrix;
+  const size_t P = (size_t)p.P;
 
-  // ---- phase 1: cull, project, covariance, radius, tile rectangle -----------------------------
+  float px = 0.f, py = 0.f, pz = 0.f;
   if (in_range) {
-    p.pixels[idx] = 0.f;
     px = __ldg(p.means3D + 3 * idx + 0);
     py = __ldg(p.means3D + 3 * idx + 1);
     pz = __ldg(p.means3D + 3 * idx + 2);
+  }
 
-    // in_frustum, auxiliary.h:152-179: z-only test (NaN passes, as in the reference).
-    vz = xform_row(V, 2, px, py, pz);
-    alive = !(vz < p.near_n || vz > p.far_n);
-    if (!alive && p.prefiltered) {
-      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-      __trap();
+  // ---- frustum test of every view (in_frustum, auxiliary.h:152-179: z only, NaN passes) ----------
+  uint32_t alive_mask = 0;
+  if (in_range) {
+    for (int v = 0; v < p.nviews; ++v) {
+      const ViewCam& vc = p.views[v];
+      const float vz = xform_row(vc.viewmatrix, 2, px, py, pz);
+      const bool ok = !(vz < vc.near_n || vz > vc.far_n);
+      if (!ok && p.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+      alive_mask |= ok ? (1u << v) : 0u;
     }
+  }
+
+  // ---- view-independent: 3D covariance (forward.cu:172-206), saved for the backward -------------
+  Cov3 c3 = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float opacity = 0.f;
+  if (alive_mask) {
+    if (p.cov3D_precomp != nullptr) {
+      const float* c = p.cov3D_precomp + 6 * (size_t)idx;
+      c3.c0 = __ldg(c + 0); c3.c1 = __ldg(c + 1); c3.c2 = __ldg(c + 2);
+      c3.c3 = __ldg(c + 3); c3.c4 = __ldg(c + 4); c3.c5 = __ldg(c + 5);
+    } else {
+      const float* s = p.scales + 3 * (size_t)idx;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      c3 = cov3d_from_scale_rot(__ldg(s), __ldg(s + 1), __ldg(s + 2), p.scale_modifier, q.x, q.y,
+                                q.z, q.w);
+      float2* dst = reinterpret_cast<float2*>(p.g.cov3D + 6 * (size_t)idx);
+      dst[0] = make_float2(c3.c0, c3.c1);
+      dst[1] = make_float2(c3.c2, c3.c3);
+      dst[2] = make_float2(c3.c4, c3.c5);
+    }
+    opacity = __ldg(p.opacities + idx);
+  }
+
+  float* wbuf = fwd_stage + warp * GFT_STAGE_FLOATS_PER_WARP;
+  const int wfirst = (int)(blockIdx.x * GFT_BLOCK + warp * 32);
+  const int nrows = max(0, min(32, p.P - wfirst));
+  const bool any_alive = __any_sync(0xffffffffu, alive_mask != 0u);
+  const bool st_sh = p.shs != nullptr && p.M == 16 && any_alive;
+  const bool st_shp = p.shs_p != nullptr && p.M_p == 16 && any_alive;
+  if (st_sh) {
+    warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
+    __syncwarp();
+  }
+
+  // ================= pass A: geometry + colour, per view ========================================
+  for (int v = 0; v < p.nviews; ++v) {
+    const ViewCam& vc = p.views[v];
+    const float* __restrict__ V = vc.viewmatrix;
+    const float* __restrict__ PM = vc.projmatrix;
+    bool alive = (alive_mask >> v) & 1u;
+    uint32_t tiles = 0;
+    int radius_i = 0;
+    uint32_t rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+    float vx = 0.f, vy = 0.f, vz = 0.f, pix_x = 0.f, pix_y = 0.f;
+    float3 cov = make_float3(0.f, 0.f, 0.f);
+    float det = 0.f;
 
     if (alive) {
+      vz = xform_row(V, 2, px, py, pz);
       vx = xform_row(V, 0, px, py, pz);
       vy = xform_row(V, 1, px, py, pz);
       const float hx = xform_row(PM, 0, px, py, pz);
@@ -169,24 +205,7 @@ preprocess_fwd_kernel(PreprocessParams p) {
       const float projx = __fmul_rn(hx, p_w);
       const float projy = __fmul_rn(hy, p_w);
 
-      Cov3 c3;
-      if (p.cov3D_precomp != nullptr) {
-        const float* c = p.cov3D_precomp + 6 * (size_t)idx;
-        c3.c0 = __ldg(c + 0); c3.c1 = __ldg(c + 1); c3.c2 = __ldg(c + 2);
-        c3.c3 = __ldg(c + 3); c3.c4 = __ldg(c + 4); c3.c5 = __ldg(c + 5);
-      } else {
-        const float* s = p.scales + 3 * (size_t)idx;
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
-        c3 = cov3d_from_scale_rot(__ldg(s), __ldg(s + 1), __ldg(s + 2), p.scale_modifier, q.x, q.y,
-                                  q.z, q.w);
-        // cov3D is saved for the backward pass (rasterizer_impl.cu:471)
-        float2* dst = reinterpret_cast<float2*>(p.cov3D + 6 * (size_t)idx);
-        dst[0] = make_float2(c3.c0, c3.c1);
-        dst[1] = make_float2(c3.c2, c3.c3);
-        dst[2] = make_float2(c3.c4, c3.c5);
-      }
-
-      const Tmat T = ewa_T(V, vx, vy, vz, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy);
+      const Tmat T = ewa_T(V, vx, vy, vz, vc.focal_x, vc.focal_y, vc.tan_fovx, vc.tan_fovy);
       cov = ewa_cov2d(T, c3);
       det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
       alive = !(det == 0.0f);  // forward.cu:325
@@ -197,126 +216,146 @@ preprocess_fwd_kernel(PreprocessParams p) {
         const float lam = fmaxf(__fadd_rn(mid, s), __fsub_rn(mid, s));
         const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(lam), 3.f));
         radius_i = (int)my_radius;
-        pix_x = ndc2pix(projx, p.W);
-        pix_y = ndc2pix(projy, p.H);
-        tile_rect(pix_x, pix_y, radius_i, p.grid_x, p.grid_y, rx0, ry0, rx1, ry1);
+        pix_x = ndc2pix(projx, vc.W);
+        pix_y = ndc2pix(projy, vc.H);
+        tile_rect(pix_x, pix_y, radius_i, vc.grid_x, vc.grid_y, rx0, ry0, rx1, ry1);
         tiles = (rx1 - rx0) * (ry1 - ry0);
         alive = tiles != 0;
       }
     }
-    if (!alive) { tiles = 0; radius_i = 0; }
-    p.radii[idx] = radius_i;
-    p.tiles_touched[idx] = tiles;
-  }
-
-  // ---- block-wide inclusive scan of `tiles` ------------------------------------------------
-  uint32_t incl = tiles;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= (uint32_t)o) incl += n;
-  }
-  if (lane == 31) s_warp_tot[warp] = incl;
-  __syncthreads();
-  uint32_t warp_base = 0, block_total = 0;
-#pragma unroll
-  for (int w = 0; w < GFT_BLOCK / 32; ++w) {
-    const uint32_t t = s_warp_tot[w];
-    if ((uint32_t)w < warp) warp_base += t;
-    block_total += t;
-  }
-  incl += warp_base;
-
-  // publish this block's aggregate now; the look-back happens after the appearance work
-  if (warp == 0 && lane == 0) {
-    if (vb == 0) st_release_u64(p.scan_state, (2ull << 32) | block_total);
-    else st_release_u64(p.scan_state + vb, (1ull << 32) | block_total);
-  }
-
-  // ---- phase 2: appearance.  The SH rows of a warp's 32 consecutive Gaussians are one contiguous
-  // chunk of global memory: it is staged through shared memory with coalesced loads whenever a
-  // lane of the warp survived the culling. ------------------------------------------------------
-  float* wbuf = fwd_stage + warp * GFT_STAGE_FLOATS_PER_WARP;
-  const int wfirst = (int)(vb * GFT_BLOCK + warp * 32);
-  const int nrows = max(0, min(32, p.P - wfirst));
-  const bool any_alive = __any_sync(0xffffffffu, alive);
-  const bool st_sh = p.shs != nullptr && p.M == 16 && any_alive;
-  const bool st_shp = p.shs_p != nullptr && p.M_p == 16 && any_alive;
-  if (st_sh) {
-    warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
-    __syncwarp();
-  }
-
-  float basis[16];
-  float cr = 0.f, cg = 0.f, cb = 0.f;
-  uint32_t clamp_bits = 0;
-  if (alive) {
-    // ---- view direction and SH basis (forward.cu:25-27,74-76) ------------------------------
-    if (p.shs != nullptr || p.shs_p != nullptr) {
-      const float cxw = __ldg(p.campos + 0), cyw = __ldg(p.campos + 1), czw = __ldg(p.campos + 2);
-      // pinned to the reference binary: FMUL(dy,dy) -> FFMA(dx,dx,.) -> FFMA(dz,dz,.), IEEE sqrt/div
-      float dirx = __fsub_rn(px, cxw);
-      float diry = __fsub_rn(py, cyw);
-      float dirz = __fsub_rn(pz, czw);
-      const float len = __fsqrt_rn(dot3c(dirx, dirx, diry, diry, dirz, dirz));
-      dirx = __fdiv_rn(dirx, len);
-      diry = __fdiv_rn(diry, len);
-      dirz = __fdiv_rn(dirz, len);
-      sh_basis(p.D, dirx, diry, dirz, basis);
+    if (!alive) { tiles = 0; radius_i = 0; alive_mask &= ~(1u << v); }
+    if (in_range) {
+      vc.radii[idx] = radius_i;
+      vc.pixels[idx] = 0.f;
+      p.g.tiles_touched[v * P + idx] = tiles;
     }
-    // ---- colour (forward.cu:346-359) ---------------------------------------------------------
-    if (p.colors_precomp != nullptr) {
-      cr = __ldg(p.colors_precomp + 3 * (size_t)idx + 0);
-      cg = __ldg(p.colors_precomp + 3 * (size_t)idx + 1);
-      cb = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
+
+    // one count per (Gaussian, tile) instance of this view
+    {
+      uint32_t* cnt = p.tile_counts + vc.tile_base;
+      const uint32_t gx = (uint32_t)vc.grid_x;
+      for_each_tile(rx0, ry0, rx1, tiles, 0u, lane,
+                    [&](uint32_t tx, uint32_t ty, uint32_t) { atomicAdd(cnt + ty * gx + tx, 1u); });
     }
-    if (p.shs != nullptr) {
-      float r0, r1, r2;
-      if (st_sh) eval_sh_rgb(p.D, wbuf + lane * 49, basis, r0, r1, r2);
-      else eval_sh_rgb(p.D, p.shs + (size_t)idx * p.M * 3, basis, r0, r1, r2);
-      r0 = __fadd_rn(r0, 0.5f); r1 = __fadd_rn(r1, 0.5f); r2 = __fadd_rn(r2, 0.5f);
-      clamp_bits |= (r0 < 0.f) ? 1u : 0u;
-      clamp_bits |= (r1 < 0.f) ? (1u << 8) : 0u;
-      clamp_bits |= (r2 < 0.f) ? (1u << 16) : 0u;
-      cr = fmaxf(r0, 0.f); cg = fmaxf(r1, 0.f); cb = fmaxf(r2, 0.f);
+
+    if (alive) {
+      // ---- colour (forward.cu:346-359) -------------------------------------------------------
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+      uint32_t clamp_bits = 0;
+      if (p.colors_precomp != nullptr) {
+        cr = __ldg(p.colors_precomp + 3 * (size_t)idx + 0);
+        cg = __ldg(p.colors_precomp + 3 * (size_t)idx + 1);
+        cb = __ldg(p.colors_precomp + 3 * (size_t)idx + 2);
+      }
+      if (p.shs != nullptr) {   // SH overwrites a precomputed colour when both are given (forward.cu:346-359)
+        // view direction and SH basis (forward.cu:25-27): FMUL(dy,dy) -> FFMA(dx,dx,.) ->
+        // FFMA(dz,dz,.), IEEE sqrt/div, as in the reference binary
+        float basis[16];
+        float dirx = __fsub_rn(px, __ldg(vc.campos + 0));
+        float diry = __fsub_rn(py, __ldg(vc.campos + 1));
+        float dirz = __fsub_rn(pz, __ldg(vc.campos + 2));
+        const float len = __fsqrt_rn(dot3c(dirx, dirx, diry, diry, dirz, dirz));
+        dirx = __fdiv_rn(dirx, len);
+        diry = __fdiv_rn(diry, len);
+        dirz = __fdiv_rn(dirz, len);
+        sh_basis(p.D, dirx, diry, dirz, basis);
+        float r0, r1, r2;
+        if (st_sh) eval_sh_rgb(p.D, wbuf + lane * 49, basis, r0, r1, r2);
+        else eval_sh_rgb(p.D, p.shs + (size_t)idx * p.M * 3, basis, r0, r1, r2);
+        r0 = __fadd_rn(r0, 0.5f); r1 = __fadd_rn(r1, 0.5f); r2 = __fadd_rn(r2, 0.5f);
+        clamp_bits |= (r0 < 0.f) ? 1u : 0u;
+        clamp_bits |= (r1 < 0.f) ? (1u << 8) : 0u;
+        clamp_bits |= (r2 < 0.f) ? (1u << 16) : 0u;
+        cr = fmaxf(r0, 0.f); cg = fmaxf(r1, 0.f); cb = fmaxf(r2, 0.f);
+      }
+
+      const float det_inv = __frcp_rn(det);
+      const float conA = __fmul_rn(cov.z, det_inv);
+      const float conB = __fmul_rn(cov.y, -det_inv);
+      const float conC = __fmul_rn(cov.x, det_inv);
+      // distance to the light (forward.cu:361): y^2 rounded, x^2 and z^2 fused, as compiled
+      const float dist = __fsqrt_rn(dot3c(vx, vx, vy, vy, vz, vz));
+
+      // ---- conservative contribution extents for sub-tile culling ---------------------------
+      // A pixel can pass the alpha test only if opacity*exp(power) >= 1/255, i.e.
+      // d^T Q d <= 2 ln(255*opacity).  The rounding error of the float `power` chain is bounded
+      // by 2k*cond(Sigma)*q (k = 4e-7), so inflating the threshold by 1/(1-4k*cond) keeps the box
+      // a superset of what the reference's arithmetic can accept.  Anything doubtful -> no cull.
+      float ex = __int_as_float(0x7f800000), ey = __int_as_float(0x7f800000);  // +inf
+      if (!p.subtile_cull) {
+        // keep +inf: no culling
+      } else if (opacity < (1.0f / 255.0f)) {
+        ex = ey = -__int_as_float(0x7f800000);  // alpha <= opacity < 1/255: can never contribute
+      } else {
+        const double dA = (double)conA, dB = (double)conB, dC = (double)conC;
+        const double dq = dA * dC - dB * dB;
+        const float mid = 0.5f * (cov.x + cov.z);
+        const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lmax = mid + sq, lmin = mid - sq;
+        const float cond = lmax / lmin;
+        if (dq > 0.0 && dA > 0.0 && dC > 0.0 && lmin > 0.f && cond < 2.0e5f && cond == cond) {
+          const float t2 = (2.0f * __logf(255.0f * opacity) + 0.04f) / (1.0f - 1.6e-6f * cond);
+          const float sxx = (float)(dC / dq), syy = (float)(dA / dq);
+          ex = sqrtf(t2 * sxx) * 1.0001f + 0.02f;
+          ey = sqrtf(t2 * syy) * 1.0001f + 0.02f;
+        }
+      }
+
+      float4* rec = reinterpret_cast<float4*>(p.g.rec + (v * P + idx) * GFT_REC_FLOATS);
+      rec[0] = make_float4(pix_x, pix_y, ex, ey);
+      rec[1] = make_float4(conA, conB, conC, opacity);
+      rec[2] = make_float4(cr, cg, cb, dist);
+      p.g.depths[v * P + idx] = vz;
+      p.g.clamped[v * P + idx] = clamp_bits;
+      reinterpret_cast<uint2*>(p.g.rect)[v * P + idx] = make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
     }
   }
+
   __syncwarp();
   if (st_shp) {
     warp_stage_in<32>(p.shs_p + (size_t)wfirst * 32, nrows, wbuf, lane);
     __syncwarp();
   }
 
-  if (alive) {
-    const float det_inv = __frcp_rn(det);
-    const float conA = __fmul_rn(cov.z, det_inv);
-    const float conB = __fmul_rn(cov.y, -det_inv);
-    const float conC = __fmul_rn(cov.x, det_inv);
-    const float opacity = __ldg(p.opacities + idx);
-
-    // ---- distance to light, falloff (forward.cu:361-363) -----------------------------------
-    // pinned to the reference binary (SASS of preprocessCUDA): y^2 rounded, x^2 and z^2 fused
+  // ================= pass B: phasor, per view (forward.cu:361-407) ==============================
+  for (int v = 0; v < p.nviews; ++v) {
+    if (!((alive_mask >> v) & 1u)) continue;
+    const ViewCam& vc = p.views[v];
+    const float* __restrict__ V = vc.viewmatrix;
+    // the same three rows as in pass A: identical bits
+    const float vz = xform_row(V, 2, px, py, pz);
+    const float vx = xform_row(V, 0, px, py, pz);
+    const float vy = xform_row(V, 1, px, py, pz);
     const float dist = __fsqrt_rn(dot3c(vx, vx, vy, vy, vz, vz));
-    const float ndc = __fmul_rn(__fsub_rn(1.f, __fdiv_rn(p.near_n, dist)),
-                                __fdiv_rn(p.far_n, __fsub_rn(p.far_n, p.near_n)));
+    const float ndc = __fmul_rn(__fsub_rn(1.f, __fdiv_rn(vc.near_n, dist)),
+                                __fdiv_rn(vc.far_n, __fsub_rn(vc.far_n, vc.near_n)));
     const float factor = __frcp_rn(__fmul_rn(dist, dist));
 
-    // ---- phasor (forward.cu:365-407) --------------------------------------------------------
     // With neither shs_p nor phasors_precomp the reference leaves real_img_amp uninitialised
     // (SURVEY A.7-7); we define those features as 0.
     float ph[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float pa0 = 0.f, pa1 = 0.f;
     bool have_ph = false;
     float phase = 0.f, amp = 0.f;
+    uint32_t amp_clamped = 0;
     if (p.phasors_precomp != nullptr) {
-      phase = __fmul_rn(dist, p.dist2phase);
+      phase = __fmul_rn(dist, vc.dist2phase);
       pa0 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 0);
       pa1 = __ldg(p.phasors_precomp + 2 * (size_t)idx + 1);
-      if (p.use_view_dependent_phase) phase = __fadd_rn(phase, pa0);
+      if (vc.use_view_dependent_phase) phase = __fadd_rn(phase, pa0);
       amp = pa1;
       have_ph = true;
     }
     if (p.shs_p != nullptr) {
+      float basis[16];
+      float dirx = __fsub_rn(px, __ldg(vc.campos + 0));
+      float diry = __fsub_rn(py, __ldg(vc.campos + 1));
+      float dirz = __fsub_rn(pz, __ldg(vc.campos + 2));
+      const float len = __fsqrt_rn(dot3c(dirx, dirx, diry, diry, dirz, dirz));
+      dirx = __fdiv_rn(dirx, len);
+      diry = __fdiv_rn(diry, len);
+      dirz = __fdiv_rn(dirz, len);
+      sh_basis(p.D, dirx, diry, dirz, basis);
       float q0, q1, dc0;
       if (st_shp) {
         eval_sh_pa(p.D, wbuf + lane * 33, basis, q0, q1);
@@ -329,17 +368,17 @@ preprocess_fwd_kernel(PreprocessParams p) {
       q1 = __fadd_rn(q1, 0.5f);
       // remove phase DC (forward.cu:115): ((q0 + 0.5) - 0.5) - FMUL(C0, sh_p[0].x)
       q0 = __fsub_rn(__fsub_rn(__fadd_rn(q0, 0.5f), 0.5f), __fmul_rn(kSH_C0, dc0));
-      if (q1 < 0.f) { clamp_bits |= (1u << 24); q1 = 0.f; }
+      if (q1 < 0.f) { amp_clamped = 1u << 24; q1 = 0.f; }
       pa0 = q0; pa1 = q1;
-      phase = __fmaf_rn(dist, p.dist2phase, p.phase_offset);
-      if (p.use_view_dependent_phase) phase = __fadd_rn(q0, phase);
+      phase = __fmaf_rn(dist, vc.dist2phase, vc.phase_offset);
+      if (vc.use_view_dependent_phase) phase = __fadd_rn(q0, phase);
       amp = q1;
       have_ph = true;
     }
     if (have_ph) {
       float sn, cs;
       sincosf(phase, &sn, &cs);
-      const float dc = p.dc_offset;   // (trig +- dc) * amp * factor, left to right (forward.cu:399-406)
+      const float dc = vc.dc_offset;   // (trig +- dc) * amp * factor, left to right (forward.cu:399-406)
       ph[0] = __fmul_rn(__fmul_rn(cs, amp), factor);
       ph[1] = __fmul_rn(__fmul_rn(sn, amp), factor);
       ph[2] = __fmul_rn(amp, factor);
@@ -348,78 +387,12 @@ preprocess_fwd_kernel(PreprocessParams p) {
       ph[5] = __fmul_rn(__fmul_rn(__fadd_rn(sn, dc), amp), factor);
       ph[6] = __fmul_rn(__fmul_rn(__fadd_rn(-sn, dc), amp), factor);
     }
-
-    // ---- conservative contribution extents for sub-tile culling ---------------------------
-    // A pixel can pass the alpha test only if opacity*exp(power) >= 1/255, i.e.
-    // d^T Q d <= 2 ln(255*opacity).  The rounding error of the float `power` chain is bounded
-    // by 2k*cond(Sigma)*q (k = 4e-7), so inflating the threshold by 1/(1-4k*cond) keeps the box
-    // a superset of what the reference's arithmetic can accept.  Anything doubtful -> no cull.
-    float ex = __int_as_float(0x7f800000), ey = __int_as_float(0x7f800000);  // +inf
-    if (!p.subtile_cull) {
-      // keep +inf: no culling
-    } else if (opacity < (1.0f / 255.0f)) {
-      ex = ey = -__int_as_float(0x7f800000);  // alpha <= opacity < 1/255: can never contribute
-    } else {
-      const double dA = (double)conA, dB = (double)conB, dC = (double)conC;
-      const double dq = dA * dC - dB * dB;
-      const float mid = 0.5f * (cov.x + cov.z);
-      const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
-      const float lmax = mid + sq, lmin = mid - sq;
-      const float cond = lmax / lmin;
-      if (dq > 0.0 && dA > 0.0 && dC > 0.0 && lmin > 0.f && cond < 2.0e5f && cond == cond) {
-        const float t2 = (2.0f * __logf(255.0f * opacity) + 0.04f) / (1.0f - 1.6e-6f * cond);
-        const float sxx = (float)(dC / dq), syy = (float)(dA / dq);
-        ex = sqrtf(t2 * sxx) * 1.0001f + 0.02f;
-        ey = sqrtf(t2 * syy) * 1.0001f + 0.02f;
-      }
-    }
-
-    float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS);
-    rec[0] = make_float4(pix_x, pix_y, ex, ey);
-    rec[1] = make_float4(conA, conB, conC, opacity);
-    rec[2] = make_float4(cr, cg, cb, dist);
+    float4* rec = reinterpret_cast<float4*>(p.g.rec + (v * P + idx) * GFT_REC_FLOATS);
     rec[3] = make_float4(ph[0], ph[1], ph[2], ph[3]);
     rec[4] = make_float4(ph[4], ph[5], ph[6], ndc);
-    p.depths[idx] = vz;
-    p.clamped[idx] = clamp_bits;
-    reinterpret_cast<float2*>(p.pa)[idx] = make_float2(pa0, pa1);
-    reinterpret_cast<uint2*>(p.rect)[idx] = make_uint2(rx0 | (ry0 << 16), rx1 | (ry1 << 16));
+    if (amp_clamped) p.g.clamped[v * P + idx] |= amp_clamped;   // own word, written in pass A
+    reinterpret_cast<float2*>(p.g.pa)[v * P + idx] = make_float2(pa0, pa1);
   }
-
-  // ---- chained scan across blocks: status word = flag<<32 | value --------------------------
-  // flag 1 = block aggregate available, 2 = inclusive prefix available.
-  if (warp == 0) {
-    unsigned long long* st = p.scan_state;
-    uint32_t excl = 0;
-    if (vb != 0) {
-      int base = (int)vb - 1;
-      while (true) {
-        const int j = base - (int)lane;
-        unsigned long long s = 0;
-        if (j >= 0) {
-          do { s = ld_acquire_u64(st + j); } while ((s >> 32) == 0ull);
-        }
-        const uint32_t flag = j >= 0 ? (uint32_t)(s >> 32) : 2u;  // virtual prefix 0 before block 0
-        const uint32_t val = j >= 0 ? (uint32_t)s : 0u;
-        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
-        // sum values of lanes up to and including the first (nearest) lane holding a prefix
-        const int first = pmask ? (__ffs(pmask) - 1) : 31;
-        uint32_t v = (lane <= (uint32_t)first) ? val : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (pmask) break;
-        base -= 32;
-      }
-      if (lane == 0) st_release_u64(st + vb, (2ull << 32) | (unsigned long long)(excl + block_total));
-    }
-    if (lane == 0) {
-      s_prefix = excl;
-      if (vb == gridDim.x - 1) *p.num_rendered = excl + block_total;
-    }
-  }
-  __syncthreads();
-  if (idx < p.P) p.point_offsets[idx] = s_prefix + incl;
 }
 
 // markVisible / checkFrustum, rasterizer_impl.cu:54-68

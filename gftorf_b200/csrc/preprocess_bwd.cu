@@ -31,13 +31,15 @@ __device__ __forceinline__ V3 dnormvdv3(V3 v, V3 dv) {
   return o;
 }
 
-// SH backward shared by colour (NC=3) and phasor (NC=2) (backward.cu:20-139, 143-260).
-// Reads the coefficient row `sh` first (direction derivative), THEN writes the gradient row `dsh`
-// — rows [0, ncoef) and zeros for rows [ncoef, M) — so `dsh` may alias `sh` (in-place in the
-// warp's shared staging buffer).  Returns dL/ddir before the normalisation Jacobian.
+// SH backward shared by colour (NC=3) and phasor (NC=2) (backward.cu:20-139, 143-260), split in
+// two so that several views can share one staged coefficient row:
+//   sh_dir_grad  reads the coefficient row and returns dL/ddir before the normalisation Jacobian;
+//   sh_coef_grad writes (FIRST) or adds (!FIRST) basis_k(dir) * g_c into the gradient row — rows
+//                [0, ncoef) and, when FIRST, zeros for rows [ncoef, M) — and may therefore
+//                overwrite the coefficient row in place once every view has read it.
 template <int NC>
-__device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, float z, const float* sh,
-                                          const float* g, float* dsh) {
+__device__ __forceinline__ V3 sh_dir_grad(int deg, float x, float y, float z, const float* sh,
+                                          const float* g) {
   float dx[NC], dy[NC], dz[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) { dx[c] = 0.f; dy[c] = 0.f; dz[c] = 0.f; }
@@ -82,10 +84,27 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, floa
       }
     }
   }
-  // all reads of `sh` are done; now the gradient row
+  V3 d = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {  // glm::dot(dXdx, dL_dX)
+    d.x += dx[c] * g[c];
+    d.y += dy[c] * g[c];
+    d.z += dz[c] * g[c];
+  }
+  return d;
+}
+
+template <int NC, bool FIRST>
+__device__ __forceinline__ void sh_coef_grad(int deg, int M, float x, float y, float z,
+                                             const float* g, float* dsh) {
+  const float xx = x * x, yy = y * y, zz = z * z;
+  const float xy = x * y, yz = y * z, xz = x * z;
   auto put = [&](int k, float basis) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = basis * g[c];
+    for (int c = 0; c < NC; ++c) {
+      if (FIRST) dsh[k * NC + c] = basis * g[c];
+      else dsh[k * NC + c] += basis * g[c];
+    }
   };
   put(0, kSH_C0);
   if (deg > 0) {
@@ -109,19 +128,13 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, float x, float y, floa
       }
     }
   }
-  const int ncoef = (deg + 1) * (deg + 1);
-  for (int k = ncoef; k < M; ++k) {
+  if (FIRST) {
+    const int ncoef = (deg + 1) * (deg + 1);
+    for (int k = ncoef; k < M; ++k) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) dsh[k * NC + c] = 0.f;
+      for (int c = 0; c < NC; ++c) dsh[k * NC + c] = 0.f;
+    }
   }
-  V3 d = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {  // glm::dot(dXdx, dL_dX)
-    d.x += dx[c] * g[c];
-    d.y += dy[c] * g[c];
-    d.z += dz[c] * g[c];
-  }
-  return d;
 }
 
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
@@ -140,230 +153,292 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 
 }  // namespace
 
-// Order of work per Gaussian (the mean gradient is a sum of five parts; they are accumulated in
-// the order SH colour, phasor, depth, cov2D, projection — the reference's order is cov2D,
-// projection, SH colour, phasor, depth; float addition order is the only difference):
+// One block = 256 consecutive Gaussians, ALL views of the batch: the parameter gradients are the
+// sums over the views, every row is written exactly once with plain stores (ACC = 0), and the
+// 364 B/Gaussian of parameters are read once.  Order of work per Gaussian (the mean gradient is a
+// sum of five parts per view; they are accumulated in the order SH colour, phasor, depth, cov2D,
+// projection — the reference's order is cov2D, projection, SH colour, phasor, depth; float
+// addition order is the only difference):
 //   1. SH colour backward and 2. phasor + SH(phase, amplitude) backward: the coefficient rows of
 //      the warp's 32 Gaussians are one contiguous chunk, staged through shared memory (coalesced
-//      in), differentiated in place, and streamed out coalesced as dL_dsh / dL_dsh_p;
-//   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation.
-template <int ACC>
-__global__ void __launch_bounds__(GFT_BLOCK, 4)
-preprocess_bwd_kernel(PreprocessBwdParams p) {
+//      in); every view first takes its direction derivative from the row, then the row is
+//      overwritten in place by the sum over views of basis(dir_v) x g_v and streamed out coalesced
+//      as dL_dsh / dL_dsh_p;
+//   3. depth / ndc, 4. cov2D backward, 5. projection per view; 6. cov3D -> scale, rotation once,
+//      from the summed dL_dcov3D (that step is linear in it).
+template <int ACC, int MINB>
+__global__ void __launch_bounds__(GFT_BLOCK, MINB)
+preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
   // ACC: add into the six parameter-gradient outputs (means3D, sh, sh_p, opacity, scales,
-  // rotations) and the two scalar offsets instead of overwriting them — several views then
-  // accumulate straight into one gradient bucket, and culled Gaussians cost no gradient traffic.
-  // Per-view outputs (means2D and the optional intermediates) are always overwritten.
+  // rotations) and the two scalar offsets instead of overwriting them (1: plain read-modify-write,
+  // 2: atomics) — several calls then accumulate into one gradient bucket, and Gaussians culled in
+  // every view of the call cost no gradient traffic.  Per-view outputs (means2D and the optional
+  // intermediates) are always overwritten.
   extern __shared__ float bwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
   __shared__ float s_red[GFT_BLOCK / 32];
   const int idx = blockIdx.x * GFT_BLOCK + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = idx < p.P;
-  const bool vis = in_range && (__ldg(p.radii + idx) > 0);
+  const size_t P = (size_t)p.P;
   float* wbuf = bwd_stage + warp * GFT_STAGE_FLOATS_PER_WARP;
   const int wfirst = blockIdx.x * GFT_BLOCK + (int)warp * 32;
   const int nrows = max(0, min(32, p.P - wfirst));
+
+  uint32_t vis_mask = 0;
+  if (in_range) {
+    for (int v = 0; v < p.nviews; ++v) vis_mask |= (__ldg(p.views[v].radii + idx) > 0) ? (1u << v) : 0u;
+  }
+  const bool vis = vis_mask != 0u;
   const bool any_vis = __any_sync(0xffffffffu, vis);
 
-  float part_phase = 0.f, part_dc = 0.f;
-
-  if (in_range && !vis) {
-    // culled: every output row is zero (the reference leaves its zero-filled tensors untouched);
-    // the SH gradient rows are zeroed through the staged path below when it is active
-    p.dL_dmeans2D[3 * (size_t)idx + 0] = 0.f;
-    p.dL_dmeans2D[3 * (size_t)idx + 1] = 0.f;
-    p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    if (!ACC) {
-      p.dL_dopacity[idx] = 0.f;
-      p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
-      p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
-      p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
-      if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
-      if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
-    }
-    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = 0.f;
-    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
-    if (p.dL_dconic) for (int k = 0; k < 4; ++k) p.dL_dconic[4 * (size_t)idx + k] = 0.f;
-    if (p.dL_ddist) p.dL_ddist[idx] = 0.f;
-    if (p.dL_dndc) p.dL_dndc[idx] = 0.f;
-  }
-
-  // ---- per-Gaussian inputs kept in registers across the staged sections ----------------------
-  const float* __restrict__ V = p.viewmatrix;
-  const float* __restrict__ proj = p.projmatrix;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
   float mx = 0.f, my = 0.f, mz = 0.f;
-  V3 dir_orig = {0.f, 0.f, 0.f};
-  float dirx = 0.f, diry = 0.f, dirz = 0.f;
-  uint32_t clamp_bits = 0;
-  float dmx = 0.f, dmy = 0.f, dmz = 0.f;
   if (vis) {
-    const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * GFT_GRAD_FLOATS);
-    // record: S_x S_y S_xx S_xy | S_yy opac col.r col.g | col.b dist ndc phA | phB phC phS -
-    a0 = __ldg(gr + 0); a1 = __ldg(gr + 1); a2 = __ldg(gr + 2); a3 = __ldg(gr + 3);
     mx = __ldg(p.means3D + 3 * (size_t)idx + 0);
     my = __ldg(p.means3D + 3 * (size_t)idx + 1);
     mz = __ldg(p.means3D + 3 * (size_t)idx + 2);
-    clamp_bits = __ldg(p.clamped + idx);
-    if (p.shs != nullptr || p.shs_p != nullptr) {
-      dir_orig.x = mx - __ldg(p.campos + 0);
-      dir_orig.y = my - __ldg(p.campos + 1);
-      dir_orig.z = mz - __ldg(p.campos + 2);
-      const float len =
-          sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-      dirx = dir_orig.x / len;
-      diry = dir_orig.y / len;
-      dirz = dir_orig.z / len;
-    }
   }
-  const float dcol[3] = {a1.z, a1.w, a2.x};
+  float dmx = 0.f, dmy = 0.f, dmz = 0.f;
+  float part_phase = 0.f, part_dc = 0.f;
+
+  // direction to the camera of view v, raw and normalised
+  auto view_dir = [&](const ViewCam& vc, V3& raw, float& nx, float& ny, float& nz) {
+    raw.x = mx - __ldg(vc.campos + 0);
+    raw.y = my - __ldg(vc.campos + 1);
+    raw.z = mz - __ldg(vc.campos + 2);
+    const float len = sqrtf(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
+    nx = raw.x / len; ny = raw.y / len; nz = raw.z / len;
+  };
+  // record: S_x S_y S_xx S_xy | S_yy opac col.r col.g | col.b dist ndc phA | phB phC phS -
+  auto grad_rec4 = [&](int v, int q) {
+    return __ldg(reinterpret_cast<const float4*>(p.grad_rec + (v * P + idx) * GFT_GRAD_FLOATS) + q);
+  };
+  // colour gradient of view v after the clamp mask (backward.cu:36-40)
+  auto colour_grad = [&](int v, float* g) {
+    const float4 a1 = grad_rec4(v, 1), a2 = grad_rec4(v, 2);
+    const uint32_t cb = __ldg(p.clamped + v * P + idx);
+    g[0] = a1.z * ((cb & 0x1u) ? 0.f : 1.f);
+    g[1] = a1.w * ((cb & 0x100u) ? 0.f : 1.f);
+    g[2] = a2.x * ((cb & 0x10000u) ? 0.f : 1.f);
+  };
 
   // ---------------- 1. SH colour backward (backward.cu:20-139) --------------------------------
   if (p.shs != nullptr) {
     const bool staged = p.M == 16;
-    if (staged && any_vis) {
-      warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
-      __syncwarp();
-    }
-    if (vis) {
-      float g[3] = {dcol[0], dcol[1], dcol[2]};
-      g[0] *= (clamp_bits & 0x1u) ? 0.f : 1.f;
-      g[1] *= (clamp_bits & 0x100u) ? 0.f : 1.f;
-      g[2] *= (clamp_bits & 0x10000u) ? 0.f : 1.f;
-      V3 dL_ddir;
-      if (staged) {
-        float* row = wbuf + lane * 49;
-        dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, row, g, row);
-      } else if (!ACC) {
-        dL_ddir = sh_backward<3>(p.D, p.M, dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g,
-                                 p.dL_dsh + (size_t)idx * p.M * 3);
-      } else {
-        float tmp[48];
-        dL_ddir = sh_backward<3>(p.D, min(p.M, 16), dirx, diry, dirz, p.shs + (size_t)idx * p.M * 3, g, tmp);
-        const int ncf = 3 * (p.D + 1) * (p.D + 1);
-        for (int k = 0; k < ncf; ++k) acc_store<ACC>(p.dL_dsh + (size_t)idx * p.M * 3 + k, tmp[k]);
-      }
-      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
-      dmx += dm.x; dmy += dm.y; dmz += dm.z;
-    } else if (in_range) {
-      if (staged) {
-        if (any_vis) for (int k = 0; k < 48; ++k) wbuf[lane * 49 + k] = 0.f;
-      } else if (!ACC) {
-        for (int k = 0; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * 3 * p.M + k] = 0.f;
-      }
-    }
     if (staged) {
       if (any_vis) {
+        warp_stage_in<48>(p.shs + (size_t)wfirst * 48, nrows, wbuf, lane);
+        __syncwarp();
+        float* row = wbuf + lane * 49;
+        if (vis) {
+          for (int v = 0; v < p.nviews; ++v) {           // every view reads the coefficients ...
+            if (!((vis_mask >> v) & 1u)) continue;
+            float g[3]; V3 raw; float nx, ny, nz;
+            colour_grad(v, g);
+            view_dir(p.views[v], raw, nx, ny, nz);
+            const V3 dm = dnormvdv3(raw, sh_dir_grad<3>(p.D, nx, ny, nz, row, g));
+            dmx += dm.x; dmy += dm.y; dmz += dm.z;
+          }
+          bool first = true;
+          for (int v = 0; v < p.nviews; ++v) {           // ... then the row becomes the gradient row
+            if (!((vis_mask >> v) & 1u)) continue;
+            float g[3]; V3 raw; float nx, ny, nz;
+            colour_grad(v, g);
+            view_dir(p.views[v], raw, nx, ny, nz);
+            if (first) sh_coef_grad<3, true>(p.D, 16, nx, ny, nz, g, row);
+            else sh_coef_grad<3, false>(p.D, 16, nx, ny, nz, g, row);
+            first = false;
+          }
+        } else if (in_range) {
+          for (int k = 0; k < 48; ++k) row[k] = 0.f;
+        }
         __syncwarp();
         warp_stage_out<48, ACC>(p.dL_dsh + (size_t)wfirst * 48, nrows, wbuf, lane);
         __syncwarp();
       } else if (!ACC) {
         for (int e = (int)lane; e < nrows * 48; e += 32) p.dL_dsh[(size_t)wfirst * 48 + e] = 0.f;
       }
+    } else if (in_range) {                               // M != 16: rows straight from global memory
+      float tmp[48];
+      const int Mc = min(p.M, 16);
+      for (int k = 0; k < 3 * Mc; ++k) tmp[k] = 0.f;
+      if (vis) {
+        const float* sh = p.shs + (size_t)idx * p.M * 3;
+        bool first = true;
+        for (int v = 0; v < p.nviews; ++v) {
+          if (!((vis_mask >> v) & 1u)) continue;
+          float g[3]; V3 raw; float nx, ny, nz;
+          colour_grad(v, g);
+          view_dir(p.views[v], raw, nx, ny, nz);
+          const V3 dm = dnormvdv3(raw, sh_dir_grad<3>(p.D, nx, ny, nz, sh, g));
+          dmx += dm.x; dmy += dm.y; dmz += dm.z;
+          if (first) sh_coef_grad<3, true>(p.D, Mc, nx, ny, nz, g, tmp);
+          else sh_coef_grad<3, false>(p.D, Mc, nx, ny, nz, g, tmp);
+          first = false;
+        }
+      }
+      if (!ACC || vis) {
+        for (int k = 0; k < 3 * Mc; ++k) acc_store<ACC>(p.dL_dsh + (size_t)idx * p.M * 3 + k, tmp[k]);
+        if (!ACC) for (int k = 3 * Mc; k < 3 * p.M; ++k) p.dL_dsh[(size_t)idx * p.M * 3 + k] = 0.f;
+      }
     }
   }
 
   // ---------------- 2. phasor backward (backward.cu:525-587) ----------------------------------
-  float dist = 0.f, m_view_x = 0.f, m_view_y = 0.f, m_view_z = 0.f;
-  if (vis) {
-    dist = __ldg(p.rec + (size_t)idx * GFT_REC_FLOATS + 11);
-    m_view_x = V[0] * mx + V[4] * my + V[8] * mz + V[12];
-    m_view_y = V[1] * mx + V[5] * my + V[9] * mz + V[13];
-    m_view_z = V[2] * mx + V[6] * my + V[10] * mz + V[14];
-  }
-  if (p.shs_p != nullptr) {
-    const bool staged = p.M_p == 16;
-    if (staged && any_vis) {
-      warp_stage_in<32>(p.shs_p + (size_t)wfirst * 32, nrows, wbuf, lane);
-      __syncwarp();
-    }
-    if (vis) {
-      const float phA = a2.w, phB = a3.x, phC = a3.y, phS = a3.z;
-      const float2 pa = __ldg(reinterpret_cast<const float2*>(p.pa) + idx);
-      float phase = dist * p.dist2phase + p.phase_offset;
-      if (p.use_view_dependent_phase) phase += pa.x;
-      const float amplitude = pa.y;
-      const float factor = 1.0f / (dist * dist);
-      float sin_p, cos_p;
-      sincosf(phase, &sin_p, &cos_p);
-      const float dc = p.dc_offset;
-      // phA = dR+dq1-dq2, phB = dI+dq3-dq4, phC = dA, phS = dq1+dq2+dq3+dq4 (summed in blend_bwd)
-      const float dphase_sum = cos_p * phB - sin_p * phA;                // backward.cu:551-559
-      const float damp_sum = cos_p * phA + sin_p * phB + phC + dc * phS;  // backward.cu:562-566
-      float gpa[2] = {0.f, 0.f};
-      if (p.use_view_dependent_phase) gpa[0] = dphase_sum * amplitude * factor;
-      part_phase = dphase_sum * amplitude * factor;
-      gpa[1] = damp_sum * factor;
-      part_dc = phS * amplitude * factor;                                 // backward.cu:567
-      const float coeff = dphase_sum * p.dist2phase * amplitude * factor / dist -
+  // per view: d(phase), d(amplitude) from the four phasor sums of the blend backward; their SH
+  // gradient seeds gpa[2]; the distance term of the mean gradient
+  auto phasor_seeds = [&](int v, const ViewCam& vc, float* gpa, bool with_mean) {
+    const float4 a2 = grad_rec4(v, 2), a3 = grad_rec4(v, 3);
+    const float phA = a2.w, phB = a3.x, phC = a3.y, phS = a3.z;
+    const float dist = __ldg(p.rec + (v * P + idx) * GFT_REC_FLOATS + 11);
+    const float2 pa = __ldg(reinterpret_cast<const float2*>(p.pa) + v * P + idx);
+    float phase = dist * vc.dist2phase + vc.phase_offset;
+    if (vc.use_view_dependent_phase) phase += pa.x;
+    const float amplitude = pa.y;
+    const float factor = 1.0f / (dist * dist);
+    float sin_p, cos_p;
+    sincosf(phase, &sin_p, &cos_p);
+    const float dc = vc.dc_offset;
+    // phA = dR+dq1-dq2, phB = dI+dq3-dq4, phC = dA, phS = dq1+dq2+dq3+dq4 (summed in blend_bwd)
+    const float dphase_sum = cos_p * phB - sin_p * phA;                // backward.cu:551-559
+    const float damp_sum = cos_p * phA + sin_p * phB + phC + dc * phS;  // backward.cu:562-566
+    gpa[0] = vc.use_view_dependent_phase ? dphase_sum * amplitude * factor : 0.f;
+    gpa[1] = damp_sum * factor;
+    // the amplitude clamp masks its SH gradient only (backward.cu:158-160)
+    gpa[1] *= (__ldg(p.clamped + v * P + idx) & 0x1000000u) ? 0.f : 1.f;
+    if (with_mean) {
+      part_phase += dphase_sum * amplitude * factor;
+      part_dc += phS * amplitude * factor;                                // backward.cu:567
+      const float* __restrict__ V = vc.viewmatrix;
+      const float m_view_x = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+      const float m_view_y = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+      const float m_view_z = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+      const float coeff = dphase_sum * vc.dist2phase * amplitude * factor / dist -
                           damp_sum * 2.0f * amplitude * factor * factor;  // backward.cu:570-577
       const float dxv = m_view_x * coeff, dyv = m_view_y * coeff, dzv = m_view_z * coeff;
       dmx += dxv * V[0] + dyv * V[1] + dzv * V[2];
       dmy += dxv * V[4] + dyv * V[5] + dzv * V[6];
       dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
-
-      // computePhasorFromSH backward.  The reference reads its 2-float local gradient array with
-      // the Gaussian index (backward.cu:154,586; DESIGN.md defect D1); the evident intent — the
-      // array's own two entries — is what is implemented.  No special case for the removed phase
-      // DC term.
-      gpa[1] *= (clamp_bits & 0x1000000u) ? 0.f : 1.f;
-      V3 dL_ddir;
-      if (staged) {
-        float* row = wbuf + lane * 33;
-        dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, row, gpa, row);
-      } else if (!ACC) {
-        dL_ddir = sh_backward<2>(p.D, p.M_p, dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2,
-                                 gpa, p.dL_dsh_p + (size_t)idx * p.M_p * 2);
-      } else {
-        float tmp[32];
-        dL_ddir = sh_backward<2>(p.D, min(p.M_p, 16), dirx, diry, dirz, p.shs_p + (size_t)idx * p.M_p * 2, gpa, tmp);
-        const int ncf = 2 * (p.D + 1) * (p.D + 1);
-        for (int k = 0; k < ncf; ++k) acc_store<ACC>(p.dL_dsh_p + (size_t)idx * p.M_p * 2 + k, tmp[k]);
-      }
-      const V3 dm = dnormvdv3(dir_orig, dL_ddir);
-      dmx += dm.x; dmy += dm.y; dmz += dm.z;
-    } else if (in_range) {
-      if (staged) {
-        if (any_vis) for (int k = 0; k < 32; ++k) wbuf[lane * 33 + k] = 0.f;
-      } else if (!ACC) {
-        for (int k = 0; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * 2 * p.M_p + k] = 0.f;
-      }
     }
+  };
+  if (p.shs_p != nullptr) {
+    // computePhasorFromSH backward.  The reference reads its 2-float local gradient array with
+    // the Gaussian index (backward.cu:154,586; DESIGN.md defect D1); the evident intent — the
+    // array's own two entries — is what is implemented.  No special case for the removed phase
+    // DC term.
+    const bool staged = p.M_p == 16;
     if (staged) {
       if (any_vis) {
+        warp_stage_in<32>(p.shs_p + (size_t)wfirst * 32, nrows, wbuf, lane);
+        __syncwarp();
+        float* row = wbuf + lane * 33;
+        if (vis) {
+          for (int v = 0; v < p.nviews; ++v) {
+            if (!((vis_mask >> v) & 1u)) continue;
+            float gpa[2]; V3 raw; float nx, ny, nz;
+            phasor_seeds(v, p.views[v], gpa, true);
+            view_dir(p.views[v], raw, nx, ny, nz);
+            const V3 dm = dnormvdv3(raw, sh_dir_grad<2>(p.D, nx, ny, nz, row, gpa));
+            dmx += dm.x; dmy += dm.y; dmz += dm.z;
+          }
+          bool first = true;
+          for (int v = 0; v < p.nviews; ++v) {
+            if (!((vis_mask >> v) & 1u)) continue;
+            float gpa[2]; V3 raw; float nx, ny, nz;
+            phasor_seeds(v, p.views[v], gpa, false);
+            view_dir(p.views[v], raw, nx, ny, nz);
+            if (first) sh_coef_grad<2, true>(p.D, 16, nx, ny, nz, gpa, row);
+            else sh_coef_grad<2, false>(p.D, 16, nx, ny, nz, gpa, row);
+            first = false;
+          }
+        } else if (in_range) {
+          for (int k = 0; k < 32; ++k) row[k] = 0.f;
+        }
         __syncwarp();
         warp_stage_out<32, ACC>(p.dL_dsh_p + (size_t)wfirst * 32, nrows, wbuf, lane);
         __syncwarp();
       } else if (!ACC) {
         for (int e = (int)lane; e < nrows * 32; e += 32) p.dL_dsh_p[(size_t)wfirst * 32 + e] = 0.f;
       }
+    } else if (in_range) {
+      float tmp[32];
+      const int Mc = min(p.M_p, 16);
+      for (int k = 0; k < 2 * Mc; ++k) tmp[k] = 0.f;
+      if (vis) {
+        const float* sp = p.shs_p + (size_t)idx * p.M_p * 2;
+        bool first = true;
+        for (int v = 0; v < p.nviews; ++v) {
+          if (!((vis_mask >> v) & 1u)) continue;
+          float gpa[2]; V3 raw; float nx, ny, nz;
+          phasor_seeds(v, p.views[v], gpa, true);
+          view_dir(p.views[v], raw, nx, ny, nz);
+          const V3 dm = dnormvdv3(raw, sh_dir_grad<2>(p.D, nx, ny, nz, sp, gpa));
+          dmx += dm.x; dmy += dm.y; dmz += dm.z;
+          if (first) sh_coef_grad<2, true>(p.D, Mc, nx, ny, nz, gpa, tmp);
+          else sh_coef_grad<2, false>(p.D, Mc, nx, ny, nz, gpa, tmp);
+          first = false;
+        }
+      }
+      if (!ACC || vis) {
+        for (int k = 0; k < 2 * Mc; ++k) acc_store<ACC>(p.dL_dsh_p + (size_t)idx * p.M_p * 2 + k, tmp[k]);
+        if (!ACC) for (int k = 2 * Mc; k < 2 * p.M_p; ++k) p.dL_dsh_p[(size_t)idx * p.M_p * 2 + k] = 0.f;
+      }
     }
   }
 
+  // ---------------- 3.-5. geometry per view ----------------------------------------------------
+  float dopac = 0.f;
+  float dcol_sum[3] = {0.f, 0.f, 0.f};
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
   if (vis) {
-    const float4 co = __ldg(reinterpret_cast<const float4*>(p.rec + (size_t)idx * GFT_REC_FLOATS) + 1);
+    const float* c3 = p.cov3D + 6 * (size_t)idx;
+    v0 = __ldg(c3 + 0); v1 = __ldg(c3 + 1); v2 = __ldg(c3 + 2);
+    v3 = __ldg(c3 + 3); v4 = __ldg(c3 + 4); v5 = __ldg(c3 + 5);
+  }
+  for (int v = 0; v < p.nviews; ++v) {
+    const ViewCam& vc = p.views[v];
+    if (!in_range) continue;
+    if (!((vis_mask >> v) & 1u)) {
+      // culled in this view: its per-view outputs are zero (the reference leaves its zero-filled
+      // tensors untouched)
+      vc.dL_dmeans2D[3 * (size_t)idx + 0] = 0.f;
+      vc.dL_dmeans2D[3 * (size_t)idx + 1] = 0.f;
+      vc.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+      if (v == 0) {
+        if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dL_ddist) p.dL_ddist[idx] = 0.f;
+        if (p.dL_dndc) p.dL_dndc[idx] = 0.f;
+      }
+      continue;
+    }
+    const float* __restrict__ V = vc.viewmatrix;
+    const float* __restrict__ proj = vc.projmatrix;
+    const float4 a0 = grad_rec4(v, 0), a1 = grad_rec4(v, 1), a2 = grad_rec4(v, 2);
+    const float4 co = __ldg(reinterpret_cast<const float4*>(p.rec + (v * P + idx) * GFT_REC_FLOATS) + 1);
+    const float dist = __ldg(p.rec + (v * P + idx) * GFT_REC_FLOATS + 11);
+    const float m_view_x = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+    const float m_view_y = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+    const float m_view_z = V[2] * mx + V[6] * my + V[10] * mz + V[14];
     // backward.cu:872-883 with the per-Gaussian conic factors pulled out of the pixel sums
-    const float dm2x = -(co.x * a0.x + co.y * a0.y) * (0.5f * (float)p.W);
-    const float dm2y = -(co.z * a0.y + co.y * a0.x) * (0.5f * (float)p.H);
+    const float dm2x = -(co.x * a0.x + co.y * a0.y) * (0.5f * (float)vc.W);
+    const float dm2y = -(co.z * a0.y + co.y * a0.x) * (0.5f * (float)vc.H);
     const float dcon_x = -0.5f * a0.z, dcon_y = -0.5f * a0.w, dcon_w = -0.5f * a1.x;
-    const float dopac = a1.y;
+    dopac += a1.y;
+    dcol_sum[0] += a1.z; dcol_sum[1] += a1.w; dcol_sum[2] += a2.x;
     const float ddist_rec = a2.y, dndc_rec = a2.z;
 
-    // pass-through outputs
-    p.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
-    p.dL_dmeans2D[3 * (size_t)idx + 1] = dm2y;
-    p.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    acc_store<ACC>(p.dL_dopacity + idx, dopac);
-    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol[k];
-    if (p.dL_dconic) {
-      reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+    vc.dL_dmeans2D[3 * (size_t)idx + 0] = dm2x;
+    vc.dL_dmeans2D[3 * (size_t)idx + 1] = dm2y;
+    vc.dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+    if (v == 0) {
+      if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+      if (p.dL_ddist) p.dL_ddist[idx] = ddist_rec;
+      if (p.dL_dndc) p.dL_dndc[idx] = dndc_rec;
     }
-    if (p.dL_ddist) p.dL_ddist[idx] = ddist_rec;
-    if (p.dL_dndc) p.dL_dndc[idx] = dndc_rec;
 
     // ---------------- 3. depth / ndc -> mean (backward.cu:589-601) ---------------------------
     {
-      const float dndc_ddist = (p.far_n * p.near_n) / ((p.far_n - p.near_n) * dist * dist);
+      const float dndc_ddist = (vc.far_n * vc.near_n) / ((vc.far_n - vc.near_n) * dist * dist);
       const float dL_ddist = dndc_rec * dndc_ddist + ddist_rec;
       const float dxv = dL_ddist * m_view_x / dist;
       const float dyv = dL_ddist * m_view_y / dist;
@@ -373,19 +448,16 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dmz += dxv * V[8] + dyv * V[9] + dzv * V[10];
     }
 
-    // ---------------- cov2D backward (4., backward.cu:276-394) ------------------------------
-    const float* c3 = p.cov3D + 6 * (size_t)idx;
-    const float v0 = __ldg(c3 + 0), v1 = __ldg(c3 + 1), v2 = __ldg(c3 + 2), v3 = __ldg(c3 + 3),
-                v4 = __ldg(c3 + 4), v5 = __ldg(c3 + 5);
+    // ---------------- 4. cov2D backward (backward.cu:276-394) --------------------------------
     float tx = m_view_x, ty = m_view_y;
     const float tz = m_view_z;
-    const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+    const float limx = 1.3f * vc.tan_fovx, limy = 1.3f * vc.tan_fovy;
     const float txtz = tx / tz, tytz = ty / tz;
     tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
     ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
     const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
     const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-    const float h_x = p.focal_x, h_y = p.focal_y;
+    const float h_x = vc.focal_x, h_y = vc.focal_y;
     const float J00 = h_x / tz, J02 = -(h_x * tx) / (tz * tz);
     const float J11 = h_y / tz, J12 = -(h_y * ty) / (tz * tz);
     // T = W * J in glm indexing (T[c][r]): T0r = W[0][r]*J00 + W[2][r]*J02 with W[c][r] = V[4r + c]
@@ -409,19 +481,17 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     const float denom = a * c - b * b;
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (denom2inv != 0) {
       dL_da = denom2inv * (-c * c * dcon_x + 2 * b * c * dcon_y + (denom - a * c) * dcon_w);
       dL_dc = denom2inv * (-a * a * dcon_w + 2 * a * b * dcon_y + (denom - a * c) * dcon_x);
       dL_db = denom2inv * 2 * (b * c * dcon_x - (denom + 2 * b * b) * dcon_y + a * b * dcon_w);
-      dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
-      dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
-      dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
-      dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
-      dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
-      dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+      dcov[0] += (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+      dcov[3] += (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+      dcov[5] += (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+      dcov[1] += 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+      dcov[2] += 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+      dcov[4] += 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
     }
-    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
 
     // dL/dT (backward.cu:358-369): B0* = T[0]-row products with Vrk, B1* likewise
     const float dL_dT00 = 2 * B00 * dL_da + B10 * dL_db;
@@ -447,7 +517,7 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
     dmy += V[4] * dL_dtx + V[5] * dL_dty + V[6] * dL_dtz;
     dmz += V[8] * dL_dtx + V[9] * dL_dty + V[10] * dL_dtz;
 
-    // ---------------- mean2D -> mean3D (backward.cu:498-519) ---------------------------------
+    // ---------------- 5. mean2D -> mean3D (backward.cu:498-519) ------------------------------
     {
       const float m_hom_w = proj[3] * mx + proj[7] * my + proj[11] * mz + proj[15];
       const float m_w = 1.0f / (m_hom_w + 0.0000001f);
@@ -457,12 +527,18 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
       dmy += (proj[4] * m_w - proj[7] * mul1) * dm2x + (proj[5] * m_w - proj[7] * mul2) * dm2y;
       dmz += (proj[8] * m_w - proj[11] * mul1) * dm2x + (proj[9] * m_w - proj[11] * mul2) * dm2y;
     }
+  }
 
+  // ---------------- the summed parameter gradients: one row each -------------------------------
+  if (vis) {
+    acc_store<ACC>(p.dL_dopacity + idx, dopac);
     acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 0, dmx);
     acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 1, dmy);
     acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 2, dmz);
+    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol_sum[k];
+    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
 
-    // ---------------- cov3D -> scale, rotation (backward.cu:399-462) -------------------------
+    // ---------------- 6. cov3D -> scale, rotation (backward.cu:399-462) ----------------------
     if (p.scales != nullptr) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
@@ -517,6 +593,18 @@ preprocess_bwd_kernel(PreprocessBwdParams p) {
         *dq_out = dq;
       }
     }
+  } else if (in_range) {
+    // culled in every view: zero rows (nothing to add in the accumulate modes)
+    if (!ACC) {
+      p.dL_dopacity[idx] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 0] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 1] = 0.f;
+      p.dL_dmeans3D[3 * (size_t)idx + 2] = 0.f;
+      if (p.dL_dscales) for (int k = 0; k < 3; ++k) p.dL_dscales[3 * (size_t)idx + k] = 0.f;
+      if (p.dL_drotations) for (int k = 0; k < 4; ++k) p.dL_drotations[4 * (size_t)idx + k] = 0.f;
+    }
+    if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = 0.f;
+    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
   }
 
   // ---- the two scalar gradients: block reduction, one atomic per block ----------------------
@@ -543,16 +631,19 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
-  static unsigned long long smem_ok0 = 0, smem_ok1 = 0, smem_ok2 = 0;
-  if (p.accumulate == 2) {          // atomic adds: several views may target the same bucket at once
-    ensure_dynamic_smem(preprocess_bwd_kernel<2>, smem, &smem_ok2);
-    preprocess_bwd_kernel<2><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  // MINB = 4 (64 registers, a few spilled words) or 3 (80 registers, no spills): option pbwd_minb
+  const bool four = option(OPT_PBWD_MINB) != 3;
+  auto go = [&](auto kernel, unsigned long long* ok) {
+    ensure_dynamic_smem(kernel, smem, ok);
+    kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  };
+  static unsigned long long ok[6] = {0, 0, 0, 0, 0, 0};
+  if (p.accumulate == 2) {          // atomic adds: several calls may target the same bucket at once
+    if (four) go(preprocess_bwd_kernel<2, 4>, &ok[0]); else go(preprocess_bwd_kernel<2, 3>, &ok[1]);
   } else if (p.accumulate) {
-    ensure_dynamic_smem(preprocess_bwd_kernel<1>, smem, &smem_ok1);
-    preprocess_bwd_kernel<1><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+    if (four) go(preprocess_bwd_kernel<1, 4>, &ok[2]); else go(preprocess_bwd_kernel<1, 3>, &ok[3]);
   } else {
-    ensure_dynamic_smem(preprocess_bwd_kernel<0>, smem, &smem_ok0);
-    preprocess_bwd_kernel<0><<<blocks, GFT_BLOCK, smem, stream>>>(p);
+    if (four) go(preprocess_bwd_kernel<0, 4>, &ok[4]); else go(preprocess_bwd_kernel<0, 3>, &ok[5]);
   }
   note_launches(1);
 }

@@ -307,6 +307,8 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
                    cudaStream_t stream, const uint32_t* d_R) {
   if (R <= 0) return 0;
   if (end_bit > 64 || end_bit <= 0) return -1;
+  // the look-back status words carry a 30-bit count next to the two flag bits
+  if ((unsigned)R > VAL_MASK) return -4;
   if (temp_bytes < own_sort_temp_bytes(R)) return -2;
   uint64_t* keys_a = const_cast<uint64_t*>(keys_a_c);
   uint32_t* vals_a = const_cast<uint32_t*>(vals_a_c);
@@ -322,7 +324,7 @@ int own_sort_pairs(void* d_temp, size_t temp_bytes, const uint64_t* keys_a_c, ui
   cudaMemsetAsync(d_temp, 0, head + (size_t)npass * per_pass * 4, stream);
 
   int hblocks = (R + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
-  hblocks = max(1, min(hblocks, 148 * 8));
+  hblocks = max(1, min(hblocks, sm_count() * 8));
   rs_histogram_kernel<<<hblocks, RS_THREADS, 0, stream>>>(keys_a, R, d_R, npass, end_bit, hist);
   rs_scan_bins_kernel<<<npass, RS_BINS, 0, stream>>>(hist);
   note_launches(2 + npass);

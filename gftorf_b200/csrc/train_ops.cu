@@ -333,7 +333,7 @@ int gft_adam_step(const GftAdamArgs* a, gft_stream_t stream_) {
   k.bc2_sqrt = (float)std::sqrt(bc2);
   k.eps = a->eps;
   long long blocks = (longest / 4 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > gft::sm_count() * 16) blocks = gft::sm_count() * 16;
   if (blocks < 1) blocks = 1;
   for (int s = 0; s < a->n_segments; ++s) k.neg_step[s] = (float)(-(a->seg[s].lr / bc1));
   gft::adam_kernel<<<(int)blocks, 256, 0, stream>>>(*a, k);

@@ -15,6 +15,7 @@ stream.  PyTorch is plumbing only: memory, streams, autograd bookkeeping.
 """
 from typing import NamedTuple, Optional
 import ctypes as C
+import os
 import threading
 
 import torch
@@ -145,13 +146,16 @@ def _native_forward(bg, means3D, colors_precomp, phasors_precomp, opacities, sca
                     scale_modifier, cov3Ds_precomp, viewmatrix, projmatrix, tanfovx, tanfovy,
                     image_height, image_width, sh, sh_p, degree, campos, prefiltered, debug,
                     near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset,
-                    R_hint=0):
+                    R_hint=0, separate_outputs=False):
     """Same argument order and 15-tuple result as `_C.rasterize_gaussians`
     (rasterize_points.cu:35-165).
 
     `R_hint` (not in the reference): an estimate of num_rendered; > 0 selects the library's hinted
     mode (GftForwardArgs.R_hint) in which the host does not wait for the instance count in the
-    middle of the forward.  Results are identical."""
+    middle of the forward.  Results are identical.
+    `separate_outputs`: every image output in its own allocation (the public autograd surface —
+    outputs of one autograd node that are views of one tensor cannot be modified in place, and
+    holding one would pin all 21 planes); default: one allocation for all 21 planes."""
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -163,11 +167,16 @@ def _native_forward(bg, means3D, colors_precomp, phasors_precomp, opacities, sca
     f32 = dict(dtype=torch.float32, device=dev)
 
     # one allocation for all 21 image planes; every element is written by the kernels
-    planes = torch.empty((21, H, W), **f32)
-    color, phasor = planes[0:3], planes[3:10]
-    depth, normal, acc = planes[10:11], planes[11:14], planes[14:15]
-    entropy, depth_distortion, amp_distortion = planes[15:16], planes[16:17], planes[17:18]
-    distribution = planes[18:21]
+    if separate_outputs:
+        planes = torch.empty((1,), **f32)
+        (color, phasor, depth, normal, acc, entropy, depth_distortion, amp_distortion,
+         distribution) = (torch.empty((c, H, W), **f32) for c in (3, 7, 1, 3, 1, 1, 1, 1, 3))
+    else:
+        planes = torch.empty((21, H, W), **f32)
+        color, phasor = planes[0:3], planes[3:10]
+        depth, normal, acc = planes[10:11], planes[11:14], planes[14:15]
+        entropy, depth_distortion, amp_distortion = planes[15:16], planes[16:17], planes[17:18]
+        distribution = planes[18:21]
     if P == 0:
         pixels = torch.zeros((P, 1), **f32)
         radii = torch.zeros((P,), dtype=torch.int32, device=dev)
@@ -224,7 +233,7 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
                      grad_out_acc, grad_entropy, grad_depth_distortion, grad_amp_distortion,
                      sh, sh_p, degree, campos, geomBuffer, R, binningBuffer, imgBuffer, debug,
                      near_n, far_n, depth_range, use_view_dependent_phase, phase_offset, dc_offset,
-                     grad_out=None, accumulate=True):
+                     grad_out=None, accumulate=True, separate_means2D=False):
     """Same argument order and 12-tuple result as `_C.rasterize_gaussians_backward`
     (rasterize_points.cu:167-281).  grad_out_normal / grad_entropy / grad_amp_distortion are
     accepted and ignored, as in the reference (backward.cu never reads them).
@@ -273,6 +282,10 @@ def _native_backward(bg, means3D, radii, colors_precomp, phasors_precomp, scales
         scratch_off = cur
         flat = torch.empty(cur + scratch_floats, **f32)
     dL_dmeans3D, dL_dmeans2D = view("means3D", P, 3) if grad_out is None else None, view("means2D", P, 3)
+    if separate_means2D:
+        # viewspace_points.grad outlives the call (densification statistics): its own allocation, so
+        # it does not pin the other gradients and the scratch records
+        dL_dmeans2D = torch.empty((P, 3), **f32)
     dL_dcolors = view("colors", P, 3)
     # grad_phasors_precomp ([P,7] for a [P,2] input in the reference) is not produced
     dL_dphasors = None
@@ -377,9 +390,11 @@ _C = _NativeModule
 _R_HISTORY = {}
 
 
+_NO_HINT = os.environ.get("GFT_NO_HINT") == "1"      # read once: the forward is launch-bound on small scenes
+
+
 def _r_hint(key):
-    import os
-    if os.environ.get("GFT_NO_HINT") == "1":
+    if _NO_HINT:
         return 0
     last = _R_HISTORY.get(key)
     return 0 if last is None else int(last * 1.25) + 4096
@@ -417,7 +432,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         )
         hint_key = (means3D.device.index, int(means3D.shape[0]), int(raster_settings.image_height),
                     int(raster_settings.image_width))
-        kw = {"R_hint": _r_hint(hint_key)} if _C is _NativeModule else {}
+        kw = {"R_hint": _r_hint(hint_key), "separate_outputs": True} if _C is _NativeModule else {}
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy them before they can be corrupted
             try:
@@ -470,7 +485,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            out = _C.rasterize_gaussians_backward(*args)
+            out = _C.rasterize_gaussians_backward(*args, **({"separate_means2D": True} if _C is _NativeModule else {}))
         (grad_means2D, grad_colors_precomp, grad_phasors_precomp, grad_opacities, grad_means3D,
          grad_cov3Ds_precomp, grad_sh, grad_sh_p, grad_scales, grad_rotations, grad_phase_offset,
          grad_dc_offset) = out

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GFT_ABI_VERSION 1
+#define GFT_ABI_VERSION 2
 
 /* Channel counts, rasterizer/cuda_rasterizer/config.h:15-23 */
 #define GFT_NUM_CHANNELS 3         /* RGB */
@@ -106,7 +106,7 @@ typedef struct GftForwardArgs {
 
 /* Returns num_rendered R (>=0), or <0 on error.  The three callbacks are called exactly once
  * each (geom, img before the first kernel; binning after the tile-count scan — a second time
- * only when R_hint was too small). */
+ * only when R_hint was too small).  A batch of one view: see gft_forward_views. */
 int gft_forward(const GftForwardArgs* args,
                 gft_alloc_fn geom_alloc, gft_alloc_fn binning_alloc, gft_alloc_fn img_alloc,
                 void* alloc_ctx, gft_stream_t stream);
@@ -116,6 +116,8 @@ int gft_forward(const GftForwardArgs* args,
 size_t gft_geom_bytes(int P);
 size_t gft_img_bytes(int width, int height);
 size_t gft_binning_bytes(int R);
+size_t gft_geom_bytes_views(int P, int n_views);
+size_t gft_img_bytes_views(int n_views, const int* widths, const int* heights);
 
 /* ------------------------------------------------------------------------------------------
  * Backward.  Replaces RasterizeGaussiansBackwardCUDA (rasterize_points.cu:167-281) +
@@ -198,6 +200,110 @@ size_t gft_backward_scratch_bytes(int P);
 int gft_backward(const GftBackwardArgs* args, gft_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched views.  One call rasterizes the SAME Gaussians for up to GFT_MAX_VIEWS cameras — the
+ * colour and the ToF camera of a training iteration (gaussian_renderer/__init__.py:107-128 makes
+ * two rasterizer calls back to back), the cameras of a multi-view batch, the frames of a
+ * render-only sweep (render.py:95-209).  Every kernel covers all views in one launch, the
+ * 364 B/Gaussian of parameters are read once per pass instead of once per view, and the backward
+ * writes each parameter-gradient row once: the SUM over the views of the batch (what autograd's
+ * AccumulateGrad produces for the reference's separate calls, train.py:279).  Per view the
+ * results are exactly those of gft_forward / gft_backward, which are batches of one.
+ * ---------------------------------------------------------------------------------------- */
+#define GFT_MAX_VIEWS 16
+
+typedef struct GftViewArgs {
+  int width, height;
+  const float* background;      /* see GftForwardArgs.background */
+  int bg_mode;
+  const float* viewmatrix;      /* 16 floats on device, column-major */
+  const float* projmatrix;      /* 16 floats on device, full view*proj */
+  const float* campos;          /* 3 floats on device */
+  float tan_fovx, tan_fovy;
+  float near_n, far_n, depth_range;
+  int use_view_dependent_phase;
+  float phase_offset, dc_offset;
+  /* forward outputs of this view (as in GftForwardArgs) */
+  float* out_color;
+  float* out_phasor;
+  float* out_depth;
+  float* out_normal;            /* may be NULL */
+  float* out_acc;
+  float* out_entropy;           /* may be NULL */
+  float* out_depth_distortion;
+  float* out_amp_distortion;    /* may be NULL */
+  float* pixels;                /* [P] */
+  float* out_distribution;
+  int* radii;                   /* [P]; written by the forward, read by the backward */
+  /* backward: incoming pixel gradients of this view and its screen-space gradient output */
+  const float* dL_dout_color;
+  const float* dL_dout_phasor;
+  const float* dL_dout_depth;
+  const float* dL_dout_acc;
+  const float* dL_dout_depth_distortion;
+  float* dL_dmeans2D;           /* [P,3] (z = 0), per view: its norm feeds densification */
+} GftViewArgs;
+
+typedef struct GftForwardViewsArgs {
+  int P, sh_degree, M, M_p, n_views;
+  const float* means3D;
+  const float* shs;
+  const float* shs_p;
+  const float* colors_precomp;
+  const float* phasors_precomp;
+  const float* opacities;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  int prefiltered;
+  int debug;
+  const GftViewArgs* views;     /* host array of n_views entries */
+  int R_hint;                   /* as GftForwardArgs.R_hint, for the instance count of the whole batch */
+} GftForwardViewsArgs;
+
+/* Returns the number of (Gaussian, tile) instances of the whole batch, or <0 on error. */
+int gft_forward_views(const GftForwardViewsArgs* args,
+                      gft_alloc_fn geom_alloc, gft_alloc_fn binning_alloc, gft_alloc_fn img_alloc,
+                      void* alloc_ctx, gft_stream_t stream);
+
+typedef struct GftBackwardViewsArgs {
+  int P, sh_degree, M, M_p, R, n_views;
+  const float* means3D;
+  const float* shs;
+  const float* shs_p;
+  const float* colors_precomp;
+  const float* phasors_precomp;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const char* geom_buffer;      /* the three workspaces handed out by gft_forward_views */
+  const char* binning_buffer;
+  const char* img_buffer;
+  const GftViewArgs* views;     /* the same views, in the same order, with the dL_* fields set */
+  /* parameter gradients, summed over the views (see GftBackwardArgs for shapes and `accumulate`) */
+  float* dL_dopacity;
+  float* dL_dmeans3D;
+  float* dL_dsh;
+  float* dL_dsh_p;
+  float* dL_dscales;
+  float* dL_drotations;
+  float* dL_dphase_offset;
+  float* dL_ddc_offset;
+  float* dL_dcolors;            /* optional */
+  float* dL_dcov3D;             /* optional */
+  float* dL_dconic;             /* optional, view 0 only */
+  float* dL_ddist;              /* optional, view 0 only */
+  float* dL_dndc;               /* optional, view 0 only */
+  float* scratch;               /* >= gft_backward_scratch_bytes_views(P, n_views) bytes */
+  int debug;
+  int accumulate;
+} GftBackwardViewsArgs;
+
+size_t gft_backward_scratch_bytes_views(int P, int n_views);
+int gft_backward_views(const GftBackwardViewsArgs* args, gft_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * markVisible (rasterize_points.cu:283-304, rasterizer_impl.cu:54-68,143-159).
  * present[i] = near <= view_z(i) <= far   (x/y are NOT tested: auxiliary.h:169)
  * ---------------------------------------------------------------------------------------- */
@@ -218,28 +324,32 @@ int gft_dist2(const float* points, int P, float* out, char* workspace, gft_strea
  * the reference's.
  * ---------------------------------------------------------------------------------------- */
 typedef struct GftWorkspaceLayout {
-  /* geometry workspace (per Gaussian) */
-  size_t geom_rec;            /* float[P][20]: x y ex ey | conA conB conC opac | r g b dist | ph0..ph3 | ph4 ph5 ph6 ndc */
-  size_t geom_depths;         /* float[P]  view-space z */
-  size_t geom_tiles_touched;  /* uint32[P] */
-  size_t geom_point_offsets;  /* uint32[P] inclusive prefix sum of tiles_touched */
-  size_t geom_rect;           /* uint16[P][4]: xmin ymin xmax ymax (tile units) */
+  /* geometry workspace: cov3D is per Gaussian; the other arrays are view-major, [n_views][P][...]
+   * (the slice of view v starts v * P * element_size bytes after the offset below) */
   size_t geom_cov3D;          /* float[P][6] */
-  size_t geom_clamped;        /* uint8[P][4]: r g b amp */
-  size_t geom_pa;             /* float[P][2]: phase_sh, amplitude */
+  size_t geom_rec;            /* float[V][P][20]: x y ex ey | conA conB conC opac | r g b dist | ph0..ph3 | ph4 ph5 ph6 ndc */
+  size_t geom_depths;         /* float[V][P]  view-space z */
+  size_t geom_tiles_touched;  /* uint32[V][P] */
+  size_t geom_rect;           /* uint16[V][P][4]: xmin ymin xmax ymax (tile units) */
+  size_t geom_clamped;        /* uint8[V][P][4]: r g b amp */
+  size_t geom_pa;             /* float[V][P][2]: phase_sh, amplitude */
   size_t geom_total;
   /* binning workspace (per instance) */
-  size_t bin_keys;            /* uint64[R] sorted keys  (tile << 32 | depth bits) */
-  size_t bin_keys_unsorted;   /* uint64[R] */
   size_t bin_point_list;      /* uint32[R] sorted Gaussian ids */
-  size_t bin_point_list_unsorted; /* uint32[R] */
+  size_t bin_entries;         /* uint64[R] sorted entries: float_bits(view_z) << 32 | Gaussian id; the
+                                 reference's key is (tile << 32) | float_bits(view_z) with the tile
+                                 given by the range the entry lies in */
   size_t bin_total;
-  /* image workspace */
-  size_t img_state;           /* float4[N]: final_T, w_z_total, w_z2_total, bits(n_contrib) */
-  size_t img_ranges;          /* uint2[T] */
+  /* image workspace: tiles and pixels of the views back to back */
+  size_t img_hdr;             /* uint32[4]: word 1 = num_rendered */
+  size_t img_tile_counts;     /* uint32[T_total] instances per tile */
+  size_t img_ranges;          /* uint2[T_total] */
+  size_t img_state;           /* float4[N_total]: final_T, w_z_total, w_z2_total, bits(n_contrib) */
   size_t img_total;
 } GftWorkspaceLayout;
 
+void gft_workspace_layout_views(int P, int R, int n_views, const int* widths, const int* heights,
+                                GftWorkspaceLayout* out);
 void gft_workspace_layout(int P, int R, int width, int height, GftWorkspaceLayout* out);
 
 /* ------------------------------------------------------------------------------------------
@@ -252,6 +362,11 @@ void gft_workspace_layout(int P, int R, int width, int height, GftWorkspaceLayou
 void gft_profile_enable(int on);
 int gft_profile_read(float* ms, const char** names, int cap);
 unsigned long long gft_launch_count(void);
+
+/* Tunables / A-B switches of the kernels ("sort_cap", "bwd_pred", "pbwd_minb", "no_cull"; defaults
+ * come from the environment variables GFT_SORT_CAP, ... read once).  Returns the previous value,
+ * <0 for an unknown name.  Results never depend on them, only speed. */
+int gft_set_option(const char* name, int value);
 
 const char* gft_last_error(void);
 int gft_abi_version(void);

@@ -30,14 +30,16 @@ def test_library_loads_and_exports_every_symbol():
     lib = C.CDLL(_capi.LIB_PATH)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert _capi.lib().gft_abi_version() == 1
+    assert _capi.lib().gft_abi_version() == _capi.ABI_VERSION
 
 
 def test_size_queries_do_not_need_a_gpu():
     lib = _capi.lib()
-    assert lib.gft_geom_bytes(1000) >= 1000 * (80 + 4 + 4 + 4 + 8 + 24 + 4 + 8)
+    assert lib.gft_geom_bytes(1000) >= 1000 * (80 + 4 + 4 + 8 + 24 + 4 + 8)
     assert lib.gft_img_bytes(640, 480) >= 640 * 480 * 16 + 1200 * 8
-    assert lib.gft_binning_bytes(100000) >= 100000 * 24
+    assert lib.gft_binning_bytes(100000) >= 100000 * 12
+    assert lib.gft_geom_bytes_views(1000, 2) >= 1000 * (24 + 2 * (80 + 4 + 4 + 8 + 4 + 8))
+    assert lib.gft_backward_scratch_bytes_views(1000, 2) >= 2 * 1000 * 64
     assert lib.gft_backward_scratch_bytes(1000) >= 1000 * 64
     assert lib.gft_dist2_workspace_bytes(1000) > 0
     lay = _capi.GftWorkspaceLayout()
@@ -52,6 +54,9 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
         "GftForwardArgs": [f[0] for f in _capi.GftForwardArgs._fields_],
         "GftBackwardArgs": [f[0] for f in _capi.GftBackwardArgs._fields_],
         "GftWorkspaceLayout": [f[0] for f in _capi.GftWorkspaceLayout._fields_],
+        "GftViewArgs": [f[0] for f in _capi.GftViewArgs._fields_],
+        "GftForwardViewsArgs": [f[0] for f in _capi.GftForwardViewsArgs._fields_],
+        "GftBackwardViewsArgs": [f[0] for f in _capi.GftBackwardViewsArgs._fields_],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gftorf.h"', "int main(void){"]
     for s, fs in fields.items():
@@ -65,7 +70,9 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
     for s, cls in (("GftForwardArgs", _capi.GftForwardArgs), ("GftBackwardArgs", _capi.GftBackwardArgs),
-                   ("GftWorkspaceLayout", _capi.GftWorkspaceLayout)):
+                   ("GftWorkspaceLayout", _capi.GftWorkspaceLayout), ("GftViewArgs", _capi.GftViewArgs),
+                   ("GftForwardViewsArgs", _capi.GftForwardViewsArgs),
+                   ("GftBackwardViewsArgs", _capi.GftBackwardViewsArgs)):
         assert int(out[s]) == C.sizeof(cls), s
         for f in fields[s]:
             assert int(out[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)

@@ -37,6 +37,11 @@ CASES = {
                    view_dependent_phase=True, phase_offset=0.3, dc_offset=0.1),
     "c3_tof": dict(P=500000, W=320, H=240, kind="trained", seed=4, depth_range=10.0,
                    bg_hw=(480, 640)),
+    # BASELINE configs[2], the colour view (TöRF real-shaped: 500k Gaussians, depth_range 10)
+    "c3_color": dict(P=500000, W=640, H=480, kind="trained", seed=4, depth_range=10.0),
+    # configs[1] at initialisation: uniform cloud, isotropic splats with a median radius of ~50 px
+    # (R/V ~ 25): thousands of instances per tile, the long-segment path of the tile sort
+    "c2_init": dict(P=300000, W=640, H=480, kind="init", seed=5),
 }
 
 
@@ -67,7 +72,7 @@ def test_forward_vs_reference_kernels(name):
 
 @needs_ref
 @pytest.mark.parametrize("name", ["tiny", "ragged", "small_orbit", "init_small", "deg0", "deg1", "deg2",
-                                  "c1", "c1_dense", "c2", "c2_vdp", "c3_tof"])
+                                  "c1", "c1_dense", "c2", "c2_vdp", "c3_tof", "c3_color", "c2_init"])
 def test_backward_vs_reference_kernels(name):
     # zero higher-order phase/amp SH keeps the reference's undefined dL_dPA out of
     # dL_dmeans3D; dL_dsh_p is compared on the one row the reference defines (Gaussian 0).
@@ -115,32 +120,83 @@ def test_sh_p_gradient_rows_by_rotating_each_gaussian_to_index_zero():
     assert checked >= 6
 
 
-@needs_oracle
-@pytest.mark.parametrize("spec", [
-    dict(P=3000, W=128, H=96, kind="trained", seed=11, pose="orbit", view_dependent_phase=True,
-         phase_offset=0.3, dc_offset=0.1),
-    dict(P=1500, W=96, H=80, kind="init", seed=12),
-])
-def test_full_gradients_vs_cpu_oracle(spec):
-    """Every gradient, including all rows of dL_dsh_p and dL_dmeans3D with non-zero SH_p, against
-    the CPU restatement (which is pinned to the reference on everything the reference defines)."""
-    inp = harness.build_inputs(device="cuda", **spec)
-    ours = harness.call_forward(rasterizer._C, inp)
-    ob = harness.call_backward(rasterizer._C, inp, ours)
+def _oracle_run(inp):
     cin = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
     cin["grads"] = {k: v.cpu() for k, v in inp["grads"].items()}
     cf = harness.call_forward(cpu_oracle.OracleModule, cin)
     cb = harness.call_backward(cpu_oracle.OracleModule, cin, cf)
+    return cf, cb
+
+
+def _assert_gradients_vs_oracle(ob, cb, tol):
+    scale = float(cb[8].double().norm())
+    for i, k in enumerate(harness.BWD_NAMES):
+        if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
+            continue
+        a, b = ob[i].cpu().double(), cb[i].double()
+        err = float((a - b).norm())
+        refn = float(b.norm())
+        assert err <= tol * max(refn, 1e-3 * scale), (k, err, refn)
+
+
+@needs_oracle
+@pytest.mark.parametrize("spec", [
+    dict(P=3000, W=128, H=96, kind="trained", pose="orbit", view_dependent_phase=True,
+         phase_offset=0.3, dc_offset=0.1),
+    dict(P=1500, W=96, H=80, kind="init"),
+])
+def test_full_gradients_vs_cpu_oracle(spec):
+    """Every gradient, including all rows of dL_dsh_p and dL_dmeans3D with non-zero SH_p, against
+    the CPU restatement (which is pinned to the reference on everything the reference defines).
+    libm's expf is not CUDA's, so a pair sitting exactly on the alpha >= 1/255 threshold can flip
+    between the two; such a scene is not skipped: the next seed is taken, and one of the first
+    four seeds must be flip-free."""
+    checked = 0
+    for seed in (11, 12, 13, 14):
+        inp = harness.build_inputs(device="cuda", seed=seed, **spec)
+        ours = harness.call_forward(rasterizer._C, inp)
+        ob = harness.call_backward(rasterizer._C, inp, ours)
+        cf, cb = _oracle_run(inp)
+        assert ours[0] == cf[0]
+        assert torch.equal(ours[11].cpu(), cf[11])
+        flips = harness.nmismatch(ours[9].cpu(), cf[9])
+        assert flips <= 2, flips
+        if flips:
+            continue
+        _assert_gradients_vs_oracle(ob, cb, harness.GRAD_REL_L2)
+        checked += 1
+        break
+    assert checked == 1
+
+
+@needs_oracle
+def test_c2_size_gradients_with_live_sh_p_vs_cpu_oracle():
+    """BASELINE configs[1] size (300k Gaussians, 640x480), ALL SH_p coefficients non-zero: the
+    reference's dL_dsh_p / the SH_p part of dL_dmeans3D are undefined there, so the
+    full-size check of those rows is against the CPU restatement — every gradient tensor as a
+    whole, and separately 4000 sampled rows so a localised error cannot hide in the norm.  A few
+    threshold flips (libm vs CUDA expf) are expected at this size; they perturb single pixels by
+    alpha ~ 1/255, which the loosened tolerance below covers — the comparison always runs."""
+    spec = dict(P=300000, W=640, H=480, kind="trained", seed=0, view_dependent_phase=True,
+                phase_offset=0.2, dc_offset=0.05)
+    inp = harness.build_inputs(device="cuda", **spec)
+    assert float(inp["shs_p"][:, 1:, :].abs().max()) > 0
+    ours = harness.call_forward(rasterizer._C, inp)
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    cf, cb = _oracle_run(inp)
     assert ours[0] == cf[0]
     assert torch.equal(ours[11].cpu(), cf[11])
-    if harness.nmismatch(ours[9].cpu(), cf[9]) == 0:  # no expf threshold flip on this scene
-        scale = float(cb[8].double().norm())
-        for i, k in enumerate(harness.BWD_NAMES):
-            if k in ("colors_precomp", "phasors_precomp", "cov3Ds_precomp"):
-                continue
-            err = float((ob[i].cpu().double() - cb[i].double()).norm())
-            refn = float(cb[i].double().norm())
-            assert err <= harness.GRAD_REL_L2 * max(refn, 1e-3 * scale), (k, err, refn)
+    flips = harness.nmismatch(ours[9].cpu(), cf[9])
+    assert flips <= 64, flips
+    tol = harness.GRAD_REL_L2 if flips == 0 else 5e-4
+    _assert_gradients_vs_oracle(ob, cb, tol)
+    vis = (cf[11] > 0).nonzero().flatten()
+    g = torch.Generator().manual_seed(1)
+    rows = vis[torch.randperm(vis.numel(), generator=g)[:4000]]
+    for i, k in ((7, "sh_p"), (4, "means3D"), (6, "sh")):
+        a, b = ob[i].cpu().double()[rows], cb[i].double()[rows]
+        assert float((a - b).norm()) <= tol * float(b.norm()), (k, flips)
+        assert float(b.norm()) > 0
 
 
 @pytest.mark.parametrize("name", golden_util.CASES)
@@ -246,12 +302,20 @@ def test_render_flow_path_precomputed_colours_no_phasor():
     rb = harness.call_backward(ref_driver.RefModule, inp, ref, colors_precomp=cp, use_shs_p=False)
     for t in ob:
         assert t is None or bool(torch.isfinite(t).all())
-    if not all(bool(torch.isfinite(t).all()) for t in rb):
+    if all(bool(torch.isfinite(t).all()) for t in rb):
+        for i in (0, 1, 3, 8, 9):  # means2D, colors_precomp, opacities, scales, rotations
+            assert harness.rel_l2(ob[i], rb[i]) <= harness.GRAD_REL_L2, harness.BWD_NAMES[i]
+    else:
         # the reference multiplied uninitialised (NaN/Inf) phasor features by the zero phasor
-        # gradient: its gradients are undefined on this run; ours are finite (checked above)
-        pytest.skip("reference blended non-finite uninitialised phasor features")
-    for i in (0, 1, 3, 8, 9):  # means2D, colors_precomp, opacities, scales, rotations
-        assert harness.rel_l2(ob[i], rb[i]) <= harness.GRAD_REL_L2, harness.BWD_NAMES[i]
+        # gradient: its gradients are undefined on this run.  Ours are finite (checked above) and
+        # are checked against the CPU restatement instead, which defines those features as 0 too.
+        cin = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+        cin["grads"] = {k: v.cpu() for k, v in inp["grads"].items()}
+        cf = harness.call_forward(cpu_oracle.OracleModule, cin, colors_precomp=cp.cpu(), use_shs_p=False)
+        cb = harness.call_backward(cpu_oracle.OracleModule, cin, cf, colors_precomp=cp.cpu(), use_shs_p=False)
+        tol = harness.GRAD_REL_L2 if harness.nmismatch(ours[9].cpu(), cf[9]) == 0 else 1e-3
+        for i in (0, 1, 3, 8, 9):
+            assert harness.rel_l2(ob[i].cpu(), cb[i]) <= tol, harness.BWD_NAMES[i]
 
 
 @needs_ref
@@ -304,23 +368,38 @@ def test_constant_background_is_not_materialised_and_matches():
     assert harness.rel_l2(ob[3], rb[3]) <= harness.GRAD_REL_L2
 
 
-def test_compact_sort_keys_are_the_reference_keys_rebased():
-    """The sort sees (tile << depth_bits) | (float_bits(z) - float_bits(near)); rebuilt in the
-    reference's format the keys must carry exactly the Gaussians' depth bits and tile ids."""
+def test_tile_segments_are_sorted_by_depth_then_index():
+    """The tile-segmented binning: every tile's slice of the sorted entries is ordered by
+    (float_bits(view_z), Gaussian index) — the order of the reference's stable radix sort of
+    (tile << 32 | depth) keys — carries exactly its Gaussians' depth bits, and `ranges` is the
+    exclusive scan of the per-tile instance counts with (0,0) for empty tiles."""
     inp = harness.build_inputs(device="cuda", **CASES["c1"])
     f = harness.call_forward(rasterizer._C, inp)
     d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
-    assert 1 <= d["key_depth_bits"] <= 28          # [znear, zfar] of the F-ToRF camera spans < 2^28 ulps
-    ck = d["keys_compact"]
-    assert bool((ck[1:] >= ck[:-1]).all())
+    k = d["keys"]
+    assert bool((k[1:] >= k[:-1]).all())
+    same = k[1:] == k[:-1]
+    assert bool((d["point_list"][1:][same] > d["point_list"][:-1][same]).all())
     g = d["point_list"].long()
+    assert torch.equal(d["entries"] & 0xffffffff, g)
     zbits = d["depths"].view(torch.int32).long()[g]
-    assert torch.equal(d["keys"] & 0xffffffff, zbits)
+    assert torch.equal(k & 0xffffffff, zbits)
+    cnt = d["tile_counts"].long()
+    assert int(cnt.sum()) == f[0] == d["num_rendered"]
+    x = torch.cumsum(cnt, 0) - cnt
     rng = d["ranges"].long()
-    tiles = d["keys"] >> 32
-    nz = (rng[:, 1] - rng[:, 0]) > 0
+    nz = cnt > 0
+    assert torch.equal(rng[nz, 0], x[nz]) and torch.equal(rng[nz, 1], (x + cnt)[nz])
+    assert int(rng[~nz].abs().sum()) == 0
+    # tile membership: Gaussian g is listed in tile t iff t lies in g's tile rectangle
+    rect = d["rect"].long()
     T = rng.shape[0]
-    assert bool((tiles[rng[nz, 0]] == torch.arange(T, device="cuda")[nz]).all())
+    gx = (inp["W"] + 15) // 16
+    tile_of = torch.repeat_interleave(torch.arange(T, device="cuda"), cnt)
+    tx, ty = tile_of % gx, tile_of // gx
+    r = rect[g]
+    assert bool(((tx >= r[:, 0]) & (tx < r[:, 2]) & (ty >= r[:, 1]) & (ty < r[:, 3])).all())
+    assert torch.equal(d["tiles_touched"].long(), torch.bincount(g, minlength=inp["P"]))
 
 
 @needs_ref
@@ -349,33 +428,42 @@ def test_truncated_sh_tensors_vs_reference_kernels(deg, M):
         assert err <= harness.GRAD_REL_L2 * max(float(b.double().norm()), 1e-3 * scale), (k, err)
 
 
-@needs_ref
-def test_sort_backends_agree_bitwise():
-    spec = CASES["c1"]
-    inp = harness.build_inputs(device="cuda", **spec)
+@pytest.mark.parametrize("name", ["c1_init", "c1_dense"])
+def test_tile_sort_paths_agree_bitwise(name):
+    """The tile sort keeps segments of up to `sort_cap` entries in shared memory and runs the wide
+    stages of longer ones on global memory.  Forcing tiny capacities sends every tile of an
+    initialisation-like cloud (thousands of instances per tile) through the long-segment path;
+    the sorted lists and the images must not change by a bit."""
+    from gftorf_b200 import _capi
+    inp = harness.build_inputs(device="cuda", **CASES[name])
     outs = {}
-    for backend in ("own", "cub"):
-        os.environ["GFT_SORT"] = backend
+    for cap in (0, 256, 1024, 16384):
+        old = _capi.set_option("sort_cap", cap)
         try:
             f = harness.call_forward(rasterizer._C, inp)
             d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
-            outs[backend] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone())
+            outs[cap] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone(), f[2].clone())
         finally:
-            os.environ.pop("GFT_SORT", None)
-    for a, b in zip(outs["own"], outs["cub"]):
-        assert torch.equal(a, b)
+            _capi.set_option("sort_cap", old)
+    assert int(debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])["tile_counts"].max()) > 256
+    for cap in (256, 1024, 16384):
+        for a, b in zip(outs[0], outs[cap]):
+            assert torch.equal(a, b), cap
 
 
 def test_subtile_culling_is_exact():
     """The conservative per-warp culling must not change a single bit of the result."""
     for name in ("c1", "c1_init", "c1_dense"):
         inp = harness.build_inputs(device="cuda", **CASES[name])
+        from gftorf_b200 import _capi
         a = harness.call_forward(rasterizer._C, inp)
-        os.environ["GFT_NO_CULL"] = "1"
+        _capi.set_option("no_cull", 1)
         try:
             b = harness.call_forward(rasterizer._C, inp)
         finally:
-            os.environ.pop("GFT_NO_CULL", None)
+            _capi.set_option("no_cull", 0)
+        assert not torch.equal(debug.decode_buffers(a[12], a[13], a[14], inp["P"], a[0], inp["W"], inp["H"])["extents"],
+                               debug.decode_buffers(b[12], b[13], b[14], inp["P"], b[0], inp["W"], inp["H"])["extents"])
         for i in range(1, 12):
             assert torch.equal(a[i], b[i]), (name, harness.FWD_NAMES[i])
         ga = harness.call_backward(rasterizer._C, inp, a)
@@ -720,3 +808,261 @@ def test_hinted_forward_is_identical_and_survives_a_bad_hint():
         inp0["shs_p"], 3, inp0["campos"], False, False, inp0["near_n"], inp0["far_n"],
         inp0["depth_range"], False, 0.0, 0.0, R_hint=5000)
     assert z[0] == 0 and torch.equal(z[1], inp0["bg"][0:3])
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining BASELINE configs: 8 M Gaussians at 1080p (configs[4]), a camera that moves every
+# frame (render.py:95-209), and batches of views (configs[1]-[3]: colour + ToF camera per
+# iteration; configs[3]: 8 cameras per iteration)
+# ------------------------------------------------------------------------------------------------
+@needs_ref
+def test_full_size_c5_forward_vs_reference():
+    """BASELINE configs[4] upper end: 8 M Gaussians (screen-space sigma 1 px) at 1920x1080,
+    forward only: every integer stage and every image plane against the reference kernels."""
+    spec = dict(P=8000000, W=1920, H=1080, kind="trained", seed=2, sigma_px=1.0)
+    inp, ours, ref = run_both(spec)
+    od, rd = decoded(inp, ours, ref)
+    rep = harness.compare_forward(ours, ref, od, rd)
+    harness.assert_forward_parity(rep)
+    assert rep["R_ours"] > 15000000
+
+
+def _orbit_views(n, W, H, device, depth_range=15.0):
+    """A trajectory around the scene: every frame has its own pose and the instance count moves by
+    far more than the 25 % margin of the R hint between some frames (zoom by field of view)."""
+    from gftorf_b200 import scenes
+    out = []
+    fovs = (1.2, 0.3, 1.2, 0.25, 1.1, 0.2, 1.2, 0.4, 1.2)
+    for i in range(n):
+        fov = fovs[i % len(fovs)]                    # wide / strong zoom alternate: R jumps both ways
+        cam = scenes.make_camera(W, H, fovx=fov, depth_range=depth_range, pose="orbit" if i else "identity", seed=100 + i)
+        out.append(cam)
+    return out
+
+
+@needs_ref
+def test_moving_camera_sequence_through_the_autograd_surface():
+    """render.py:95-209 renders a trajectory frame by frame.  The public surface sizes the binning
+    workspace from the previous frame's instance count (+25 %); on a moving camera that estimate
+    is sometimes too small and the tail of the forward re-runs.  Every frame must equal the
+    reference kernels bit for bit, whichever path it took."""
+    from gftorf_b200 import scenes
+    W, H, P = 320, 240, 60000
+    base = harness.build_inputs(device="cuda", P=P, W=W, H=H, kind="trained", seed=17, sigma_px=2.5)
+    cams = _orbit_views(9, W, H, "cuda")
+    t = lambda a: torch.from_numpy(a).cuda()
+    means2D = torch.zeros_like(base["means3D"])
+    Rs, overflowed = [], 0
+    rasterizer._R_HISTORY.clear()
+    for cam in cams:
+        inp = dict(base, viewmatrix=t(cam["viewmatrix"]), projmatrix=t(cam["projmatrix"]),
+                   campos=t(cam["campos"]), tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+                   near_n=cam["znear"], far_n=cam["zfar"])
+        s = rasterizer.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"], bg=inp["bg"],
+            scale_modifier=1.0, viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"], sh_degree=3,
+            campos=inp["campos"], prefiltered=False, debug=False, near_n=inp["near_n"], far_n=inp["far_n"],
+            depth_range=inp["depth_range"])
+        hint = rasterizer._r_hint((0, P, H, W))
+        with torch.no_grad():
+            out = rasterizer.GaussianRasterizer(s)(
+                means3D=inp["means3D"], means2D=means2D, opacities=inp["opacities"], shs=inp["shs"],
+                shs_p=inp["shs_p"], scales=inp["scales"], rotations=inp["rotations"])
+        ref = harness.call_forward(ref_driver.RefModule, inp)
+        torch.cuda.synchronize()
+        for i in range(11):
+            assert torch.equal(out[i], ref[i + 1]), (len(Rs), harness.FWD_NAMES[i + 1])
+        if Rs and ref[0] > hint:
+            overflowed += 1
+        Rs.append(ref[0])
+    assert overflowed >= 1, Rs       # the too-small-hint path really ran
+    assert min(Rs) > 0
+
+
+def _two_camera_inputs(P, wh_a, wh_b, seed, kind="trained", **kw):
+    """The same Gaussians seen by two cameras of different resolution; the background map is sized
+    from the first camera and reused for the second (train.py:121-128, quirk A.7-3)."""
+    (Wa, Ha), (Wb, Hb) = wh_a, wh_b
+    a = harness.build_inputs(device="cuda", P=P, W=Wa, H=Ha, kind=kind, seed=seed, **kw)
+    b = harness.build_inputs(device="cuda", P=P, W=Wb, H=Hb, kind=kind, seed=seed, pose="orbit",
+                             bg_hw=(Ha, Wa) if Wb * Hb <= Wa * Ha else None, **kw)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p"):
+        b[k] = a[k]
+    if Wb * Hb <= Wa * Ha:
+        b["bg"] = a["bg"]
+    return a, b
+
+
+def _spec(inp):
+    from gftorf_b200 import views as V
+    return V.ViewSpec(inp["H"], inp["W"], inp["tanfovx"], inp["tanfovy"], inp["bg"], inp["viewmatrix"],
+                      inp["projmatrix"], inp["campos"], inp["near_n"], inp["far_n"], inp["depth_range"],
+                      inp["use_view_dependent_phase"], inp["phase_offset"], inp["dc_offset"])
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [
+    dict(P=6000, wh_a=(128, 96), wh_b=(96, 80), seed=31),
+    dict(P=20000, wh_a=(320, 240), wh_b=(320, 240), seed=32, view_dependent_phase=True, phase_offset=0.2,
+         dc_offset=0.1),
+    dict(P=300000, wh_a=(640, 480), wh_b=(640, 480), seed=0),           # BASELINE configs[1]
+    dict(P=500000, wh_a=(640, 480), wh_b=(320, 240), seed=4, depth_range=10.0),   # configs[2]
+    dict(P=30000, wh_a=(160, 120), wh_b=(101, 67), seed=33, kind="init"),
+])
+def test_view_batch_equals_the_reference_calls_view_by_view(shape):
+    """gft_forward_views / gft_backward_views: one call for the colour and the ToF camera of an
+    iteration.  Per view every integer stage and image is the reference kernels' result bit for
+    bit; the parameter gradients are the sum of the reference's two backward calls (what
+    AccumulateGrad produces, train.py:279); means2D gradients stay per view."""
+    from gftorf_b200 import views as V
+    shape = dict(shape)
+    a, b = _two_camera_inputs(shape.pop("P"), shape.pop("wh_a"), shape.pop("wh_b"), shape.pop("seed"),
+                              zero_shp_rest=True, **shape)
+    fwd = V.forward_views(a["means3D"], a["opacities"], a["scales"], a["rotations"], a["shs"], a["shs_p"],
+                          [_spec(a), _spec(b)], 3)
+    dec = debug.decode_views(fwd.geom, fwd.binning, fwd.img, a["P"], fwd.R,
+                             [(a["W"], a["H"]), (b["W"], b["H"])])
+    refs = []
+    for i, inp in enumerate((a, b)):
+        ref = harness.call_forward(ref_driver.RefModule, inp)
+        torch.cuda.synchronize()
+        rd = ref_driver.decode_buffers(ref[12], ref[13], ref[14], inp["P"], ref[0], inp["W"], inp["H"])
+        ours = (dec[i]["num_rendered"],) + tuple(fwd.outs[i])
+        rep = harness.compare_forward(ours, ref, dec[i], rd)
+        harness.assert_forward_parity(rep)
+        refs.append(ref)
+    assert fwd.R == refs[0][0] + refs[1][0]
+    out = V.backward_views(fwd, [a["grads"], b["grads"]])
+    rbs = [harness.call_backward(ref_driver.RefModule, inp, ref) for inp, ref in zip((a, b), refs)]
+    torch.cuda.synchronize()
+    scale = float((rbs[0][8] + rbs[1][8]).double().norm())
+    for name, i in dict(means3D=4, shs=6, opacities=3, scales=8, rotations=9, phase_offset=10, dc_offset=11).items():
+        expect = (rbs[0][i] + rbs[1][i]).double()
+        err = float((out[name].double() - expect).norm())
+        assert err <= harness.GRAD_REL_L2 * max(float(expect.norm()), 1e-3 * scale), (name, err)
+    assert harness.rel_l2(out["shs_p"][0], rbs[0][7][0] + rbs[1][7][0]) <= harness.GRAD_REL_L2
+    for i in range(2):
+        assert harness.rel_l2(out["means2D"][i], rbs[i][0]) <= harness.GRAD_REL_L2
+
+
+def test_view_batch_gradients_equal_single_view_calls_with_live_sh_p():
+    """With all SH_p coefficients live (where the reference is undefined, D1) the batch must still
+    equal OUR single-view calls: same images bit for bit, gradients = sum of the two calls."""
+    from gftorf_b200 import views as V
+    a, b = _two_camera_inputs(9000, (160, 120), (128, 96), 35, view_dependent_phase=True,
+                              phase_offset=0.3, dc_offset=0.05)
+    fwd = V.forward_views(a["means3D"], a["opacities"], a["scales"], a["rotations"], a["shs"], a["shs_p"],
+                          [_spec(a), _spec(b)], 3)
+    out = V.backward_views(fwd, [a["grads"], b["grads"]])
+    singles = []
+    for i, inp in enumerate((a, b)):
+        f = harness.call_forward(rasterizer._C, inp)
+        for j in range(1, 12):
+            assert torch.equal(f[j], fwd.outs[i][j - 1]), (i, harness.FWD_NAMES[j])
+        singles.append(harness.call_backward(rasterizer._C, inp, f))
+    for name, i in dict(means3D=4, shs=6, shs_p=7, opacities=3, scales=8, rotations=9, phase_offset=10,
+                        dc_offset=11).items():
+        assert harness.rel_l2(out[name], singles[0][i] + singles[1][i]) <= harness.GRAD_REL_L2, name
+    for i in range(2):
+        assert harness.rel_l2(out["means2D"][i], singles[i][0]) <= harness.GRAD_REL_L2
+    # Gaussians culled in both views: zero rows
+    vis = (fwd.radii[0] > 0) | (fwd.radii[1] > 0)
+    assert int((~vis).sum()) > 0
+    for name in ("means3D", "shs", "shs_p", "opacities", "scales", "rotations"):
+        assert float(out[name][~vis].abs().sum()) == 0.0, name
+
+
+def test_view_batch_of_eight_cameras_and_bucket_accumulation():
+    """BASELINE configs[3] shape in small: 8 cameras x (colour + ToF resolution) = 16 views in one
+    call, gradients written straight into a GradBucket; a second call accumulates into it."""
+    from gftorf_b200 import views as V, parallel, scenes
+    P = 12000
+    base = harness.build_inputs(device="cuda", P=P, W=192, H=108, kind="trained", seed=61, sigma_px=2.0)
+    t = lambda x: torch.from_numpy(x).cuda()
+    specs, grads = [], []
+    for c in range(8):
+        for (W, H) in ((192, 108), (64, 48)):
+            cam = scenes.make_camera(W, H, pose="orbit" if c else "identity", seed=200 + c)
+            specs.append(V.ViewSpec(H, W, cam["tanfovx"], cam["tanfovy"], base["bg"], t(cam["viewmatrix"]),
+                                    t(cam["projmatrix"]), t(cam["campos"]), cam["znear"], cam["zfar"],
+                                    cam["depth_range"]))
+            grads.append({k: t(v) for k, v in scenes.make_pixel_grads(H, W, seed=300 + c).items()})
+    args = (base["means3D"], base["opacities"], base["scales"], base["rotations"], base["shs"], base["shs_p"])
+    fwd = V.forward_views(*args, specs, 3)
+    assert len(fwd.outs) == 16 and fwd.R > 0
+    out = V.backward_views(fwd, grads)
+    # view by view through the single-view entry point
+    acc = None
+    for i, sp in enumerate(specs):
+        f1 = V.forward_views(*args, [sp], 3)
+        for j in range(11):
+            assert torch.equal(f1.outs[0][j], fwd.outs[i][j]), (i, j)
+        o1 = V.backward_views(f1, [grads[i]])
+        assert harness.rel_l2(out["means2D"][i], o1["means2D"][0]) <= harness.GRAD_REL_L2
+        acc = {k: v.clone() for k, v in o1.items()} if acc is None else {k: acc[k] + o1[k] for k in acc}
+    for k in ("means3D", "shs", "shs_p", "opacities", "scales", "rotations", "phase_offset", "dc_offset"):
+        assert harness.rel_l2(out[k], acc[k]) <= harness.GRAD_REL_L2, k
+    # bucket: first call overwrites (no zero fill), second call adds
+    params = {k: base[k] for k in ("means3D", "scales", "rotations", "opacities", "shs", "shs_p")}
+    bucket = parallel.GradBucket(params, [torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")])
+    bucket.flat.fill_(float("nan"))
+    go = bucket.grad_out()
+    fa = V.forward_views(*args, specs[:8], 3)
+    V.backward_views(fa, grads[:8], grad_out=go, accumulate=False)
+    fb = V.forward_views(*args, specs[8:], 3)
+    V.backward_views(fb, grads[8:], grad_out=go, accumulate=True)
+    for k in ("means3D", "shs", "shs_p", "opacities", "scales", "rotations", "phase_offset", "dc_offset"):
+        assert harness.rel_l2(go[k], out[k]) <= harness.GRAD_REL_L2, k
+
+
+@needs_ref
+def test_rasterize_views_autograd_matches_two_reference_calls():
+    """The differentiable batched surface: outputs are independent tensors (in-place ops allowed),
+    leaves receive the summed gradients, means2D [V,P,3] the per-view ones."""
+    from gftorf_b200 import views as V
+    a, b = _two_camera_inputs(7000, (128, 96), (96, 64), 71, zero_shp_rest=True)
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+    leaves = {k: a[k].clone().requires_grad_(True) for k in names}
+    m2d = torch.zeros((2, 7000, 3), device="cuda", requires_grad=True)
+    outs = V.rasterize_views(leaves["means3D"], m2d, leaves["opacities"], leaves["shs"], leaves["shs_p"],
+                             leaves["scales"], leaves["rotations"], [_spec(a), _spec(b)], 3)
+    loss = 0
+    for o, inp in zip(outs, (a, b)):
+        g = inp["grads"]
+        assert len(o) == 11 and o[10].dtype == torch.int32
+        loss = loss + (o[0] * g["color"]).sum() + (o[1] * g["phasor"]).sum() + (o[2] * g["depth"]).sum() \
+            + (o[4] * g["acc"]).sum() + (o[6] * g["depth_distortion"]).sum()
+    loss.backward()
+    outs[0][0].clamp_(0, 1)          # outputs are independent tensors: in-place ops are legal
+    refs = [harness.call_forward(ref_driver.RefModule, inp) for inp in (a, b)]
+    rbs = [harness.call_backward(ref_driver.RefModule, inp, r) for inp, r in zip((a, b), refs)]
+    for o, r in zip(outs, refs):
+        for i in range(1, 10):
+            assert torch.equal(o[i], r[i + 1]), harness.FWD_NAMES[i + 1]
+    for k, i in dict(means3D=4, opacities=3, shs=6, scales=8, rotations=9).items():
+        assert harness.rel_l2(leaves[k].grad, rbs[0][i] + rbs[1][i]) <= harness.GRAD_REL_L2, k
+    for v in range(2):
+        assert harness.rel_l2(m2d.grad[v], rbs[v][0]) <= harness.GRAD_REL_L2
+
+
+def test_public_outputs_are_independent_tensors():
+    """In-place edits of a returned image must be legal under autograd (the reference returns
+    separate tensors), and the screen-space gradient must not pin the scratch allocation."""
+    inp = harness.build_inputs(device="cuda", **CASES["tiny"])
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in names}
+    m2d = torch.zeros_like(inp["means3D"], requires_grad=True)
+    s = rasterizer.GaussianRasterizationSettings(
+        image_height=inp["H"], image_width=inp["W"], tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"],
+        bg=inp["bg"], scale_modifier=1.0, viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+        sh_degree=3, campos=inp["campos"], prefiltered=False, debug=False, near_n=inp["near_n"],
+        far_n=inp["far_n"], depth_range=inp["depth_range"])
+    out = rasterizer.GaussianRasterizer(s)(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                          shs=leaves["shs"], shs_p=leaves["shs_p"], scales=leaves["scales"],
+                                          rotations=leaves["rotations"])
+    ptrs = {t.untyped_storage().data_ptr() for t in out}
+    assert len(ptrs) == 11
+    depth = out[2].clone()
+    out[2].clamp_(min=0.5)           # raised "view ... output of a function that returns multiple views" before
+    (out[0].sum() + depth.sum()).backward()
+    assert m2d.grad.untyped_storage().nbytes() == m2d.grad.numel() * 4
