@@ -131,7 +131,7 @@ class GftWorkspaceLayout(C.Structure):
         "geom_cov3D", "geom_rec", "geom_depths", "geom_tiles_touched", "geom_rect",
         "geom_clamped", "geom_pa", "geom_total",
         "bin_point_list", "bin_entries", "bin_total",
-        "img_hdr", "img_tile_counts", "img_ranges", "img_state", "img_total")]
+        "img_hdr", "img_sub_bins", "img_tile_counts", "img_ranges", "img_state", "img_total")]
 
 
 # Every symbol include/gftorf.h declares; tests/test_abi.py checks the list against the header.
@@ -238,6 +238,6 @@ def launch_count():
 def set_option(name, value):
     """Flip a kernel tunable / A-B switch (include/gftorf.h: gft_set_option); returns the old value."""
     old = lib().gft_set_option(name.encode(), int(value))
-    if old < 0 and name not in ("sort_cap", "bwd_pred", "pbwd_minb", "no_cull"):
+    if old < 0 and name not in ("sort_cap", "sort_radix", "sub_bins", "bwd_pred", "pbwd_minb", "no_cull"):
         raise KeyError(name)
     return old

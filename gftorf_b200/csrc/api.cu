@@ -98,20 +98,34 @@ GeomWs geom_layout(int P, int V) {
   return g;
 }
 
-// image: header (word 1 = num_rendered) | tile counters | tile cursors | tile ranges | pixel state
+// image: header (word 1 = num_rendered) | sub-bin counters | cursors | starts | tile ranges | pixel state
 struct ImgWs {
-  size_t hdr, counts, cursors, ranges, state, total;
+  size_t hdr, counts, cursors, starts, ranges, state, total;
   size_t T_total, N_total;
+  int S;     // sub-counters per tile
 };
+
+// Sub-counters per tile: as many as the option allows while one block can still scan them all.
+int sub_bins_for(size_t T_total) {
+  int S = gft::option(gft::OPT_SUB_BINS);
+  if (S < 1) S = 1;
+  if (S > 16) S = 16;
+  while (S & (S - 1)) S &= S - 1;            // power of two
+  while (S > 1 && T_total * (size_t)S > 131072) S >>= 1;
+  return S;
+}
 
 ImgWs img_layout(size_t T_total, size_t N_total) {
   ImgWs m;
   m.T_total = T_total; m.N_total = N_total;
+  m.S = sub_bins_for(T_total);
+  const size_t nb = (T_total > 0 ? T_total : 1) * (size_t)m.S;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
   m.hdr = take(256);
-  m.counts = take((T_total > 0 ? T_total : 1) * 4);
-  m.cursors = take((T_total > 0 ? T_total : 1) * 4);
+  m.counts = take(nb * 4);
+  m.cursors = take(nb * 4);
+  m.starts = take((nb + 1) * 4);
   m.ranges = take((T_total > 0 ? T_total : 1) * 8);
   m.state = take((N_total > 0 ? N_total : 1) * 16);
   m.total = off;
@@ -199,8 +213,10 @@ struct OptDef { const char* name; const char* env; int def; };
 const OptDef kOpts[OPT_COUNT] = {
     {"sort_cap", "GFT_SORT_CAP", 0},     // entries per block of the tile sort held in shared memory (0 = automatic)
     {"bwd_pred", "GFT_BWD_PRED", 1},     // branch-free replay in the blend backward
-    {"pbwd_minb", "GFT_PBWD_MINB", 4},   // resident blocks per SM the preprocess backward is compiled for (3 or 4)
+    {"pbwd_minb", "GFT_PBWD_MINB", 3},   // resident blocks per SM the preprocess backward is compiled for (3 or 4)
     {"no_cull", "GFT_NO_CULL", 0},       // 1: no sub-tile culling extents
+    {"sort_radix", "GFT_SORT_RADIX", 1}, // 0: bitonic network instead of the shared-memory radix sort per tile
+    {"sub_bins", "GFT_SUB_BINS", 16},    // sub-counters per tile of the binning (power of two, <= 16)
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};
@@ -305,6 +321,7 @@ void gft_workspace_layout_views(int P, int R, int n_views, const int* widths, co
   }
   const ImgWs m = img_layout(T, N);
   o->img_hdr = m.hdr;
+  o->img_sub_bins = (size_t)m.S;
   o->img_tile_counts = m.counts;
   o->img_ranges = m.ranges;
   o->img_state = m.state;
@@ -376,9 +393,10 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
   uint32_t* hdr = reinterpret_cast<uint32_t*>(img + il.hdr);
   uint32_t* counts = reinterpret_cast<uint32_t*>(img + il.counts);
   uint32_t* cursors = reinterpret_cast<uint32_t*>(img + il.cursors);
+  uint32_t* starts = reinterpret_cast<uint32_t*>(img + il.starts);
   uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
-  // header + tile counters are adjacent: one fill
-  cudaMemsetAsync(hdr, 0, (il.counts - il.hdr) + T_total * 4, stream);
+  // header + sub-bin counters are adjacent: one fill
+  cudaMemsetAsync(hdr, 0, (il.counts - il.hdr) + T_total * (size_t)il.S * 4, stream);
 
   gft::PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -397,6 +415,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
   pp.g.clamped = reinterpret_cast<uint32_t*>(geom + gl.clamped);
   pp.g.pa = reinterpret_cast<float*>(geom + gl.pa);
   pp.tile_counts = counts;
+  pp.sub_bins = il.S;
   for (int i = 0; i < NV; ++i) fill_cam(pp.views[i], a->views[i], dims[i]);
   { Stage st("preprocess_fwd", stream); gft::launch_preprocess_fwd(pp, stream); }
   GFT_CUDA_OK("preprocess");
@@ -410,7 +429,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
   // for the preprocess + scan kernels only.
   auto scan_and_post_R = [&](uint32_t cap) -> int {
     { Stage st("tile_scan", stream);
-      gft::launch_tile_scan(counts, (int)T_total, cap, ranges, cursors, hdr, stream); }
+      gft::launch_tile_scan(counts, (int)T_total, il.S, cap, starts, ranges, cursors, hdr, stream); }
     GFT_CUDA_OK("tile_scan");
     cudaError_t e = cudaMemcpyAsync(hs->pinned, d_R, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaEventRecord(hs->ev, stream);
@@ -436,7 +455,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
     unsigned long long* entries = reinterpret_cast<unsigned long long*>(bin + bl.entries);
     if (cap > 0) {
       { Stage st("scatter_entries", stream);
-        gft::launch_scatter_entries(pp, ranges, cursors, entries, stream); }
+        gft::launch_scatter_entries(pp, starts, cursors, entries, stream); }
       GFT_CUDA_OK("scatter_entries");
       { Stage st("tile_sort", stream);
         gft::launch_tile_sort(ranges, (int)T_total, entries, point_list, (int)((size_t)cap / T_total), stream); }

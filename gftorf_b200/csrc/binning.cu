@@ -8,13 +8,19 @@
 // the reference sorts keys (tile << 32) | float_bits(view_z) with a STABLE radix sort over
 // instances emitted in ascending Gaussian order, so inside a tile the list is ordered by
 // (float_bits(view_z), Gaussian index).  Here
-//   1. the preprocess kernel counts the instances of every tile (tile_counts, one RED each),
-//   2. tile_scan_kernel turns the counts into `ranges` (an exclusive scan over tiles IS the
-//      reference's ranges array) and the instance count R,
+//   1. the preprocess kernel counts the instances of every tile (tile_counts, one RED each).  A
+//      tile has S sub-counters (Gaussian index mod S): ~1000 instances per tile hammering ONE
+//      address serialise in the L2 (measured 0.165 ms for 2.4 M atomics on 2400 addresses, the
+//      same whether 2 or 16 views are batched); S = 16 spreads them over 16 addresses,
+//   2. tile_scan_kernel turns the counts into sub-bin starts, `ranges` (an exclusive scan over
+//      tiles IS the reference's ranges array) and the instance count R,
 //   3. scatter_entries_kernel writes every instance's 64-bit entry (depth bits << 32 | index)
-//      into its tile's segment at a slot taken from an atomic cursor (arbitrary order),
-//   4. tile_sort_kernel sorts each segment on the whole 64-bit entry — a total order, so the
-//      arbitrary slot order of step 3 does not matter and the result is the reference's list.
+//      into its tile's segment at a slot taken from the sub-bin's atomic cursor (arbitrary order),
+//   4. tile_sort_kernel sorts each segment: a stable 4-pass LSD radix sort on the 32 depth bits
+//      in shared memory, then a check for equal depths in the wrong index order (only then the
+//      whole 64-bit entry is sorted, with the bitonic network that also serves segments too long
+//      for shared memory).  The result is a total order on (depth bits, index), so the arbitrary
+//      slot order of step 3 does not matter and the list is the reference's.
 // HBM traffic: 8 B written + 8 B read + 12 B written per instance (28 B) instead of
 // 12 + 8 + 6 x 24 + 8 = 172 B for emit + histogram + radix passes + ranges.
 #include "common.cuh"
@@ -30,28 +36,37 @@ typedef unsigned long long u64;
 
 constexpr int SCAN_THREADS = 1024;
 
-// One block scans all tile counters (T_total <= 16 views x 8160 tiles at 1080p).
+// One block scans all sub-bin counters (n = T_total * S <= 131072, S chosen by the caller):
+// starts[i] = exclusive prefix (clamped to `capacity`), starts[n] = min(R, capacity), then
+// ranges[t] = (starts[t*S], starts[(t+1)*S]), with (0,0) for empty tiles — the reference's
+// memset + identifyTileRanges never touch those (rasterizer_impl.cu:118-140,341).
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(const uint32_t* __restrict__ counts, int T, uint32_t capacity,
-                 uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
-                 uint32_t* __restrict__ hdr) {
+tile_scan_kernel(const uint32_t* __restrict__ counts, int T, int S, uint32_t capacity,
+                 uint32_t* __restrict__ starts, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ cursors, uint32_t* __restrict__ hdr) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = T * S;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  // chunks of SCAN_THREADS*4 counters: every thread owns 4 consecutive ones (one 16-byte load)
-  for (int base = 0; base < T; base += SCAN_THREADS * 4) {
+  // chunks of SCAN_THREADS*4 counters: every thread owns 4 consecutive ones
+  for (int base = 0; base < n; base += SCAN_THREADS * 4) {
     const int i0 = base + (int)tid * 4;
     uint32_t c[4];
+    if (i0 + 3 < n) {
+      const uint4 q = *reinterpret_cast<const uint4*>(counts + i0);
+      c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c[k] = (i0 + k < T) ? counts[i0 + k] : 0u;
+      for (int k = 0; k < 4; ++k) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
+    }
     const uint32_t mine = c[0] + c[1] + c[2] + c[3];
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t)o) incl += n;
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
@@ -65,24 +80,30 @@ tile_scan_kernel(const uint32_t* __restrict__ counts, int T, uint32_t capacity,
     uint32_t x = s_carry + wbase + incl - mine;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i0 + k < T) {
-        const uint32_t y = x + c[k];
-        // empty tiles read (0,0): the reference's memset + identifyTileRanges never touch them
-        ranges[i0 + k] = c[k] ? make_uint2(min(x, capacity), min(y, capacity)) : make_uint2(0u, 0u);
+      if (i0 + k < n) {
+        starts[i0 + k] = min(x, capacity);
         cursors[i0 + k] = 0u;
-        x = y;
+        x += c[k];
       }
     }
     __syncthreads();
     if (tid == 0) s_carry += total;
     __syncthreads();
   }
-  if (tid == 0) hdr[1] = s_carry;   // num_rendered
+  if (tid == 0) {
+    starts[n] = min(s_carry, capacity);
+    hdr[1] = s_carry;   // num_rendered
+  }
+  __syncthreads();      // the block's own global writes are visible to it from here on
+  for (int t = tid; t < T; t += SCAN_THREADS) {
+    const uint32_t x = starts[t * S], y = starts[(t + 1) * S];
+    ranges[t] = y > x ? make_uint2(x, y) : make_uint2(0u, 0u);
+  }
 }
 
 // grid: (ceil(P/256), nviews).  Same tile enumeration as the counting in the preprocess kernel.
 __global__ void __launch_bounds__(GFT_BLOCK)
-scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint2* __restrict__ ranges,
+scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint32_t* __restrict__ starts,
                        uint32_t* __restrict__ cursors, u64* __restrict__ entries) {
   const int v = blockIdx.y;
   const ViewCam& vc = p.views[v];
@@ -97,12 +118,12 @@ scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint2* 
     tiles = (rx1 - rx0) * (ry1 - ry0);
   }
   const uint32_t gx = (uint32_t)vc.grid_x, tb = (uint32_t)vc.tile_base;
+  const uint32_t S = (uint32_t)p.sub_bins;
   const float* __restrict__ depths = p.g.depths + v * P;
   for_each_tile(rx0, ry0, rx1, tiles, (uint32_t)idx, lane, [&](uint32_t tx, uint32_t ty, uint32_t g) {
-    const uint32_t t = tb + ty * gx + tx;
-    const uint2 rg = __ldg(ranges + t);
-    const uint32_t slot = rg.x + atomicAdd(cursors + t, 1u);
-    if (slot < rg.y)   // only ever false when a caller's size hint was too small
+    const uint32_t i = (tb + ty * gx + tx) * S + (g & (S - 1u));
+    const uint32_t slot = __ldg(starts + i) + atomicAdd(cursors + i, 1u);
+    if (slot < __ldg(starts + i + 1))   // only ever false when a caller's size hint was too small
       entries[slot] = ((u64)__float_as_uint(__ldg(depths + g)) << 32) | (u64)g;
   });
 }
@@ -148,11 +169,81 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
   return n <= 1u ? 1u : (1u << (32 - __clz(n - 1u)));
 }
 
+// Stable LSD radix sort of s_a[0,n) on bits [32,64) (the depth bits), 8 bits per pass, ping-pong
+// between s_a and s_b; the result is back in s_a.  256 threads = 256 digit bins.  Warp w owns the
+// contiguous span [w*span, (w+1)*span) and walks it 32 entries at a time, so ranks follow the
+// current order (stability): per pass a per-warp digit histogram (shared-memory atomics), an
+// exclusive scan over (digit, warp), then every 32-entry row is ranked with match_any against the
+// warp's running digit offsets and scattered into the other buffer.
+__device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint32_t* s_hist,
+                                                        uint32_t* s_wtot, uint32_t n) {
+  constexpr int WARPS = SORT_THREADS / 32;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t items = (n + SORT_THREADS - 1) / SORT_THREADS;
+  const uint32_t span = items * 32u;
+  const uint32_t w0 = warp * span;
+  u64* src = s_a;
+  u64* dst = s_b;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 32 + 8 * pass;
+    for (uint32_t i = tid; i < WARPS * 256u; i += SORT_THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    for (uint32_t i = 0; i < items; ++i) {
+      const uint32_t e = w0 + i * 32u + lane;
+      if (e < n) atomicAdd(&s_hist[warp * 256u + ((uint32_t)(src[e] >> shift) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    {
+      // digit d = tid: exclusive prefix over warps, then over digits
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const uint32_t c = s_hist[w * 256 + tid];
+        s_hist[w * 256 + tid] = run;
+        run += c;
+      }
+      uint32_t incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      uint32_t wb = 0;
+      for (uint32_t w = 0; w < warp; ++w) wb += s_wtot[w];
+      const uint32_t excl = wb + incl - run;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s_hist[w * 256 + tid] += excl;
+    }
+    __syncthreads();
+    for (uint32_t i = 0; i < items; ++i) {
+      const uint32_t e = w0 + i * 32u + lane;
+      const bool ok = e < n;
+      const u64 key = ok ? src[e] : 0ull;
+      const uint32_t d = ok ? ((uint32_t)(key >> shift) & 0xffu) : 0x100u + lane;   // padding lanes match nobody
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader && ok) {
+        old = s_hist[warp * 256u + d];
+        s_hist[warp * 256u + d] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      if (ok) dst[old + __popc(peers & ((1u << lane) - 1u))] = key;
+      __syncwarp();
+    }
+    __syncthreads();
+    u64* t = src; src = dst; dst = t;
+  }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
-                 uint32_t* __restrict__ point_list, uint32_t cap) {
+                 uint32_t* __restrict__ point_list, uint32_t cap, int use_radix) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
   u64* s = reinterpret_cast<u64*>(sort_smem_raw);
+  __shared__ uint32_t s_wtot[SORT_THREADS / 32];
   const uint2 rg = ranges[blockIdx.x];
   const uint32_t n = rg.y - rg.x;
   if (n == 0u) return;
@@ -163,8 +254,21 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
   if (n <= cap) {
     for (uint32_t i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
     __syncthreads();
-    const uint32_t m = next_pow2(n);
-    for (uint32_t k = 2; k <= m; k <<= 1) level_in_shared(s, n, k, true, m >> 1);
+    bool need_full = true;
+    if (use_radix && n > 32u) {
+      u64* s_b = s + cap;
+      uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_b + cap);
+      radix_depth_sort_shared(s, s_b, s_hist, s_wtot, n);
+      // equal depths must be in ascending index order; the slots came from atomics, so a tie may
+      // be the wrong way round — then (and only then) the whole 64-bit entries are sorted
+      int bad = 0;
+      for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS) bad |= (s[i] > s[i + 1]) ? 1 : 0;
+      need_full = __syncthreads_or(bad) != 0;
+    }
+    if (need_full) {
+      const uint32_t m = next_pow2(n);
+      for (uint32_t k = 2; k <= m; k <<= 1) level_in_shared(s, n, k, true, m >> 1);
+    }
     for (uint32_t i = tid; i < n; i += SORT_THREADS) {
       const u64 e = s[i];
       g[i] = e;
@@ -218,33 +322,37 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
 
 }  // namespace
 
-void launch_tile_scan(const uint32_t* tile_counts, int T_total, uint32_t capacity, uint2* ranges,
-                      uint32_t* cursors, uint32_t* hdr, cudaStream_t stream) {
-  tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_counts, T_total, capacity, ranges, cursors, hdr);
+void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
+                      uint32_t* starts, uint2* ranges, uint32_t* cursors, uint32_t* hdr,
+                      cudaStream_t stream) {
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_counts, T_total, sub_bins, capacity, starts,
+                                                   ranges, cursors, hdr);
   note_launches(1);
 }
 
-void launch_scatter_entries(const PreprocessParams& pp, const uint2* ranges, uint32_t* cursors,
+void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
                             unsigned long long* entries, cudaStream_t stream) {
   if (pp.P <= 0) return;
   const dim3 grid((pp.P + GFT_BLOCK - 1) / GFT_BLOCK, pp.nviews);
-  scatter_entries_kernel<<<grid, GFT_BLOCK, 0, stream>>>(pp, ranges, cursors, entries);
+  scatter_entries_kernel<<<grid, GFT_BLOCK, 0, stream>>>(pp, starts, cursors, entries);
   note_launches(1);
 }
 
 void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entries,
                       uint32_t* point_list, int mean_len_hint, cudaStream_t stream) {
   if (T_total <= 0) return;
-  // shared-memory capacity per block: 4096 entries (32 KB, 7 blocks/SM) for ordinary scenes, 8192
-  // (64 KB, 3 blocks/SM) when the tile lists are long on average (initialisation-like clouds)
+  // Entries per block held in shared memory.  Radix path: two buffers + 8 KB of histograms, i.e.
+  // 40 KB at 2048 (5 blocks/SM), 72 KB at 4096 (3 blocks/SM); longer segments take the bitonic
+  // path on 4096-entry chunks.  Option sort_cap forces a capacity, sort_radix = 0 the bitonic
+  // network everywhere (A/B runs, tests of the long-segment path).
   const int forced = option(OPT_SORT_CAP);
-  uint32_t cap = mean_len_hint > 1500 ? 8192u : 4096u;
-  if (forced == 256 || forced == 1024 || forced == 2048 || forced == 4096 || forced == 8192 || forced == 16384)
-    cap = (uint32_t)forced;
-  const int smem = (int)cap * 8;
+  const int use_radix = option(OPT_SORT_RADIX) != 0;
+  uint32_t cap = mean_len_hint > 700 ? 4096u : 2048u;
+  if (forced == 256 || forced == 1024 || forced == 2048 || forced == 4096 || forced == 8192) cap = (uint32_t)forced;
+  const int smem = use_radix ? (int)cap * 16 + 8 * 256 * 4 : (int)cap * 8;
   static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(tile_sort_kernel, 16384 * 8, &smem_ok);
-  tile_sort_kernel<<<T_total, SORT_THREADS, smem, stream>>>(ranges, entries, point_list, cap);
+  ensure_dynamic_smem(tile_sort_kernel, 8192 * 16 + 8 * 256 * 4, &smem_ok);
+  tile_sort_kernel<<<T_total, SORT_THREADS, smem, stream>>>(ranges, entries, point_list, cap, use_radix);
   note_launches(1);
 }
 

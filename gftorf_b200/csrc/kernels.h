@@ -34,7 +34,7 @@ inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_ma
 int sm_count();
 
 // Tunables / A-B switches (gft_set_option in the C ABI; defaults from the environment, read once).
-enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_COUNT };
+enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_SORT_RADIX, OPT_SUB_BINS, OPT_COUNT };
 int option(int id);
 
 // Records the thread-local error string behind gft_last_error() and returns `code` (api.cu).
@@ -86,7 +86,8 @@ struct PreprocessParams {
   int prefiltered;
   int subtile_cull;        // 0: write infinite extents (blend kernels then test every pair)
   GeomViews g;
-  uint32_t* tile_counts;   // [T_total] zero-filled before the launch; += 1 per (Gaussian, tile) instance
+  uint32_t* tile_counts;   // [T_total][sub_bins] zero-filled before the launch; += 1 per (Gaussian, tile) instance
+  int sub_bins;            // sub-counters per tile (power of two): Gaussian g counts into sub-bin g % sub_bins
   ViewCam views[GFT_MAX_VIEWS];
 };
 
@@ -95,15 +96,16 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
                          float near_n, float far_n, cudaStream_t stream);
 
 // ---- binning: tile-segmented (binning.cu) ------------------------------------------------------
-// tile_counts -> ranges (exclusive scan over the global tile index; empty tiles read (0,0) like
-// the reference's memset + identifyTileRanges, rasterizer_impl.cu:118-140,341), the instance
-// count R in hdr[1], cursors zeroed.  Ranges are clamped to `capacity` (only ever effective when
-// a caller's size hint was too small; the forward is then repeated with the exact size).
-void launch_tile_scan(const uint32_t* tile_counts, int T_total, uint32_t capacity, uint2* ranges,
-                      uint32_t* cursors, uint32_t* hdr, cudaStream_t stream);
+// tile_counts [T_total][S] -> starts [T_total*S + 1] (exclusive scan), ranges (empty tiles read
+// (0,0) like the reference's memset + identifyTileRanges, rasterizer_impl.cu:118-140,341), the
+// instance count R in hdr[1], cursors zeroed.  Everything is clamped to `capacity` (only ever
+// effective when a caller's size hint was too small; the forward is then repeated exactly).
+void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
+                      uint32_t* starts, uint2* ranges, uint32_t* cursors, uint32_t* hdr,
+                      cudaStream_t stream);
 // Every (view, Gaussian, tile) instance writes its entry (float_bits(view_z) << 32 | Gaussian id)
-// into its tile's segment, at a slot handed out by an atomic cursor (any order).
-void launch_scatter_entries(const PreprocessParams& pp, const uint2* ranges, uint32_t* cursors,
+// into its tile's segment, at a slot handed out by its sub-bin's atomic cursor (any order).
+void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
                             unsigned long long* entries, cudaStream_t stream);
 // Sorts every tile segment on the 64-bit entry (depth bits, then Gaussian id): exactly the order
 // of the reference's stable radix sort of (tile << 32 | depth) keys over instances emitted in

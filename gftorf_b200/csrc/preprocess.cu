@@ -232,10 +232,11 @@ preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p) {
 
     // one count per (Gaussian, tile) instance of this view
     {
-      uint32_t* cnt = p.tile_counts + vc.tile_base;
+      const uint32_t S = (uint32_t)p.sub_bins;
+      uint32_t* cnt = p.tile_counts + (size_t)vc.tile_base * S;
       const uint32_t gx = (uint32_t)vc.grid_x;
-      for_each_tile(rx0, ry0, rx1, tiles, 0u, lane,
-                    [&](uint32_t tx, uint32_t ty, uint32_t) { atomicAdd(cnt + ty * gx + tx, 1u); });
+      for_each_tile(rx0, ry0, rx1, tiles, (uint32_t)idx & (S - 1u), lane,
+                    [&](uint32_t tx, uint32_t ty, uint32_t sub) { atomicAdd(cnt + (ty * gx + tx) * S + sub, 1u); });
     }
 
     if (alive) {

@@ -137,6 +137,50 @@ __device__ __forceinline__ void sh_coef_grad(int deg, int M, float x, float y, f
   }
 }
 
+// computeCov3D backward (backward.cu:399-462): dL/dscale and dL/drot from dL/dSigma (6 upper-tri
+// floats), ADDED to ds / dq.  Applied per view (the reference's arithmetic for every call), the
+// views' results then add like the reference's separate calls add in AccumulateGrad.
+__device__ __forceinline__ void cov3d_backward(const float* dcov, const float4* rotation,
+                                               const float* scale, float mod, float* ds, float4& dq) {
+  // loaded here, per view (L1 hits), rather than kept live across the view loop
+  const float4 q = __ldg(rotation);
+  const float sx = mod * __ldg(scale + 0), sy = mod * __ldg(scale + 1), sz = mod * __ldg(scale + 2);
+  const float r = q.x, x = q.y, y = q.z, z = q.w;
+  // R[c][r] as filled column by column by glm::mat3(...)
+  const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
+  const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
+  const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
+  // M = S * R : M[c][r] = s_r * R[c][r]
+  const float M00 = sx * R00, M01 = sy * R01, M02 = sz * R02;
+  const float M10 = sx * R10, M11 = sy * R11, M12 = sz * R12;
+  const float M20 = sx * R20, M21 = sy * R21, M22 = sz * R22;
+  // dL_dSigma (symmetric), columns
+  const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2];
+  const float S11 = dcov[3], S12 = 0.5f * dcov[4], S22 = dcov[5];
+  // dL_dM = 2 * M * dL_dSigma ; (A*B)[c][r] = sum_k A[k][r] * B[c][k]
+  const float D00 = 2.f * (M00 * S00 + M10 * S01 + M20 * S02);
+  const float D01 = 2.f * (M01 * S00 + M11 * S01 + M21 * S02);
+  const float D02 = 2.f * (M02 * S00 + M12 * S01 + M22 * S02);
+  const float D10 = 2.f * (M00 * S01 + M10 * S11 + M20 * S12);
+  const float D11 = 2.f * (M01 * S01 + M11 * S11 + M21 * S12);
+  const float D12 = 2.f * (M02 * S01 + M12 * S11 + M22 * S12);
+  const float D20 = 2.f * (M00 * S02 + M10 * S12 + M20 * S22);
+  const float D21 = 2.f * (M01 * S02 + M11 * S12 + M21 * S22);
+  const float D22 = 2.f * (M02 * S02 + M12 * S12 + M22 * S22);
+  // Rt[i] = (R[0][i], R[1][i], R[2][i]); dL_dMt[i] = (D[0][i], D[1][i], D[2][i])
+  ds[0] += R00 * D00 + R10 * D10 + R20 * D20;
+  ds[1] += R01 * D01 + R11 * D11 + R21 * D21;
+  ds[2] += R02 * D02 + R12 * D12 + R22 * D22;
+  // dL_dMt[i] *= s_i ; Mt[i][j] = D[j][i] * s_i
+  const float t00 = D00 * sx, t01 = D10 * sx, t02 = D20 * sx;
+  const float t10 = D01 * sy, t11 = D11 * sy, t12 = D21 * sy;
+  const float t20 = D02 * sz, t21 = D12 * sz, t22 = D22 * sz;
+  dq.x += 2 * z * (t01 - t10) + 2 * y * (t20 - t02) + 2 * x * (t12 - t21);
+  dq.y += 2 * y * (t10 + t01) + 2 * z * (t20 + t02) + 2 * r * (t12 - t21) - 4 * x * (t22 + t11);
+  dq.z += 2 * x * (t10 + t01) + 2 * r * (t20 - t02) + 2 * z * (t12 + t21) - 4 * y * (t22 + t00);
+  dq.w += 2 * r * (t01 - t10) + 2 * x * (t20 + t02) + 2 * y * (t12 + t21) - 4 * z * (t11 + t00);
+}
+
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
   v = warp_sum(v);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -164,8 +208,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 //      in); every view first takes its direction derivative from the row, then the row is
 //      overwritten in place by the sum over views of basis(dir_v) x g_v and streamed out coalesced
 //      as dL_dsh / dL_dsh_p;
-//   3. depth / ndc, 4. cov2D backward, 5. projection per view; 6. cov3D -> scale, rotation once,
-//      from the summed dL_dcov3D (that step is linear in it).
+//   3. depth / ndc, 4. cov2D backward, 5. projection, 6. cov3D -> scale, rotation, per view.
 template <int ACC, int MINB>
 __global__ void __launch_bounds__(GFT_BLOCK, MINB)
 preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
@@ -388,13 +431,10 @@ preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
   // ---------------- 3.-5. geometry per view ----------------------------------------------------
   float dopac = 0.f;
   float dcol_sum[3] = {0.f, 0.f, 0.f};
-  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f;
-  if (vis) {
-    const float* c3 = p.cov3D + 6 * (size_t)idx;
-    v0 = __ldg(c3 + 0); v1 = __ldg(c3 + 1); v2 = __ldg(c3 + 2);
-    v3 = __ldg(c3 + 3); v4 = __ldg(c3 + 4); v5 = __ldg(c3 + 5);
-  }
+  bool first_vis = true;    // dL_dcov3D / dL_dcolors rows: first visible view stores, later ones add
+  float ds[3] = {0.f, 0.f, 0.f};
+  float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+
   for (int v = 0; v < p.nviews; ++v) {
     const ViewCam& vc = p.views[v];
     if (!in_range) continue;
@@ -467,7 +507,10 @@ preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
     const float T10 = V[1] * J11 + V[2] * J12;
     const float T11 = V[5] * J11 + V[6] * J12;
     const float T12 = V[9] * J11 + V[10] * J12;
-    // cov2D = T^T * Vrk^T * T, upper 2x2
+    // cov2D = T^T * Vrk^T * T, upper 2x2 (the 3D covariance is re-read per view: L1 hits)
+    const float* c3 = p.cov3D + 6 * (size_t)idx;
+    const float v0 = __ldg(c3 + 0), v1 = __ldg(c3 + 1), v2 = __ldg(c3 + 2), v3 = __ldg(c3 + 3),
+                v4 = __ldg(c3 + 4), v5 = __ldg(c3 + 5);
     const float B00 = T00 * v0 + T01 * v1 + T02 * v2;  // (Vrk * T[0]) rows
     const float B01 = T00 * v1 + T01 * v3 + T02 * v4;
     const float B02 = T00 * v2 + T01 * v4 + T02 * v5;
@@ -481,17 +524,30 @@ preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
     const float denom = a * c - b * b;
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (denom2inv != 0) {
       dL_da = denom2inv * (-c * c * dcon_x + 2 * b * c * dcon_y + (denom - a * c) * dcon_w);
       dL_dc = denom2inv * (-a * a * dcon_w + 2 * a * b * dcon_y + (denom - a * c) * dcon_x);
       dL_db = denom2inv * 2 * (b * c * dcon_x - (denom + 2 * b * b) * dcon_y + a * b * dcon_w);
-      dcov[0] += (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
-      dcov[3] += (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
-      dcov[5] += (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
-      dcov[1] += 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
-      dcov[2] += 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
-      dcov[4] += 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
+      dcov[0] = (T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc);
+      dcov[3] = (T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc);
+      dcov[5] = (T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc);
+      dcov[1] = 2 * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2 * T10 * T11 * dL_dc;
+      dcov[2] = 2 * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2 * T10 * T12 * dL_dc;
+      dcov[4] = 2 * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2 * T11 * T12 * dL_dc;
     }
+    if (p.dL_dcov3D) {     // gradient of cov3D_precomp (rare path): accumulated in place
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float* o = p.dL_dcov3D + 6 * (size_t)idx + k;
+        *o = first_vis ? dcov[k] : *o + dcov[k];
+      }
+    }
+    first_vis = false;
+    // ---------------- 6. cov3D -> scale, rotation of this view (backward.cu:399-462) -----------
+    if (p.scales != nullptr)
+      cov3d_backward(dcov, reinterpret_cast<const float4*>(p.rotations) + idx, p.scales + 3 * (size_t)idx,
+                     p.scale_modifier, ds, dq);
 
     // dL/dT (backward.cu:358-369): B0* = T[0]-row products with Vrk, B1* likewise
     const float dL_dT00 = 2 * B00 * dL_da + B10 * dL_db;
@@ -536,52 +592,11 @@ preprocess_bwd_kernel(const __grid_constant__ PreprocessBwdParams p) {
     acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 1, dmy);
     acc_store<ACC>(p.dL_dmeans3D + 3 * (size_t)idx + 2, dmz);
     if (p.dL_dcolors) for (int k = 0; k < 3; ++k) p.dL_dcolors[3 * (size_t)idx + k] = dcol_sum[k];
-    if (p.dL_dcov3D) for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
 
-    // ---------------- 6. cov3D -> scale, rotation (backward.cu:399-462) ----------------------
     if (p.scales != nullptr) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
-      const float r = q.x, x = q.y, y = q.z, z = q.w;
-      const float sx = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 0);
-      const float sy = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 1);
-      const float sz = p.scale_modifier * __ldg(p.scales + 3 * (size_t)idx + 2);
-      // R[c][r] as filled column by column by glm::mat3(...)
-      const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
-      const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
-      const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
-      // M = S * R : M[c][r] = s_r * R[c][r]
-      const float M00 = sx * R00, M01 = sy * R01, M02 = sz * R02;
-      const float M10 = sx * R10, M11 = sy * R11, M12 = sz * R12;
-      const float M20 = sx * R20, M21 = sy * R21, M22 = sz * R22;
-      // dL_dSigma (symmetric), columns
-      const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2];
-      const float S11 = dcov[3], S12 = 0.5f * dcov[4], S22 = dcov[5];
-      // dL_dM = 2 * M * dL_dSigma ; (A*B)[c][r] = sum_k A[k][r] * B[c][k]
-      const float D00 = 2.f * (M00 * S00 + M10 * S01 + M20 * S02);
-      const float D01 = 2.f * (M01 * S00 + M11 * S01 + M21 * S02);
-      const float D02 = 2.f * (M02 * S00 + M12 * S01 + M22 * S02);
-      const float D10 = 2.f * (M00 * S01 + M10 * S11 + M20 * S12);
-      const float D11 = 2.f * (M01 * S01 + M11 * S11 + M21 * S12);
-      const float D12 = 2.f * (M02 * S01 + M12 * S11 + M22 * S12);
-      const float D20 = 2.f * (M00 * S02 + M10 * S12 + M20 * S22);
-      const float D21 = 2.f * (M01 * S02 + M11 * S12 + M21 * S22);
-      const float D22 = 2.f * (M02 * S02 + M12 * S12 + M22 * S22);
-      // Rt[i] = (R[0][i], R[1][i], R[2][i]); dL_dMt[i] = (D[0][i], D[1][i], D[2][i])
-      const float ds_x = R00 * D00 + R10 * D10 + R20 * D20;
-      const float ds_y = R01 * D01 + R11 * D11 + R21 * D21;
-      const float ds_z = R02 * D02 + R12 * D12 + R22 * D22;
-      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 0, ds_x);
-      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 1, ds_y);
-      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 2, ds_z);
-      // dL_dMt[i] *= s_i ; Mt[i][j] = D[j][i] * s_i
-      const float t00 = D00 * sx, t01 = D10 * sx, t02 = D20 * sx;
-      const float t10 = D01 * sy, t11 = D11 * sy, t12 = D21 * sy;
-      const float t20 = D02 * sz, t21 = D12 * sz, t22 = D22 * sz;
-      float4 dq;
-      dq.x = 2 * z * (t01 - t10) + 2 * y * (t20 - t02) + 2 * x * (t12 - t21);
-      dq.y = 2 * y * (t10 + t01) + 2 * z * (t20 + t02) + 2 * r * (t12 - t21) - 4 * x * (t22 + t11);
-      dq.z = 2 * x * (t10 + t01) + 2 * r * (t20 - t02) + 2 * z * (t12 + t21) - 4 * y * (t22 + t00);
-      dq.w = 2 * r * (t01 - t10) + 2 * x * (t20 + t02) + 2 * y * (t12 + t21) - 4 * z * (t11 + t00);
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 0, ds[0]);
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 1, ds[1]);
+      acc_store<ACC>(p.dL_dscales + 3 * (size_t)idx + 2, ds[2]);
       float4* dq_out = reinterpret_cast<float4*>(p.dL_drotations) + idx;
       if (ACC == 2) {
         atomicAdd(dq_out, dq);          // RED.E.ADD.F32x4
@@ -631,8 +646,8 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
   if (p.P <= 0) return;
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
-  // MINB = 4 (64 registers, a few spilled words) or 3 (80 registers, no spills): option pbwd_minb
-  const bool four = option(OPT_PBWD_MINB) != 3;
+  // MINB = 3 (80 registers, no spills; default) or 4 (64 registers, 100 B spilled): option pbwd_minb
+  const bool four = option(OPT_PBWD_MINB) == 4;
   auto go = [&](auto kernel, unsigned long long* ok) {
     ensure_dynamic_smem(kernel, smem, ok);
     kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);

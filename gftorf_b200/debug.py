@@ -25,7 +25,8 @@ def decode_views(geom, binning, img, P, R, sizes):
     tiles = [((w + 15) // 16) * ((h + 15) // 16) for w, h in sizes]
     T_total, N_total = sum(tiles), sum(w * h for w, h in sizes)
     all_ranges = v(img, lay.img_ranges, 8 * T_total, torch.int32).view(T_total, 2)
-    all_counts = v(img, lay.img_tile_counts, 4 * T_total, torch.int32)
+    S = int(lay.img_sub_bins)
+    all_counts = v(img, lay.img_tile_counts, 4 * T_total * S, torch.int32).view(T_total, S).sum(1, dtype=torch.int32)
     all_state = v(img, lay.img_state, 16 * N_total, torch.float32).view(N_total, 4)
     if R > 0:
         entries = v(binning, lay.bin_entries, 8 * R, torch.int64)

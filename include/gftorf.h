@@ -342,7 +342,8 @@ typedef struct GftWorkspaceLayout {
   size_t bin_total;
   /* image workspace: tiles and pixels of the views back to back */
   size_t img_hdr;             /* uint32[4]: word 1 = num_rendered */
-  size_t img_tile_counts;     /* uint32[T_total] instances per tile */
+  size_t img_sub_bins;        /* S: sub-counters per tile (a number, not an offset) */
+  size_t img_tile_counts;     /* uint32[T_total][S] instances per tile, split by Gaussian id mod S */
   size_t img_ranges;          /* uint2[T_total] */
   size_t img_state;           /* float4[N_total]: final_T, w_z_total, w_z2_total, bits(n_contrib) */
   size_t img_total;
@@ -363,7 +364,8 @@ void gft_profile_enable(int on);
 int gft_profile_read(float* ms, const char** names, int cap);
 unsigned long long gft_launch_count(void);
 
-/* Tunables / A-B switches of the kernels ("sort_cap", "bwd_pred", "pbwd_minb", "no_cull"; defaults
+/* Tunables / A-B switches of the kernels ("sort_cap", "sort_radix", "sub_bins", "bwd_pred",
+ * "pbwd_minb", "no_cull"; defaults
  * come from the environment variables GFT_SORT_CAP, ... read once).  Returns the previous value,
  * <0 for an unknown name.  Results never depend on them, only speed. */
 int gft_set_option(const char* name, int value);

@@ -90,7 +90,11 @@ def test_backward_vs_reference_kernels(name):
             continue
         err = float((ob[i].double() - rb[i].double()).norm())
         refn = float(rb[i].double().norm())
-        assert err <= harness.GRAD_REL_L2 * max(refn, 1e-3 * scale), (k, err, refn)
+        # the two scalar offsets are single float32 sums over all Gaussians of signed terms, which
+        # the reference accumulates with one atomic per Gaussian in arbitrary order
+        # (backward.cu:556,567): their own run-to-run spread is a few 1e-4 on large clouds
+        tol = 1e-3 if k in ("phase_offset", "dc_offset") else harness.GRAD_REL_L2
+        assert err <= tol * max(refn, 1e-3 * scale), (k, err, refn)
 
 
 @needs_ref
@@ -437,18 +441,50 @@ def test_tile_sort_paths_agree_bitwise(name):
     from gftorf_b200 import _capi
     inp = harness.build_inputs(device="cuda", **CASES[name])
     outs = {}
-    for cap in (0, 256, 1024, 16384):
+    configs = [(0, 1), (256, 1), (1024, 1), (8192, 1), (0, 0), (256, 0)]     # (sort_cap, sort_radix)
+    for cap, radix in configs:
         old = _capi.set_option("sort_cap", cap)
+        old_r = _capi.set_option("sort_radix", radix)
         try:
             f = harness.call_forward(rasterizer._C, inp)
             d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
-            outs[cap] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone(), f[2].clone())
+            outs[(cap, radix)] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone(), f[2].clone())
         finally:
             _capi.set_option("sort_cap", old)
-    assert int(debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])["tile_counts"].max()) > 256
-    for cap in (256, 1024, 16384):
-        for a, b in zip(outs[0], outs[cap]):
-            assert torch.equal(a, b), cap
+            _capi.set_option("sort_radix", old_r)
+    assert int(d["tile_counts"].max()) > 256
+    for cfg in configs[1:]:
+        for a, b in zip(outs[configs[0]], outs[cfg]):
+            assert torch.equal(a, b), cfg
+
+
+def test_equal_depths_keep_ascending_index_order():
+    """Gaussians at EXACTLY the same view depth: the reference's stable sort lists them in
+    ascending index order inside every tile; the tile sort must too (its radix passes see only the
+    depth bits, the slots come from atomics — the tie check has to catch it)."""
+    inp = harness.build_inputs(device="cuda", P=6000, W=160, H=120, kind="trained", seed=81, sigma_px=4.0)
+    m = inp["means3D"].clone()
+    m[:, 2] = torch.where(torch.arange(6000, device="cuda") % 3 == 0, torch.full_like(m[:, 2], 2.0), m[:, 2])
+    inp["means3D"] = m                      # identity camera: view z = world z
+    for radix in (1, 0):
+        from gftorf_b200 import _capi
+        old = _capi.set_option("sort_radix", radix)
+        try:
+            f = harness.call_forward(rasterizer._C, inp)
+        finally:
+            _capi.set_option("sort_radix", old)
+        d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
+        k = d["keys"]
+        same = k[1:] == k[:-1]
+        assert int(same.sum()) > 1000
+        assert bool((k[1:] >= k[:-1]).all())
+        assert bool((d["point_list"][1:][same] > d["point_list"][:-1][same]).all())
+        if ref_driver.available():
+            ref = harness.call_forward(ref_driver.RefModule, inp)
+            rd = ref_driver.decode_buffers(ref[12], ref[13], ref[14], inp["P"], ref[0], inp["W"], inp["H"])
+            assert torch.equal(d["point_list"], rd["point_list"])
+            for i in range(1, 12):
+                assert torch.equal(f[i], ref[i]), harness.FWD_NAMES[i]
 
 
 def test_subtile_culling_is_exact():
