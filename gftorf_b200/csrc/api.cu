@@ -217,6 +217,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"no_cull", "GFT_NO_CULL", 0},       // 1: no sub-tile culling extents
     {"sort_radix", "GFT_SORT_RADIX", 1}, // 0: bitonic network instead of the shared-memory radix sort per tile
     {"sub_bins", "GFT_SUB_BINS", 16},    // sub-counters per tile of the binning (power of two, <= 16)
+    {"sort_match", "GFT_SORT_MATCH", 0}, // 1: MATCH.ANY instead of eight ballots for the radix ranking
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};

@@ -50,18 +50,24 @@ tile_scan_kernel(const uint32_t* __restrict__ counts, int T, int S, uint32_t cap
   const int n = T * S;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  // chunks of SCAN_THREADS*4 counters: every thread owns 4 consecutive ones
-  for (int base = 0; base < n; base += SCAN_THREADS * 4) {
-    const int i0 = base + (int)tid * 4;
-    uint32_t c[4];
-    if (i0 + 3 < n) {
-      const uint4 q = *reinterpret_cast<const uint4*>(counts + i0);
-      c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
-    } else {
+  // chunks of SCAN_THREADS*16 counters: every thread owns 16 consecutive ones (four 16-byte loads)
+  constexpr int PER = 16;
+  for (int base = 0; base < n; base += SCAN_THREADS * PER) {
+    const int i0 = base + (int)tid * PER;
+    uint32_t c[PER];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
+    for (int q = 0; q < PER / 4; ++q) {
+      if (i0 + 4 * q + 3 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(counts + i0 + 4 * q);
+        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[4 * q + k] = (i0 + 4 * q + k < n) ? counts[i0 + 4 * q + k] : 0u;
+      }
     }
-    const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) mine += c[k];
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -79,7 +85,7 @@ tile_scan_kernel(const uint32_t* __restrict__ counts, int T, int S, uint32_t cap
     }
     uint32_t x = s_carry + wbase + incl - mine;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < PER; ++k) {
       if (i0 + k < n) {
         starts[i0 + k] = min(x, capacity);
         cursors[i0 + k] = 0u;
@@ -144,21 +150,24 @@ __device__ __forceinline__ void ce_shared(u64* s, uint32_t a, uint32_t b) {
   if (x > y) { s[a] = y; s[b] = x; }
 }
 
-// all stages of distance < min(cap, k) of level k on the shared chunk s[0, len)
+// all stages of distance < min(cap, k) of level k on the shared chunk s[0, len); k and every
+// distance j are powers of two, so the index arithmetic is shifts and masks (a division by a
+// run-time value costs ~25 instructions and made this network instruction-bound)
 __device__ __forceinline__ void level_in_shared(u64* s, uint32_t len, uint32_t k, bool with_flip,
                                                 uint32_t pairs) {
   if (with_flip) {
-    const uint32_t half = k >> 1;
+    const uint32_t half = k >> 1, lh = 31u - __clz(half);
     for (uint32_t t = threadIdx.x; t < pairs; t += SORT_THREADS) {
-      const uint32_t lo = t & (half - 1), blk = t / half;
-      const uint32_t a = blk * k + lo, b = blk * k + (k - 1u - lo);
+      const uint32_t lo = t & (half - 1), base = (t >> lh) << (lh + 1);
+      const uint32_t a = base + lo, b = base + (k - 1u - lo);
       if (b < len) ce_shared(s, a, b);
     }
     __syncthreads();
   }
   for (uint32_t j = with_flip ? (k >> 2) : (k >> 1); j > 0; j >>= 1) {
+    const uint32_t lj = 31u - __clz(j);
     for (uint32_t t = threadIdx.x; t < pairs; t += SORT_THREADS) {
-      const uint32_t a = ((t / j) * (j << 1)) + (t & (j - 1)), b = a + j;
+      const uint32_t a = ((t >> lj) << (lj + 1)) + (t & (j - 1)), b = a + j;
       if (b < len) ce_shared(s, a, b);
     }
     __syncthreads();
@@ -175,6 +184,7 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
 // current order (stability): per pass a per-warp digit histogram (shared-memory atomics), an
 // exclusive scan over (digit, warp), then every 32-entry row is ranked with match_any against the
 // warp's running digit offsets and scattered into the other buffer.
+template <bool HW_MATCH>
 __device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint32_t* s_hist,
                                                         uint32_t* s_wtot, uint32_t n) {
   constexpr int WARPS = SORT_THREADS / 32;
@@ -222,14 +232,14 @@ __device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint
       const bool ok = e < n;
       const u64 key = ok ? src[e] : 0ull;
       const uint32_t d = ok ? ((uint32_t)(key >> shift) & 0xffu) : 0x100u + lane;   // padding lanes match nobody
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit8(d, ok);
       const uint32_t leader = __ffs(peers) - 1;
       uint32_t old = 0;
       if (lane == leader && ok) {
         old = s_hist[warp * 256u + d];
         s_hist[warp * 256u + d] = old + __popc(peers);
       }
-      old = __shfl_sync(0xffffffffu, old, leader);
+      old = __shfl_sync(0xffffffffu, old, ok ? leader : lane);
       if (ok) dst[old + __popc(peers & ((1u << lane) - 1u))] = key;
       __syncwarp();
     }
@@ -258,7 +268,8 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
     if (use_radix && n > 32u) {
       u64* s_b = s + cap;
       uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_b + cap);
-      radix_depth_sort_shared(s, s_b, s_hist, s_wtot, n);
+      if (use_radix == 2) radix_depth_sort_shared<true>(s, s_b, s_hist, s_wtot, n);
+      else radix_depth_sort_shared<false>(s, s_b, s_hist, s_wtot, n);
       // equal depths must be in ascending index order; the slots came from atomics, so a tie may
       // be the wrong way round — then (and only then) the whole 64-bit entries are sorted
       int bad = 0;
@@ -288,10 +299,10 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
     __syncthreads();
   }
   for (uint32_t k = cap << 1; k <= m; k <<= 1) {
-    const uint32_t half = k >> 1;
+    const uint32_t half = k >> 1, lh = 31u - __clz(half);
     for (uint32_t t = tid; t < (m >> 1); t += SORT_THREADS) {       // flip, distance up to k-1
-      const uint32_t lo = t & (half - 1), blk = t / half;
-      const uint32_t a = blk * k + lo, b = blk * k + (k - 1u - lo);
+      const uint32_t lo = t & (half - 1), base = (t >> lh) << (lh + 1);
+      const uint32_t a = base + lo, b = base + (k - 1u - lo);
       if (b < n) {
         const u64 x = __ldcg(g + a), y = __ldcg(g + b);
         if (x > y) { g[a] = y; g[b] = x; }
@@ -299,8 +310,9 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
     }
     __syncthreads();
     for (uint32_t j = k >> 2; j >= cap; j >>= 1) {                    // half-cleaners across chunks
+      const uint32_t lj = 31u - __clz(j);
       for (uint32_t t = tid; t < (m >> 1); t += SORT_THREADS) {
-        const uint32_t a = ((t / j) * (j << 1)) + (t & (j - 1)), b = a + j;
+        const uint32_t a = ((t >> lj) << (lj + 1)) + (t & (j - 1)), b = a + j;
         if (b < n) {
           const u64 x = __ldcg(g + a), y = __ldcg(g + b);
           if (x > y) { g[a] = y; g[b] = x; }
@@ -346,7 +358,7 @@ void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entr
   // path on 4096-entry chunks.  Option sort_cap forces a capacity, sort_radix = 0 the bitonic
   // network everywhere (A/B runs, tests of the long-segment path).
   const int forced = option(OPT_SORT_CAP);
-  const int use_radix = option(OPT_SORT_RADIX) != 0;
+  const int use_radix = option(OPT_SORT_RADIX) != 0 ? (option(OPT_SORT_MATCH) != 0 ? 2 : 1) : 0;
   uint32_t cap = mean_len_hint > 700 ? 4096u : 2048u;
   if (forced == 256 || forced == 1024 || forced == 2048 || forced == 4096 || forced == 8192) cap = (uint32_t)forced;
   const int smem = use_radix ? (int)cap * 16 + 8 * 256 * 4 : (int)cap * 8;

@@ -239,6 +239,22 @@ __device__ __forceinline__ void for_each_tile(uint32_t rx0, uint32_t ry0, uint32
   }
 }
 
+// Lanes of the warp whose 8-bit digit equals this lane's, among the lanes with `ok` set: eight
+// ballots, one per digit bit (independent, pipelined: ~50 cycles).  The MATCH.ANY instruction
+// gives the same mask but its latency on sm_100 is ~1400 cycles (measured through the radix
+// passes: 16 rows of a 4096-pair tile took 12 us of a 14 us pass) — option sort_match = 1 selects
+// it for A/B runs.
+__device__ __forceinline__ uint32_t match_digit8(uint32_t d, bool ok) {
+  uint32_t m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
 // ---- warp-cooperative staging of per-Gaussian rows ------------------------------------------
 // The SH tensors are [P][ROW] row-major, so the rows of a warp's 32 consecutive Gaussians are one
 // contiguous chunk of global memory.  These helpers move the chunk between global memory (fully

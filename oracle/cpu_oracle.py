@@ -243,3 +243,14 @@ class OracleModule:
     rasterize_gaussians = staticmethod(rasterize_gaussians)
     rasterize_gaussians_backward = staticmethod(rasterize_gaussians_backward)
     mark_visible = staticmethod(mark_visible)
+
+
+def rasterize_autograd(asm, view, means2D=None):
+    """The reference's autograd Function over the CPU port (oracle/autograd_wrap.py)."""
+    from . import autograd_wrap
+    global _AUTOGRAD
+    try:
+        fn = _AUTOGRAD
+    except NameError:
+        fn = _AUTOGRAD = autograd_wrap.make(OracleModule)
+    return fn(asm, means2D, view)

@@ -217,6 +217,18 @@ class RefModule:
     mark_visible = staticmethod(mark_visible)
 
 
+_AUTOGRAD = None
+
+
+def rasterize_autograd(asm, means2D, view):
+    """The reference's autograd Function over the reference kernels (oracle/autograd_wrap.py)."""
+    from . import autograd_wrap
+    global _AUTOGRAD
+    if _AUTOGRAD is None:
+        _AUTOGRAD = autograd_wrap.make(RefModule)
+    return _AUTOGRAD(asm, means2D, view)
+
+
 def decode_buffers(geom, binning, img, P, R, W, H):
     """Typed views into the reference's opaque buffers, offsets from its own fromChunk walk
     (ref_layout in ref_shim.cu)."""

@@ -215,3 +215,51 @@ def densify_and_prune(params, exp_avg, exp_avg_sq, grad_accum, denom, max_grad, 
         mask = mask | (ws > 0.05 * extent) | (ws < 0.001 * extent)
     prune(mask)
     return p, m, v
+
+
+# ---- the deformation MLP (bench.py's CPU pipeline baseline) -----------------------------------------
+class DeformNetwork(torch.nn.Module):
+    """utils/time_utils.py:56-127: positional encodings of xyz (10 frequencies) and t (6), an
+    8-layer 256-wide ReLU MLP with a skip connection into layer 5, linear heads for d_xyz, d_rot
+    and the four 16-coefficient SH deltas.  As in the reference's forward (:126-127), d_rot and
+    the phase/amplitude SH deltas are returned as zeros; initialisation as initialize_weights
+    (:87-104) with xavier_init_dxyz off."""
+
+    def __init__(self, D=8, W=256, xyz_multires=10, t_multires=6, sh_degree=3):
+        super().__init__()
+        self.skips = [D // 2]
+        self.xf = 2.0 ** torch.linspace(0.0, xyz_multires - 1, xyz_multires)
+        self.tf = 2.0 ** torch.linspace(0.0, t_multires - 1, t_multires)
+        in_ch = 3 + 3 * 2 * xyz_multires + 1 + 2 * t_multires
+        self.linear = torch.nn.ModuleList(
+            [torch.nn.Linear(in_ch, W)] +
+            [torch.nn.Linear(W, W) if i not in self.skips else torch.nn.Linear(W + in_ch, W) for i in range(D - 1)])
+        n = (1 + sh_degree) ** 2
+        self.xyz_warp, self.rot = torch.nn.Linear(W, 3), torch.nn.Linear(W, 4)
+        self.r, self.g, self.b, self.a = (torch.nn.Linear(W, n) for _ in range(4))
+        for l in self.linear:
+            torch.nn.init.xavier_normal_(l.weight)
+            torch.nn.init.constant_(l.bias, 0.0)
+        for l in (self.xyz_warp, self.rot, self.r, self.g, self.b, self.a):
+            torch.nn.init.normal_(l.weight, mean=0.0, std=1e-5)
+            torch.nn.init.constant_(l.bias, 0.0)
+
+    @staticmethod
+    def _embed(x, freqs):
+        out = [x]
+        for f in freqs:
+            out += [torch.sin(x * f), torch.cos(x * f)]
+        return torch.cat(out, -1)
+
+    def forward(self, x, t):
+        emb = torch.cat([self._embed(x, self.xf), self._embed(t, self.tf)], dim=-1)
+        h = emb
+        for i, l in enumerate(self.linear):
+            h = F.relu(l(h))
+            if i in self.skips:
+                h = torch.cat([emb, h], -1)
+        d_xyz = self.xyz_warp(h)
+        d_sh = torch.stack([self.r(h), self.g(h), self.b(h)], dim=-1)
+        d_rot = torch.zeros_like(self.rot(h))
+        d_sh_p = torch.zeros(d_sh.shape[0], d_sh.shape[1], 2, dtype=d_sh.dtype, device=d_sh.device)
+        return d_xyz, d_rot, d_sh, d_sh_p
