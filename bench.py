@@ -155,84 +155,60 @@ def bwd_args(params, v, f, empty, zero3, zero1):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  Sampled in
-    process through NVML (two light queries every `interval_ms`); an external `nvidia-smi -lms`
-    loop, which round 1 used, takes the driver's global lock for its eight-field query and is the
-    prime suspect for the one 4-8 ms straggler step per run seen in SCALE_r01.  Falls back to
-    nvidia-smi only when NVML is not importable."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), through NVML, from
+    the timing thread itself: one sample right before every timed step's L2 flush, i.e. while the
+    GPU is under the load of the region but outside the step's own CUDA events.  (A background
+    poller — round 1 ran `nvidia-smi -lms`, an NVML thread was tried first this round — takes the
+    driver's lock under a kernel launch every now and then: one 2.7-8 ms straggler step per run in
+    SCALE_r01 and again with the NVML thread.)  Falls back to one nvidia-smi query after the region
+    when NVML is not importable."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4))
 
-    def __init__(self, index, interval_ms=50):
-        self.index, self.interval = index, interval_ms / 1e3
-        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.proc = [], [], set(), False, None, None
-        self.source = None
-
-    def start(self):
+    def __init__(self, index, every=1):
+        self.index, self.every, self.n = index, max(1, every), 0
+        self.sm, self.mx, self.reasons, self.nv, self.h = [], [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
-            self.source = "nvml"
-            self.thread = threading.Thread(target=self._loop, daemon=True)
-            self.thread.start()
         except Exception:
-            self._start_smi()
+            self.nv = None
 
-    def _loop(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for name, bit in self.REASONS:
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(self.interval)
-
-    def _start_smi(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def sample(self):
+        self.n += 1
+        if self.nv is None or (self.n % self.every):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
-            self.lines = []
-            self.thread = threading.Thread(target=lambda: [self.lines.append(l.strip()) for l in self.proc.stdout],
-                                           daemon=True)
-            self.thread.start()
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for name, bit in self.REASONS:
+                if r & bit:
+                    self.reasons.add(name)
         except Exception:
-            self.proc = None
+            pass
 
-    def stop(self):
-        self.stop_flag = True
-        if self.source == "nvidia-smi" and self.proc:
-            time.sleep(0.25)
-            self.proc.terminate()
-            for l in self.lines:
-                p = [x.strip() for x in l.split(",")]
-                if len(p) < 6:
-                    continue
-                try:
-                    self.sm.append(float(p[0])); self.mx.append(float(p[1]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
-                    if val.lower().startswith("active"):
-                        self.reasons.add(name)
-        elif self.thread is not None:
-            self.thread.join(timeout=1.0)
+    def result(self):
+        if self.nv is None:
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                p = [x.strip() for x in subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                    text=True, timeout=20).split(",")]
+                reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6])
+                           if v.lower().startswith("active")]
+                return {"sm_mhz": float(p[0]), "sm_max_mhz": float(p[1]), "reasons": reasons, "samples": 1,
+                        "source": "nvidia-smi, one query right after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": None}
         if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": self.source}
-        # median over the samples taken under load (an idle GPU parks at a few hundred MHz)
-        load = [x for x in self.sm if x >= 0.5 * max(self.sm)]
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": "nvml"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "sm_mhz_min": float(min(self.sm)), "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml, sampled by the timing thread before every timed step"}
 
 
 def stage_bytes(stage, P, V, R, N, T, nviews=1):
@@ -290,7 +266,7 @@ class Timer:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(self, step_fn, K, W, flush=True):
+    def run(self, step_fn, K, W, flush=True, sampler=None):
         for _ in range(W):
             step_fn()
         self.barrier()
@@ -300,6 +276,8 @@ class Timer:
         t0 = time.perf_counter()
         out = None
         for i in range(K):
+            if sampler is not None:
+                sampler.sample()               # clocks under load, outside the step's events
             if flush:
                 self.flush.zero_()             # 256 MiB > 126 MB L2, untimed
             evs[i][0].record()
@@ -448,17 +426,15 @@ def run_gpu(args, impl):
         return stats
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local, args.clock_interval_ms)
-    if rank == 0 and not args.no_clocks:
-        sampler.start()
-    for _ in range(W):        # launch counting starts after the first warm-up (smem attribute calls etc.)
+    sampler = ClockSampler(local, every=max(1, K // 64)) if (rank == 0 and not args.no_clocks) else None
+    for _ in range(W):        # launch counting starts after the warm-up (smem attribute calls etc.)
         step_resident()
     n0 = arm.capi.launch_count() if impl == "ours" else 0
-    total_ms, stats = timer.run(step_resident, K, 0)
+    total_ms, stats = timer.run(step_resident, K, 0, sampler=sampler)
     launches = (arm.capi.launch_count() - n0) if impl == "ours" else None
     step_ms = list(timer.steps_ms)
     wall_ms = timer.wall_ms
-    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
+    clocks = sampler.result() if sampler is not None else None
 
     # per-kernel durations: a second pass of the same steps with the library's stage events on
     stages, stage_steps = [], max(10, K // 4)
@@ -805,12 +781,13 @@ def c4_block(arm, impl, dev, timer, rank, world):
         if world > 1:
             bucket.allreduce() if impl == "ours" else arm.allreduce(params)
         return stats
-    K = 5 if impl == "ours" else 3
+    K = 6 if impl == "ours" else 4
     ms, stats = timer.run(step, K, 3)
     out = {"workload": "BASELINE configs[3]: 8 cameras x (1920x1080 colour + 640x480 ToF), 2M Gaussians, "
                        f"{len(mine)} camera(s) on this rank, fwd+bwd of all views + gradient allreduce",
            "scaling": "strong", "cameras_per_iter": 8, "n_gpus": world,
-           "ms_per_iter": round(ms / K, 3), "iter_ms_min_med_max": min_med_max(timer.steps_ms),
+           "ms_per_iter": round(ms / K, 3), "ms_per_iter_median": min_med_max(timer.steps_ms)[1],
+           "iter_ms_min_med_max": min_med_max(timer.steps_ms),
            "mpix_s": round(8 * (1920 * 1080 + 640 * 480) / 1e6 * K / (ms / 1e3), 2)}
     if rank == 0 and stats:
         Vs, Rs = view_stats(arm, stats, views)
@@ -1195,7 +1172,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-clocks", action="store_true", help="do not sample the clocks during the run")
-    ap.add_argument("--clock-interval-ms", type=int, default=50)
     ap.add_argument("--resident-only", action="store_true",
                     help="skip the e2e / render-only / block / cpu_baseline legs (for runs under ncu)")
     ap.add_argument("--blocks", default="all",

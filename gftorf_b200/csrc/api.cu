@@ -98,9 +98,10 @@ GeomWs geom_layout(int P, int V) {
   return g;
 }
 
-// image: header (word 1 = num_rendered) | sub-bin counters | cursors | starts | tile ranges | pixel state
+// image: header (word 0 = scan ticket, word 1 = num_rendered, bytes 256.. = scan chain state) |
+// sub-bin counters | cursors | starts | tile ranges | launch order | pixel state
 struct ImgWs {
-  size_t hdr, counts, cursors, starts, ranges, state, total;
+  size_t hdr, counts, cursors, starts, ranges, order, state, total;
   size_t T_total, N_total;
   int S;     // sub-counters per tile
 };
@@ -122,11 +123,12 @@ ImgWs img_layout(size_t T_total, size_t N_total) {
   const size_t nb = (T_total > 0 ? T_total : 1) * (size_t)m.S;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += up256(bytes); return o; };
-  m.hdr = take(256);
+  m.hdr = take(512);       // 16 header bytes + 32 x 8 B of scan state (n <= 131072 -> <= 32 scan blocks)
   m.counts = take(nb * 4);
   m.cursors = take(nb * 4);
   m.starts = take((nb + 1) * 4);
   m.ranges = take((T_total > 0 ? T_total : 1) * 8);
+  m.order = take((T_total > 0 ? T_total : 1) * 4);
   m.state = take((N_total > 0 ? N_total : 1) * 16);
   m.total = off;
   return m;
@@ -218,6 +220,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"sort_radix", "GFT_SORT_RADIX", 1}, // 0: bitonic network instead of the shared-memory radix sort per tile
     {"sub_bins", "GFT_SUB_BINS", 16},    // sub-counters per tile of the binning (power of two, <= 16)
     {"sort_match", "GFT_SORT_MATCH", 0}, // 1: MATCH.ANY instead of eight ballots for the radix ranking
+    {"tile_order", "GFT_TILE_ORDER", 1}, // 0: blend blocks in tile index order instead of longest list first
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};
@@ -396,8 +399,10 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
   uint32_t* cursors = reinterpret_cast<uint32_t*>(img + il.cursors);
   uint32_t* starts = reinterpret_cast<uint32_t*>(img + il.starts);
   uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
-  // header + sub-bin counters are adjacent: one fill
-  cudaMemsetAsync(hdr, 0, (il.counts - il.hdr) + T_total * (size_t)il.S * 4, stream);
+  uint32_t* order = reinterpret_cast<uint32_t*>(img + il.order);
+  unsigned long long* scan_state = reinterpret_cast<unsigned long long*>(img + il.hdr + 256);
+  // header + scan state + sub-bin counters + cursors are adjacent: one fill
+  cudaMemsetAsync(hdr, 0, il.starts - il.hdr, stream);
 
   gft::PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -430,7 +435,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
   // for the preprocess + scan kernels only.
   auto scan_and_post_R = [&](uint32_t cap) -> int {
     { Stage st("tile_scan", stream);
-      gft::launch_tile_scan(counts, (int)T_total, il.S, cap, starts, ranges, cursors, hdr, stream); }
+      gft::launch_tile_scan(counts, (int)T_total, il.S, cap, starts, ranges, order, hdr, scan_state, stream); }
     GFT_CUDA_OK("tile_scan");
     cudaError_t e = cudaMemcpyAsync(hs->pinned, d_R, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaEventRecord(hs->ev, stream);
@@ -466,6 +471,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
     std::memset(&bp, 0, sizeof(bp));
     bp.nviews = NV; bp.T_total = (int)T_total;
     bp.ranges = ranges; bp.point_list = point_list;
+    bp.order = gft::option(gft::OPT_TILE_ORDER) ? order : nullptr;
     bp.img_state = reinterpret_cast<float4*>(img + il.state);
     for (int i = 0; i < NV; ++i) {
       const GftViewArgs& v = a->views[i];
@@ -507,6 +513,8 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
     if (R > a->R_hint) {   // estimate too small: redo scan + binning + blend with the exact size
       for (int i = 0; i < NV; ++i)
         cudaMemsetAsync(a->views[i].pixels, 0, (size_t)P * sizeof(float), stream);
+      cudaMemsetAsync(hdr, 0, il.counts - il.hdr, stream);                 // ticket + scan state
+      cudaMemsetAsync(cursors, 0, T_total * (size_t)il.S * 4, stream);
       rc = scan_and_post_R(0xffffffffu);
       if (rc < 0) return rc;
       rc = bin_and_blend(R);
@@ -569,6 +577,7 @@ int gft_backward_views(const GftBackwardViewsArgs* a, gft_stream_t stream_) {
     std::memset(&bp, 0, sizeof(bp));
     bp.nviews = NV; bp.T_total = (int)T_total;
     bp.ranges = reinterpret_cast<const uint2*>(img + il.ranges);
+    bp.order = gft::option(gft::OPT_TILE_ORDER) ? reinterpret_cast<const uint32_t*>(img + il.order) : nullptr;
     bp.point_list = reinterpret_cast<const uint32_t*>(bin);  // sorted list: offset 0 of the workspace
     bp.img_state = reinterpret_cast<const float4*>(img + il.state);
     for (int i = 0; i < NV; ++i) {

@@ -35,75 +35,133 @@ namespace {
 typedef unsigned long long u64;
 
 constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;                       // one 16-byte load / store per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-// One block scans all sub-bin counters (n = T_total * S <= 131072, S chosen by the caller):
-// starts[i] = exclusive prefix (clamped to `capacity`), starts[n] = min(R, capacity), then
-// ranges[t] = (starts[t*S], starts[(t+1)*S]), with (0,0) for empty tiles — the reference's
-// memset + identifyTileRanges never touch those (rasterizer_impl.cu:118-140,341).
+// Exclusive scan of the n = T_total * S sub-bin counters into starts[0..n] (clamped to `capacity`),
+// R = starts[n] unclamped into hdr[1].  Single pass over ceil(n / 4096) blocks, chained with the
+// decoupled look-back; a block's place in the chain is its ticket (hdr[0]), not blockIdx, so the
+// look-back never waits for a block that has not started.  state[b] = flag << 32 | value with
+// flag 1 = block aggregate, 2 = inclusive prefix (one 64-bit word: relaxed accesses suffice).
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(const uint32_t* __restrict__ counts, int T, int S, uint32_t capacity,
-                 uint32_t* __restrict__ starts, uint2* __restrict__ ranges,
-                 uint32_t* __restrict__ cursors, uint32_t* __restrict__ hdr) {
+scan_starts_kernel(const uint32_t* __restrict__ counts, int n, uint32_t capacity,
+                   uint32_t* __restrict__ starts, uint32_t* __restrict__ hdr,
+                   unsigned long long* __restrict__ state) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_bid, s_prefix;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = T * S;
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) s_bid = atomicAdd(hdr, 1u);
   __syncthreads();
-  // chunks of SCAN_THREADS*16 counters: every thread owns 16 consecutive ones (four 16-byte loads)
-  constexpr int PER = 16;
-  for (int base = 0; base < n; base += SCAN_THREADS * PER) {
-    const int i0 = base + (int)tid * PER;
-    uint32_t c[PER];
+  const uint32_t bid = s_bid;
+  const int i0 = (int)bid * SCAN_TILE + (int)tid * SCAN_ITEMS;
+  uint32_t c[SCAN_ITEMS];
+  if (i0 + SCAN_ITEMS <= n) {
+    const uint4 q = *reinterpret_cast<const uint4*>(counts + i0);
+    c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+  } else {
 #pragma unroll
-    for (int q = 0; q < PER / 4; ++q) {
-      if (i0 + 4 * q + 3 < n) {
-        const uint4 v = *reinterpret_cast<const uint4*>(counts + i0 + 4 * q);
-        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c[4 * q + k] = (i0 + 4 * q + k < n) ? counts[i0 + 4 * q + k] : 0u;
-      }
-    }
-    uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) mine += c[k];
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t)o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-      const uint32_t t = s_warp[w];
-      if ((uint32_t)w < warp) wbase += t;
-      total += t;
-    }
-    uint32_t x = s_carry + wbase + incl - mine;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      if (i0 + k < n) {
-        starts[i0 + k] = min(x, capacity);
-        cursors[i0 + k] = 0u;
-        x += c[k];
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_carry += total;
-    __syncthreads();
+    for (int k = 0; k < SCAN_ITEMS; ++k) c[k] = (i0 + k < n) ? counts[i0 + k] : 0u;
   }
-  if (tid == 0) {
-    starts[n] = min(s_carry, capacity);
-    hdr[1] = s_carry;   // num_rendered
+  const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += v;
   }
-  __syncthreads();      // the block's own global writes are visible to it from here on
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if ((uint32_t)w < warp) wbase += t;
+    total += t;
+  }
+  if (warp == 0) {
+    uint32_t excl = 0;
+    if (bid == 0) {
+      if (lane == 0) st_release_u64(state, (2ull << 32) | total);
+    } else {
+      if (lane == 0) st_release_u64(state + bid, (1ull << 32) | total);
+      int base = (int)bid - 1;
+      while (true) {
+        const int j = base - (int)lane;
+        unsigned long long sv = 0;
+        if (j >= 0) {
+          do { sv = ld_acquire_u64(state + j); } while ((sv >> 32) == 0ull);
+        }
+        const uint32_t flag = j >= 0 ? (uint32_t)(sv >> 32) : 2u;   // virtual prefix 0 before block 0
+        const uint32_t val = j >= 0 ? (uint32_t)sv : 0u;
+        const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
+        const int first = __ffs(pmask) - 1;       // nearest predecessor that already owns a prefix
+        uint32_t v = (pmask == 0u || lane <= (uint32_t)first) ? val : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (pmask) break;
+        base -= 32;
+      }
+      if (lane == 0) st_release_u64(state + bid, (2ull << 32) | (unsigned long long)(excl + total));
+    }
+    if (lane == 0) s_prefix = excl;
+  }
+  __syncthreads();
+  uint32_t x = s_prefix + wbase + incl - mine;
+  uint32_t o4[SCAN_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { o4[k] = min(x, capacity); x += c[k]; }
+  if (i0 + SCAN_ITEMS <= n) {
+    *reinterpret_cast<uint4*>(starts + i0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (i0 + k < n) starts[i0 + k] = o4[k];
+  }
+  if (bid == gridDim.x - 1 && tid == 0) {
+    const uint32_t R = s_prefix + total;
+    starts[n] = min(R, capacity);
+    hdr[1] = R;   // num_rendered
+  }
+}
+
+// ranges[t] = (starts[t*S], starts[(t+1)*S]), with (0,0) for empty tiles — the reference's memset
+// + identifyTileRanges never touch those (rasterizer_impl.cu:118-140,341) — and the launch order of
+// the blend kernels.  One block: T <= 16 views x 8160 tiles.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_ranges_kernel(const uint32_t* __restrict__ starts, int T, int S, uint2* __restrict__ ranges,
+                   uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_bk[128];
+  const uint32_t tid = threadIdx.x;
+  // Launch order of the blend kernels: longest tile lists first.  A blend block's time is
+  // proportional to its tile's list length, the lists differ by 2-4x, and a grid is only ~5 blocks
+  // per resident slot deep, so in index order a long tile that starts late leaves most SMs idle at
+  // the end of the kernel.  128 buckets on a quarter-octave scale; the order inside a bucket is
+  // whatever the atomics give (it only decides which SM runs a tile, never a result).
+  auto bucket = [](uint32_t len) -> uint32_t {
+    if (len < 4u) return len;
+    const uint32_t e = 31u - __clz(len);
+    return min(127u, e * 4u + ((len >> (e - 2u)) & 3u));
+  };
+  if (tid < 128) s_bk[tid] = 0u;
+  __syncthreads();
   for (int t = tid; t < T; t += SCAN_THREADS) {
-    const uint32_t x = starts[t * S], y = starts[(t + 1) * S];
+    const uint32_t x = __ldg(starts + (size_t)t * S), y = __ldg(starts + (size_t)(t + 1) * S);
     ranges[t] = y > x ? make_uint2(x, y) : make_uint2(0u, 0u);
+    atomicAdd(&s_bk[bucket(y - x)], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int b = 127; b >= 0; --b) {
+      const uint32_t c = s_bk[b];
+      s_bk[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += SCAN_THREADS) {
+    const uint32_t x = __ldg(starts + (size_t)t * S), y = __ldg(starts + (size_t)(t + 1) * S);
+    order[atomicAdd(&s_bk[bucket(y - x)], 1u)] = (uint32_t)t;
   }
 }
 
@@ -335,11 +393,13 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
 }  // namespace
 
 void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
-                      uint32_t* starts, uint2* ranges, uint32_t* cursors, uint32_t* hdr,
-                      cudaStream_t stream) {
-  tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_counts, T_total, sub_bins, capacity, starts,
-                                                   ranges, cursors, hdr);
-  note_launches(1);
+                      uint32_t* starts, uint2* ranges, uint32_t* order, uint32_t* hdr,
+                      unsigned long long* scan_state, cudaStream_t stream) {
+  const int n = T_total * sub_bins;
+  scan_starts_kernel<<<(n + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, stream>>>(tile_counts, n, capacity, starts,
+                                                                                  hdr, scan_state);
+  tile_ranges_kernel<<<1, SCAN_THREADS, 0, stream>>>(starts, T_total, sub_bins, ranges, order);
+  note_launches(2);
 }
 
 void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,

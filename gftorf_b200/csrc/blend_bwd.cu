@@ -86,10 +86,11 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile_g = p.order ? __ldg(p.order + blockIdx.x) : blockIdx.x;   // longest lists first
   int vi = 0;
-  for (int v = 1; v < p.nviews; ++v) vi = ((int)blockIdx.x >= p.views[v].tile_base) ? v : vi;
+  for (int v = 1; v < p.nviews; ++v) vi = ((int)tile_g >= p.views[v].tile_base) ? v : vi;
   const BlendViewBwd& vw = p.views[vi];
-  const uint32_t tile = blockIdx.x - (uint32_t)vw.tile_base;
+  const uint32_t tile = tile_g - (uint32_t)vw.tile_base;
   const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
@@ -104,7 +105,7 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   const float4* __restrict__ recs = vw.rec;
   float* __restrict__ grad_rec = vw.grad_rec;
 
-  const uint2 range = p.ranges[blockIdx.x];
+  const uint2 range = p.ranges[tile_g];
   const int n = (int)(range.y - range.x);
 
   // ---- per-pixel forward state, incoming gradients and the constants derived from them ----

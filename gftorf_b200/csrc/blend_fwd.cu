@@ -62,10 +62,11 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpStage* ring = reinterpret_cast<WarpStage*>(fwd_smem_raw) + warp * WSTAGES;
   // the view this tile belongs to (uniform per block)
+  const uint32_t tile_g = p.order ? __ldg(p.order + blockIdx.x) : blockIdx.x;   // longest lists first
   int vi = 0;
-  for (int v = 1; v < p.nviews; ++v) vi = ((int)blockIdx.x >= p.views[v].tile_base) ? v : vi;
+  for (int v = 1; v < p.nviews; ++v) vi = ((int)tile_g >= p.views[v].tile_base) ? v : vi;
   const BlendViewFwd& vw = p.views[vi];
-  const uint32_t tile = blockIdx.x - (uint32_t)vw.tile_base;
+  const uint32_t tile = tile_g - (uint32_t)vw.tile_base;
   const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
@@ -79,7 +80,7 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
   const float4* __restrict__ recs = vw.rec;
   float* __restrict__ pixels = vw.pixels;
 
-  const uint2 range = p.ranges[blockIdx.x];
+  const uint2 range = p.ranges[tile_g];
   const int n = (int)(range.y - range.x);
   const int nb = (n + 31) >> 5;
 

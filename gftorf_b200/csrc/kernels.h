@@ -34,7 +34,7 @@ inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_ma
 int sm_count();
 
 // Tunables / A-B switches (gft_set_option in the C ABI; defaults from the environment, read once).
-enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_SORT_RADIX, OPT_SUB_BINS, OPT_SORT_MATCH, OPT_COUNT };
+enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_SORT_RADIX, OPT_SUB_BINS, OPT_SORT_MATCH, OPT_TILE_ORDER, OPT_COUNT };
 int option(int id);
 
 // Records the thread-local error string behind gft_last_error() and returns `code` (api.cu).
@@ -96,13 +96,15 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
                          float near_n, float far_n, cudaStream_t stream);
 
 // ---- binning: tile-segmented (binning.cu) ------------------------------------------------------
-// tile_counts [T_total][S] -> starts [T_total*S + 1] (exclusive scan), ranges (empty tiles read
-// (0,0) like the reference's memset + identifyTileRanges, rasterizer_impl.cu:118-140,341), the
-// instance count R in hdr[1], cursors zeroed.  Everything is clamped to `capacity` (only ever
-// effective when a caller's size hint was too small; the forward is then repeated exactly).
+// tile_counts [T_total][S] -> starts [T_total*S + 1] (exclusive scan, chained over blocks through
+// `scan_state`; hdr[0] is its ticket counter), ranges (empty tiles read (0,0) like the reference's
+// memset + identifyTileRanges, rasterizer_impl.cu:118-140,341), the instance count R in hdr[1] and
+// `order`, the global tile ids by descending list length (launch order of the blend kernels).
+// hdr, scan_state and the cursors must be zero on entry.  Everything is clamped to `capacity`
+// (only ever effective when a caller's size hint was too small; the forward is then repeated).
 void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
-                      uint32_t* starts, uint2* ranges, uint32_t* cursors, uint32_t* hdr,
-                      cudaStream_t stream);
+                      uint32_t* starts, uint2* ranges, uint32_t* order, uint32_t* hdr,
+                      unsigned long long* scan_state, cudaStream_t stream);
 // Every (view, Gaussian, tile) instance writes its entry (float_bits(view_z) << 32 | Gaussian id)
 // into its tile's segment, at a slot handed out by its sub-bin's atomic cursor (any order).
 void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
@@ -141,6 +143,7 @@ struct BlendViewFwd {
 };
 struct BlendFwdParams {
   int nviews, T_total;
+  const uint32_t* order;   // block b works on global tile order[b] (nullptr: b)
   const uint2* ranges;
   const uint32_t* point_list;
   float4* img_state;  // final_T, w_z_total, w_z2_total, n_contrib bits
@@ -163,6 +166,7 @@ struct BlendViewBwd {
 };
 struct BlendBwdParams {
   int nviews, T_total;
+  const uint32_t* order;
   const uint2* ranges;
   const uint32_t* point_list;
   const float4* img_state;

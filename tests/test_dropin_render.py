@@ -1,0 +1,206 @@
+"""The UNCHANGED reference render() / render_eval() (gaussian_renderer/__init__.py:19-139,206-300)
+and its GaussianModel getters, run on the GPU on top of the drop-in packages
+(gftorf_b200/dropin/diff_gaussian_rasterization_w_tof, .../simple_knn), against the same calls on
+top of the reference's OWN Python surface over the reference kernels (oracle/_ref as `_C`).
+
+The reference's Python is imported from /root/reference when that exists (the build container),
+otherwise from the bytecode oracle/build_pyref.py compiled from it into oracle/_ref/pyref (the GPU
+box, where the reference checkout is absent; no reference source is in the repo).  Every image the
+reference returns must be bit-identical, every leaf gradient (raw model parameters and the
+deformation deltas) within 1e-4 relative L2."""
+import importlib
+import importlib.util
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+from oracle import ref_driver
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+PYREF = os.path.join(ROOT, "oracle", "_ref", "pyref")
+RAST_SRC = os.path.join(REF, "submodules/diff-gaussian-rasterization-w-tof/diff_gaussian_rasterization_w_tof/__init__.py")
+
+
+def ref_root():
+    if os.path.exists(os.path.join(REF, "gaussian_renderer", "__init__.py")):
+        return REF
+    if os.path.exists(os.path.join(PYREF, "gaussian_renderer", "__init__.pyc")):
+        return PYREF
+    return None
+
+
+needs = pytest.mark.skipif(ref_root() is None or not ref_driver.available(),
+                           reason="neither /root/reference nor oracle/_ref/pyref + libgftorf_ref.so present")
+
+
+def reference_surface_over_ref_kernels():
+    """The reference's own diff_gaussian_rasterization_w_tof/__init__.py with `_C` = the reference
+    kernels (oracle/_ref through oracle/ref_driver.py)."""
+    name = "_ref_surface_gpu"
+    for k in [k for k in sys.modules if k.startswith(name)]:
+        del sys.modules[k]
+    path = RAST_SRC if os.path.exists(RAST_SRC) else os.path.join(PYREF, "ref_rasterizer_surface", "__init__.pyc")
+    spec = importlib.util.spec_from_file_location(name, path, submodule_search_locations=[])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    cmod = types.ModuleType(name + "._C")
+    cmod.rasterize_gaussians = ref_driver.RefModule.rasterize_gaussians
+    cmod.rasterize_gaussians_backward = ref_driver.RefModule.rasterize_gaussians_backward
+    cmod.mark_visible = ref_driver.RefModule.mark_visible
+    sys.modules[name + "._C"] = cmod
+    mod._C = cmod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def import_reference_renderer(rasterizer_pkg):
+    """A fresh import of the reference's gaussian_renderer with `diff_gaussian_rasterization_w_tof`
+    bound to `rasterizer_pkg` and `simple_knn` to our drop-in."""
+    root = ref_root()
+    for k in [k for k in sys.modules if k.split(".")[0] in ("gaussian_renderer", "scene", "utils", "arguments")]:
+        del sys.modules[k]
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    sys.modules.setdefault("cv2", types.ModuleType("cv2"))
+    ply = types.ModuleType("plyfile")
+    ply.PlyData = ply.PlyElement = object
+    sys.modules.setdefault("plyfile", ply)
+    dropin = os.path.join(ROOT, "gftorf_b200", "dropin")
+    if dropin not in sys.path:
+        sys.path.insert(0, dropin)
+    for k in [k for k in sys.modules if k.split(".")[0] in ("simple_knn", "diff_gaussian_rasterization_w_tof")]:
+        del sys.modules[k]
+    importlib.import_module("simple_knn._C")                 # our drop-in (distCUDA2)
+    scene = types.ModuleType("scene")                         # the package without its dataset loaders
+    scene.__path__ = [os.path.join(root, "scene")]
+    sys.modules["scene"] = scene
+    sys.modules["diff_gaussian_rasterization_w_tof"] = rasterizer_pkg
+    gr = importlib.import_module("gaussian_renderer")
+    gm = importlib.import_module("scene.gaussian_model")
+    return gr, gm.GaussianModel
+
+
+def build_model(GaussianModel, inp, frac_dynamic, seed):
+    import test_train_loop as tl
+    raw = tl.initial_model(inp)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    P = inp["P"]
+    pc = object.__new__(GaussianModel)
+    pc.isotropic = False
+    pc.use_view_dependent_phase = False
+    pc.active_sh_degree = 3
+    pc.setup_functions()
+    names = dict(xyz="_xyz", opacity="_opacity", scaling="_scaling", rotation="_rotation",
+                 f_dc_color="_features_dc_color", f_rest_color="_features_rest_color",
+                 phase_f_dc="_features_dc_phase", phase_f_rest="_features_rest_phase",
+                 amp_f_dc="_features_dc_amp", amp_f_rest="_features_rest_amp")
+    leaves = {}
+    for k, attr in names.items():
+        leaves[k] = torch.nn.Parameter(raw[k].clone())
+        setattr(pc, attr, leaves[k])
+    pc._features_seg_color = (torch.rand(P, 1, device="cuda", generator=g) < frac_dynamic).float()
+    Nd = int((pc._features_seg_color[:, 0] > 0.5).sum())
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    deltas = dict(d_xyz=(r(Nd, 3) * 0.01).requires_grad_(True), d_rot=(r(Nd, 4) * 0.02).requires_grad_(True),
+                  d_sh=(r(Nd, 16, 3) * 0.02).requires_grad_(True), d_sh_p=torch.zeros(Nd, 16, 2, device="cuda", requires_grad=True))
+    return pc, leaves, deltas
+
+
+def camera_namespace(cc, ct):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    fov = lambda tan: 2.0 * math.atan(tan)
+    return types.SimpleNamespace(
+        FoVx=fov(cc["tanfovx"]), FoVy=fov(cc["tanfovy"]), image_height=cc["height"], image_width=cc["width"],
+        world_view_transform=t(cc["viewmatrix"]), full_proj_transform=t(cc["projmatrix"]), camera_center=t(cc["campos"]),
+        znear=cc["znear"], zfar=cc["zfar"],
+        FoVx_tof=fov(ct["tanfovx"]), FoVy_tof=fov(ct["tanfovy"]), tof_image_height=ct["height"], tof_image_width=ct["width"],
+        world_view_transform_tof=t(ct["viewmatrix"]), full_proj_transform_tof=t(ct["projmatrix"]),
+        camera_center_tof=t(ct["campos"]), depth_range=torch.tensor(cc["depth_range"]),
+        phase_offset=torch.tensor(0.15), dc_offset=torch.tensor(0.05))
+
+
+def run_arm(rasterizer_pkg, inp, cam, weights, frac_dynamic):
+    gr, GaussianModel = import_reference_renderer(rasterizer_pkg)
+    pc, leaves, deltas = build_model(GaussianModel, inp, frac_dynamic, seed=5)
+    opt = types.SimpleNamespace(optimize_phase_offset=False, optimize_dc_offset=False)
+    pkg = gr.render(cam, pc, deltas["d_xyz"], deltas["d_rot"], deltas["d_sh"], deltas["d_sh_p"], None, opt, inp["bg"])
+    loss = sum((pkg[k] * w).sum() for k, w in weights.items())
+    loss.backward()
+    with torch.no_grad():
+        ev = {}
+        for tof in (False, True):
+            e = gr.render_eval(cam, pc, deltas["d_xyz"], deltas["d_rot"], deltas["d_sh"], deltas["d_sh_p"], inp["bg"], tof=tof)
+            ev.update({f"eval_{int(tof)}_{k}": v for k, v in e.items() if isinstance(v, torch.Tensor)})
+    grads = {k: v.grad.clone() for k, v in leaves.items()}
+    grads.update({k: v.grad.clone() for k, v in deltas.items() if v.grad is not None})
+    grads["viewspace_points"] = pkg["viewspace_points"].grad.clone()
+    outs = {k: v.detach().clone() for k, v in pkg.items() if isinstance(v, torch.Tensor) and k != "viewspace_points"}
+    outs.update({k: v.detach().clone() for k, v in ev.items()})
+    torch.cuda.synchronize()
+    return outs, grads
+
+
+@needs
+@pytest.mark.parametrize("frac_dynamic", [0.0, 0.3])
+def test_unchanged_reference_render_on_the_dropin_packages(frac_dynamic):
+    from gftorf_b200 import scenes
+    P, (Wc, Hc), (Wt, Ht) = 6000, (160, 120), (96, 72)
+    # zero higher-order phase/amplitude SH: keeps the reference's undefined dL_dPA
+    # out of the position gradient; its dL_dsh_p itself is compared on Gaussian 0 only
+    inp = harness.build_inputs(device="cuda", P=P, W=Wc, H=Hc, kind="trained", seed=91, sigma_px=2.5,
+                               depth_range=15.0, zero_shp_rest=True)
+    cc = scenes.make_camera(Wc, Hc, depth_range=15.0, seed=91)
+    ct = scenes.make_camera(Wt, Ht, depth_range=15.0, pose="orbit", seed=92)
+    cam = camera_namespace(cc, ct)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    weights = dict(render=torch.randn(3, Hc, Wc, device="cuda", generator=g),
+                   render_phasor=torch.randn(7, Ht, Wt, device="cuda", generator=g),
+                   render_depth=torch.randn(1, Ht, Wt, device="cuda", generator=g) * 0.1,
+                   render_depth_color=torch.randn(1, Hc, Wc, device="cuda", generator=g) * 0.1,
+                   render_acc=torch.randn(1, Ht, Wt, device="cuda", generator=g),
+                   depth_distortion_color=torch.randn(1, Hc, Wc, device="cuda", generator=g))
+
+    dropin = os.path.join(ROOT, "gftorf_b200", "dropin")
+    if dropin not in sys.path:
+        sys.path.insert(0, dropin)
+    for k in [k for k in sys.modules if k.split(".")[0] == "diff_gaussian_rasterization_w_tof"]:
+        del sys.modules[k]
+    ours_pkg = importlib.import_module("diff_gaussian_rasterization_w_tof")      # the drop-in package
+    assert ours_pkg.__file__.startswith(dropin)
+    outs_a, grads_a = run_arm(ours_pkg, inp, cam, weights, frac_dynamic)
+    outs_b, grads_b = run_arm(reference_surface_over_ref_kernels(), inp, cam, weights, frac_dynamic)
+
+    assert set(outs_a) == set(outs_b) and len(outs_a) >= 12
+    for k in outs_a:
+        assert outs_a[k].shape == outs_b[k].shape and outs_a[k].dtype == outs_b[k].dtype, k
+        assert torch.equal(outs_a[k], outs_b[k]), k
+    assert set(grads_a) == set(grads_b)
+    scale = float(grads_b["scaling"].double().norm())
+    for k in grads_a:
+        a, b = grads_a[k].double(), grads_b[k].double()
+        if k in ("phase_f_dc", "phase_f_rest", "amp_f_dc", "amp_f_rest", "d_sh_p"):
+            if k == "d_sh_p":
+                continue             # rows of dynamic Gaussians: undefined in the reference (D1)
+            a, b = a[0], b[0]        # the one row the reference defines
+        err = float((a - b).norm())
+        assert err <= harness.GRAD_REL_L2 * max(float(b.norm()), 1e-3 * scale), (k, err, float(b.norm()))
+    assert float(grads_a["viewspace_points"].abs().sum()) > 0
+
+
+@needs
+def test_dropin_distcuda2_is_what_the_reference_model_imports():
+    stub = types.ModuleType("diff_gaussian_rasterization_w_tof")
+    stub.GaussianRasterizationSettings = stub.GaussianRasterizer = object
+    _, GaussianModel = import_reference_renderer(stub)
+    gm = sys.modules["scene.gaussian_model"]
+    pts = torch.rand(5000, 3, device="cuda")
+    assert torch.equal(gm.distCUDA2(pts), ref_driver.distCUDA2(pts))
