@@ -48,10 +48,96 @@ __global__ void __launch_bounds__(256) nvls_allreduce_kernel(float4* __restrict_
   for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce_add(mc + i));
 }
 
+// ---- one kernel: cross-GPU barrier, reduce + broadcast of this rank's slice, cross-GPU barrier ----
+// The barriers run over the symmetric-memory signal pads (one 32-bit word per (block, peer) pair):
+// block b of rank r flips word [b][r] in every peer's pad from 0 to 1 (release, system scope) and
+// then flips the words [b][p] of its own pad back from 1 to 0 (acquire), i.e. it waits for block b
+// of every peer.  Barrier 1: a peer's block can only run when that peer's stream has finished
+// every earlier kernel, so its gradients are complete.  Barrier 2: block b of every rank has
+// stored its part; a rank's kernel ends when all its blocks have passed barrier 2, and every part
+// of the bucket belongs to some block index, so the whole bucket is complete when the kernel ends.
+// No host-launched barrier kernels around the exchange (they cost 2 x ~20 us of the 0.33 ms).
+__device__ __forceinline__ void put_signal(uint32_t* addr) {
+  uint32_t old;
+  long long spins = 0;
+  do {
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+    if (++spins > (1ll << 31)) __trap();     // a lost peer must not hang the GPU
+  } while (old != 0u);
+}
+__device__ __forceinline__ void wait_signal(uint32_t* addr) {
+  uint32_t old;
+  long long spins = 0;
+  do {
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+    if (++spins > (1ll << 31)) __trap();
+  } while (old != 1u);
+}
+__device__ __forceinline__ void peer_barrier(uint32_t* const* pads, uint32_t word0, int rank, int world) {
+  if ((int)threadIdx.x < world) {
+    const int peer = (int)threadIdx.x;
+    put_signal(pads[peer] + word0 + (size_t)blockIdx.x * world + rank);
+    wait_signal(pads[rank] + word0 + (size_t)blockIdx.x * world + peer);
+  }
+}
+
+template <int AR_UNROLL>
+__global__ void __launch_bounds__(512)
+nvls_allreduce_fused_kernel(float4* __restrict__ mc, long long begin, long long end,
+                            uint32_t* const* __restrict__ pads, uint32_t word0, int rank, int world) {
+  peer_barrier(pads, word0, rank, world);
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (AR_UNROLL - 1) * stride < end; i += AR_UNROLL * stride) {
+    float4 v[AR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) v[u] = mc_ld_reduce_add(mc + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) mc_st(mc + i + u * stride, v[u]);
+  }
+  for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce_add(mc + i));
+  __threadfence_system();      // this thread's multicast stores are performed everywhere ...
+  __syncthreads();             // ... for every thread of the block, before the block signals
+  peer_barrier(pads, word0, rank, world);
+}
+
 }  // namespace
 }  // namespace gft
 
 extern "C" {
+
+int gft_nvls_allreduce_fused(float* multicast_ptr, long long n_floats, int rank, int world,
+                             void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
+                             gft_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!multicast_ptr || !signal_pads_dev) return gft::set_error(-1, "gft_nvls_allreduce_fused: null pointer");
+  if (world <= 0 || world > 32 || rank < 0 || rank >= world) return gft::set_error(-1, "gft_nvls_allreduce_fused: bad rank / world");
+  if (n_floats < 0 || (n_floats & 3) || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
+    return gft::set_error(-1, "gft_nvls_allreduce_fused: length must be a multiple of 4 floats, pointer 16-byte aligned");
+  const long long total = n_floats >> 2;
+  const long long per = (total + world - 1) / world;
+  const long long begin = per * rank, end = begin + per < total ? begin + per : total;
+  // the upper half of every signal pad is ours (the lower half serves the host-side barriers)
+  const int word0 = pad_words / 2;
+  int max_blocks = (pad_words - word0) / world;
+  if (max_blocks < 1) return gft::set_error(-1, "gft_nvls_allreduce_fused: signal pad too small");
+  // EVERY rank must launch the same number of blocks (block b pairs with block b of its peers),
+  // so the count depends only on the arguments all ranks share
+  long long want = blocks > 0 ? blocks : (long long)gft::sm_count() * 2;
+  const long long need = (per + 512 - 1) / 512;
+  if (want > need) want = need > 0 ? need : 1;
+  if (want > max_blocks) want = max_blocks;
+  float4* mc = reinterpret_cast<float4*>(multicast_ptr);
+  uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads_dev);
+  if (unroll == 8) gft::nvls_allreduce_fused_kernel<8><<<(int)want, 512, 0, stream>>>(mc, begin, end > begin ? end : begin, pads, (uint32_t)word0, rank, world);
+  else if (unroll == 2) gft::nvls_allreduce_fused_kernel<2><<<(int)want, 512, 0, stream>>>(mc, begin, end > begin ? end : begin, pads, (uint32_t)word0, rank, world);
+  else gft::nvls_allreduce_fused_kernel<4><<<(int)want, 512, 0, stream>>>(mc, begin, end > begin ? end : begin, pads, (uint32_t)word0, rank, world);
+  gft::note_launches(1);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(e));
+  return 0;
+}
 
 int gft_nvls_allreduce_sum(float* multicast_ptr, long long n_floats, int rank, int world,
                            gft_stream_t stream_) {

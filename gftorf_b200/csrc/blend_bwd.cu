@@ -68,12 +68,58 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- ring mode: 16 slots of 32 Gaussians, one mbarrier pair per slot -----------------------------
+constexpr int RING_SLOTS = 16;
+constexpr int RING_LEAD = 8;     // a chunk is requested 8 chunks before its use; warp w requests chunks w, w+8, ...
+struct RingSlot {
+  float4 r0[32], r1[32], r2[32], r3[32], r4[32];
+  int id[32];
+};
+static_assert(RING_SLOTS * sizeof(RingSlot) == 2 * sizeof(BwdBufT<GFT_BLOCK>), "ring and double buffer share the staging area");
+
+__device__ __forceinline__ void cp_async4_ca(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared.b64 t, [%0]; }" ::"r"(a) : "memory");
+}
+// arrive-on triggered when all cp.async operations this thread issued before have landed
+__device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long* bar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 8000000000ll) __trap();   // seconds: a protocol error must not hang the GPU
+  }
+}
+
 }  // namespace
 
 // 8 warps = the eight 8x4 patches of one 16x16 tile (see blend_fwd.cu), BATCH = 256 Gaussians
 // staged per step (one per thread) into a double buffer.  One launch covers the tiles of all
 // views of the batch (global tile index = blockIdx.x).
-template <int MINB, bool PRED>
+// RING: instead of one double buffer of 256 Gaussians filled by the whole block between two
+// __syncthreads (ncu: 18 % of the warp samples wait there for the busiest warp of the tile), the
+// staging area is a ring of 16 slots x 32 Gaussians with a full / empty mbarrier pair per slot.
+// Warp w requests chunks w, w+8, ... eight chunks ahead of their use (cp.async, the slot's `full`
+// barrier fires when the 32 lanes' copies have landed) and every warp releases a slot when it is
+// done with it, so a warp only ever waits for a chunk that has not arrived or for the slowest
+// warp falling more than 8 chunks behind — never for the block.  Every wait depends on strictly
+// earlier chunks only, so the protocol cannot deadlock.
+template <int MINB, bool PRED, bool RING>
 __global__ void __launch_bounds__(GFT_BLOCK, MINB)
 blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   constexpr int WARPS = GFT_BLOCK / 32;
@@ -81,7 +127,9 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   using BwdBuf = BwdBufT<BATCH>;
   extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
   BwdBuf* buf = reinterpret_cast<BwdBuf*>(bwd_smem_raw);
+  RingSlot* ring = reinterpret_cast<RingSlot*>(bwd_smem_raw);
   __shared__ uint32_t s_wmax[WARPS];
+  __shared__ __align__(8) unsigned long long s_full[RING_SLOTS], s_empty[RING_SLOTS];
   // per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
   float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
 
@@ -159,6 +207,10 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
   if (lane == 0) s_wmax[warp] = wmax;
+  if (RING && tid < RING_SLOTS) {
+    mbar_init(&s_full[tid], 32);       // one arrive per lane of the requesting warp, when its copies land
+    mbar_init(&s_empty[tid], WARPS);   // one arrive per warp of the block, when it is done with the slot
+  }
   __syncthreads();
   uint32_t bmax = 0;
 #pragma unroll
@@ -189,7 +241,7 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   };
 
   // backward.cu:739-754 — the same alpha chain as the forward, so the same pairs are replayed
-  auto eval_pair = [&](const BwdBuf& s, int base, int k, float& G, float& alpha, float& dx,
+  auto eval_pair = [&](const auto& s, int base, int k, float& G, float& alpha, float& dx,
                        float& dy) -> bool {
     const float4 g0 = s.r0[k];
     const float4 g1 = s.r1[k];
@@ -202,7 +254,7 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
     return ((uint32_t)(base + k) < last_contributor) && neg && !(alpha < 1.0f / 255.0f);
   };
 
-  auto replay = [&](const BwdBuf& s, int k, bool contrib, float G, float alpha, float dx, float dy) {
+  auto replay = [&](const auto& s, int k, bool contrib, float G, float alpha, float dx, float dy) {
     if (!__any_sync(0xffffffffu, contrib)) return;
     float v[16];
     if (PRED) {
@@ -281,6 +333,67 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
       atomicAdd(grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane >> 1), sum);
   };
 
+  // one chunk of <= 32 candidates already in shared memory: cull against the warp's patch, replay
+  // the survivors back to front, two at a time (their alpha chains are independent of the pixel's
+  // running state and overlap; the replay itself stays sequential)
+  auto walk = [&](const auto& s, int base, int c, int m_w) {
+    const int jj = c + (int)lane;
+    bool hit = false;
+    if (jj < m_w) {
+      const float4 g0 = s.r0[jj];
+      hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
+              g0.y - g0.w > patch_y1);
+    }
+    uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    while (mask) {
+      const int s1 = 31 - __clz(mask);
+      mask &= ~(1u << s1);
+      const bool two = mask != 0u;
+      const int s2 = two ? (31 - __clz(mask)) : s1;
+      if (two) mask &= ~(1u << s2);
+      float G1, G2, al1, al2, dx1, dy1, dx2, dy2;
+      const bool c1 = eval_pair(s, base, c + s1, G1, al1, dx1, dy1);
+      const bool c2 = eval_pair(s, base, c + s2, G2, al2, dx2, dy2);
+      replay(s, c + s1, c1, G1, al1, dx1, dy1);
+      if (two) replay(s, c + s2, c2, G2, al2, dx2, dy2);
+    }
+  };
+
+  if (RING) {
+    const int nc = (n_eff + 31) >> 5;                 // chunks, processed from the last to the first
+    auto request = [&](int q) {                       // whole warp; sequence number q <-> chunk nc-1-q
+      const int slot = q % RING_SLOTS, fill = q / RING_SLOTS;
+      if (fill > 0) mbar_wait(&s_empty[slot], (uint32_t)(fill - 1) & 1u);   // every warp left the old contents
+      const int pos = (nc - 1 - q) * 32 + (int)lane;
+      if (pos < n_eff) {
+        const uint32_t* src = p.point_list + range.x + pos;
+        const int g = (int)__ldg(src);
+        const float4* r = recs + (size_t)g * (GFT_REC_FLOATS / 4);
+        RingSlot& d = ring[slot];
+        cp_async4_ca(&d.id[lane], src);
+        cp_async16(&d.r0[lane], r + 0);
+        cp_async16(&d.r1[lane], r + 1);
+        cp_async16(&d.r2[lane], r + 2);
+        cp_async16(&d.r3[lane], r + 3);
+        cp_async16(&d.r4[lane], r + 4);
+      }
+      mbar_arrive_on_copies(&s_full[slot]);
+    };
+    if ((int)warp < nc) request((int)warp);           // chunks 0..7 of the sequence
+    for (int q = 0; q < nc; ++q) {
+      const int ahead = q + RING_LEAD;
+      if (ahead < nc && (ahead & (WARPS - 1)) == (int)warp) request(ahead);
+      const int slot = q % RING_SLOTS;
+      mbar_wait(&s_full[slot], (uint32_t)(q / RING_SLOTS) & 1u);
+      const int base = (nc - 1 - q) * 32;
+      const int m_w = min(min(32, n_eff - base), (int)wmax - base);   // positions >= wmax: nothing for this warp
+      if (m_w > 0) walk(ring[slot], base, 0, m_w);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[slot]);
+    }
+    return;
+  }
+
   int cur = 0;
   if (nb > 0) stage(nb - 1, cur);
   for (int b = nb - 1; b >= 0; --b) {
@@ -291,43 +404,19 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
     const BwdBuf& s = buf[cur];
     const int base = b * BATCH;
     const int m = min(BATCH, n_eff - base);
-
     const int m_w = min(m, (int)wmax - base);  // positions >= wmax contribute nothing for this warp
-    for (int c = ((m_w - 1) >> 5) << 5; c >= 0 && m_w > 0; c -= 32) {
-      const int jj = c + (int)lane;
-      bool hit = false;
-      if (jj < m_w) {
-        const float4 g0 = s.r0[jj];
-        hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
-                g0.y - g0.w > patch_y1);
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        // two candidates per trip (back to front): their alpha chains are independent of the
-        // pixel's running state and overlap; the replay itself stays sequential
-        const int s1 = 31 - __clz(mask);
-        mask &= ~(1u << s1);
-        const bool two = mask != 0u;
-        const int s2 = two ? (31 - __clz(mask)) : s1;
-        if (two) mask &= ~(1u << s2);
-        float G1, G2, al1, al2, dx1, dy1, dx2, dy2;
-        const bool c1 = eval_pair(s, base, c + s1, G1, al1, dx1, dy1);
-        const bool c2 = eval_pair(s, base, c + s2, G2, al2, dx2, dy2);
-        replay(s, c + s1, c1, G1, al1, dx1, dy1);
-        if (two) replay(s, c + s2, c2, G2, al2, dx2, dy2);
-      }
-    }
+    for (int c = ((m_w - 1) >> 5) << 5; c >= 0 && m_w > 0; c -= 32) walk(s, base, c, m_w);
     cur ^= 1;
   }
 }
 
 namespace {
-template <int MINB, bool PRED>
+template <int MINB, bool PRED, bool RING>
 void launch_bwd_variant(const BlendBwdParams& p, cudaStream_t stream) {
   const int smem = 2 * (int)sizeof(BwdBufT<GFT_BLOCK>) + (GFT_BLOCK / 32) * RED_FLOATS * 4;
   static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_bwd_kernel<MINB, PRED>, smem, &smem_ok);
-  blend_bwd_kernel<MINB, PRED><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
+  ensure_dynamic_smem(blend_bwd_kernel<MINB, PRED, RING>, smem, &smem_ok);
+  blend_bwd_kernel<MINB, PRED, RING><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
 }
 }  // namespace
 
@@ -339,9 +428,15 @@ void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
   // block per SM (+4 %), replays with few contributing pixels sent straight to the record with
   // per-lane reductions (+4 %), a warp-autonomous variant like the forward's (+6 %), half-tile
   // blocks (+-1 %), the shuffle butterfly instead of the shared-memory transpose (+7 %).
-  // Option bwd_pred = 0 (GFT_BWD_PRED=0) selects the branchy replay for A/B runs.
-  if (option(OPT_BWD_PRED) != 0) launch_bwd_variant<3, true>(p, stream);
-  else launch_bwd_variant<3, false>(p, stream);
+  // Options bwd_pred = 0 (branchy replay) and bwd_ring (mbarrier ring vs block double buffer) for A/B runs.
+  const bool pred = option(OPT_BWD_PRED) != 0, ring = option(OPT_BWD_RING) != 0;
+  if (ring) {
+    if (pred) launch_bwd_variant<3, true, true>(p, stream);
+    else launch_bwd_variant<3, false, true>(p, stream);
+  } else {
+    if (pred) launch_bwd_variant<3, true, false>(p, stream);
+    else launch_bwd_variant<3, false, false>(p, stream);
+  }
   note_launches(1);
 }
 

@@ -110,7 +110,11 @@ class GradBucket:
     no pack or copy step between the last backward and the allreduce."""
 
     def __init__(self, params: Dict[str, torch.Tensor], scalars: Sequence[torch.Tensor] = (),
-                 symmetric: bool = False, group=None):
+                 symmetric=False, group=None):
+        """`symmetric`: False — an ordinary tensor, exchanged with NCCL; True — symmetric memory
+        bound to an NVLink multicast object, exchanged by the library's one-kernel NVLS allreduce
+        (`gft_nvls_allreduce_fused`); "auto" — symmetric memory, and `autotune()` (called here)
+        times NCCL against the NVLS kernels on this very buffer and keeps the fastest."""
         self.names = [n for n, _ in PARAM_LAYOUT if n in params]
         self.params = params
         self.scalars = list(scalars)
@@ -122,19 +126,30 @@ class GradBucket:
             cur += (n + 3) // 4 * 4  # 16-byte aligned slices
         self.sizes = sizes
         self._symm = None
+        self.mode = "nccl"
+        self.tuning = None
         if symmetric:
             self.flat = self._alloc_symmetric(cur, ref.device, group)
+            if self._symm is not None:
+                self.mode = "nvls_fused"
+                if symmetric == "auto":
+                    self.autotune(group)
         else:
             self.flat = torch.zeros(cur, dtype=torch.float32, device=ref.device)
 
     def _alloc_symmetric(self, n, device, group):
         """The bucket in symmetric memory bound to an NVLink multicast object, so the exchange can
-        run through the switch (`gft_nvls_allreduce_sum`).  Collective: every rank of `group` must
-        construct its bucket at the same point.  Falls back to an ordinary tensor (and NCCL) when
-        the platform offers no multicast."""
+        run through the switch.  Collective: every rank of `group` must construct its bucket at
+        the same point.  Falls back to an ordinary tensor (and NCCL) when the platform offers no
+        multicast."""
         try:
             import torch.distributed._symmetric_memory as symm
             g = group if group is not None else dist.group.WORLD
+            try:        # room for one signal word per (block, peer) of the fused kernel's barriers
+                if symm.get_signal_pad_size() < 65536:
+                    symm.set_signal_pad_size(65536)
+            except Exception:
+                pass
             flat = symm.empty(n, dtype=torch.float32, device=device)
             hdl = symm.rendezvous(flat, g.group_name)
             flat.zero_()
@@ -144,6 +159,35 @@ class GradBucket:
         except Exception:
             self._symm = None
             return torch.zeros(n, dtype=torch.float32, device=device)
+
+    def autotune(self, group=None, iters=8):
+        """Times the available exchanges on the bucket (contents preserved) and keeps the fastest
+        (max over ranks, so every rank picks the same).  Collective."""
+        if self._symm is None or not dist.is_initialized():
+            return
+        keep = self.flat.clone()
+        res = {}
+        for mode in ("nccl", "nvls", "nvls_fused"):
+            self.mode = mode
+            try:
+                for _ in range(3):
+                    self.allreduce(group)
+                torch.cuda.synchronize()
+                dist.barrier(group)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    self.allreduce(group)
+                b.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([a.elapsed_time(b) / iters], device=self.flat.device)
+            except Exception:
+                t = torch.tensor([float("inf")], device=self.flat.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            res[mode] = float(t)
+        self.mode = min(res, key=res.get)
+        self.tuning = {k: round(v, 4) for k, v in res.items()}
+        self.flat.copy_(keep)
 
     def views(self):
         tensors = [self.params[n] for n in self.names] + self.scalars
@@ -175,21 +219,29 @@ class GradBucket:
         """Sum (or mean) over ranks.  No-op in a single process."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        if self._symm is not None and not async_op:
-            # through the NVSwitch: barrier, one kernel (multimem.ld_reduce + multimem.st on this
-            # rank's slice), barrier — all on the current stream
+        if self._symm is not None and not async_op and self.mode != "nccl":
             import ctypes as C
             from . import train_ops
             hdl = self._symm
             lib = train_ops._lib()
-            hdl.barrier(channel=0)
             mc = int(hdl.multicast_ptr) + int(self.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])
             stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
-            with torch.cuda.device(self.flat.device):
-                rc = lib.gft_nvls_allreduce_sum(C.c_void_p(mc), C.c_longlong(self.flat.numel()), hdl.rank,
-                                                hdl.world_size, stream)
-            train_ops._check(rc, "gft_nvls_allreduce_sum")
-            hdl.barrier(channel=1)
+            if self.mode == "nvls_fused":
+                # ONE kernel: barrier over the signal pads, multimem.ld_reduce + multimem.st on this
+                # rank's slice, barrier
+                with torch.cuda.device(self.flat.device):
+                    rc = lib.gft_nvls_allreduce_fused(C.c_void_p(mc), C.c_longlong(self.flat.numel()), hdl.rank,
+                                                      hdl.world_size, C.c_void_p(int(hdl.signal_pad_ptrs_dev)),
+                                                      int(hdl.signal_pad_size) // 4, 0, 4, stream)
+                train_ops._check(rc, "gft_nvls_allreduce_fused")
+            else:
+                # host-launched barrier, one kernel, barrier — all on the current stream
+                hdl.barrier(channel=0)
+                with torch.cuda.device(self.flat.device):
+                    rc = lib.gft_nvls_allreduce_sum(C.c_void_p(mc), C.c_longlong(self.flat.numel()), hdl.rank,
+                                                    hdl.world_size, stream)
+                train_ops._check(rc, "gft_nvls_allreduce_sum")
+                hdl.barrier(channel=1)
             if average:
                 self.flat.div_(hdl.world_size)
             return None

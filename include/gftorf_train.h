@@ -223,6 +223,16 @@ int gft_densify_apply(const GftDensifyApplyArgs* args, gft_stream_t stream);
 int gft_nvls_allreduce_sum(float* multicast_ptr, long long n_floats, int rank, int world,
                            gft_stream_t stream);
 
+/* The same exchange as ONE kernel: a cross-GPU barrier over the symmetric-memory signal pads, the
+ * reduce + broadcast of this rank's slice, and a second barrier — no host-launched barrier
+ * kernels around it.  `signal_pads_dev`: device array of `world` pointers to the ranks' signal
+ * pads (torch: SymmetricMemory.signal_pad_ptrs_dev), each `pad_words` 32-bit words, zero-filled;
+ * the library uses their upper half.  `blocks` (0 = automatic) and `unroll` (2, 4 or 8) must be
+ * the same on every rank.  Collective: every rank of the group must call it. */
+int gft_nvls_allreduce_fused(float* multicast_ptr, long long n_floats, int rank, int world,
+                             void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
+                             gft_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,11 @@ def main(ref="/root/reference"):
         os.makedirs(os.path.dirname(t), exist_ok=True)
         py_compile.compile(s, cfile=t, dfile=src, doraise=True)
         n += 1
-    print(f"compiled {n} reference modules to {OUT}")
+    # one archive next to the tree: file-sync tools commonly skip *.pyc, an opaque .tar travels
+    import tarfile
+    with tarfile.open(OUT + ".tar", "w") as tf:
+        tf.add(OUT, arcname="pyref")
+    print(f"compiled {n} reference modules to {OUT} (+ {OUT}.tar)")
 
 
 if __name__ == "__main__":

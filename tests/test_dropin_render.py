@@ -30,10 +30,29 @@ PYREF = os.path.join(ROOT, "oracle", "_ref", "pyref")
 RAST_SRC = os.path.join(REF, "submodules/diff-gaussian-rasterization-w-tof/diff_gaussian_rasterization_w_tof/__init__.py")
 
 
+_ROOT_CACHE = []
+
+
 def ref_root():
+    if not _ROOT_CACHE:
+        _ROOT_CACHE.append(_find_ref_root())
+    return _ROOT_CACHE[0]
+
+
+def _find_ref_root():
+    global PYREF
     if os.path.exists(os.path.join(REF, "gaussian_renderer", "__init__.py")):
         return REF
     if os.path.exists(os.path.join(PYREF, "gaussian_renderer", "__init__.pyc")):
+        return PYREF
+    tar = os.path.join(ROOT, "oracle", "_ref", "pyref.tar")       # *.pyc files may not have travelled
+    if os.path.exists(tar):
+        import tarfile
+        import tempfile
+        dst = tempfile.mkdtemp(prefix="gft_pyref_")
+        with tarfile.open(tar) as tf:
+            tf.extractall(dst)
+        PYREF = os.path.join(dst, "pyref")
         return PYREF
     return None
 

@@ -513,6 +513,34 @@ def test_subtile_culling_is_exact():
             assert err <= harness.GRAD_REL_L2 * max(float(y.double().norm()), 1e-2 * scale)
 
 
+@pytest.mark.parametrize("name", ["ragged", "c1", "c1_init"])
+def test_blend_backward_variants_agree(name):
+    """The blend backward exists in four shapes (block double buffer or mbarrier ring of 32-Gaussian
+    chunks; branch-free or branchy replay).  They replay the same pairs with the same arithmetic,
+    so they differ by the order of the floating-point atomics only."""
+    from gftorf_b200 import _capi
+    inp = harness.build_inputs(device="cuda", **CASES[name])
+    f = harness.call_forward(rasterizer._C, inp)
+    res = {}
+    for ring in (0, 1):
+        for pred in (0, 1):
+            o1, o2 = _capi.set_option("bwd_ring", ring), _capi.set_option("bwd_pred", pred)
+            try:
+                res[(ring, pred)] = harness.call_backward(rasterizer._C, inp, f)
+                torch.cuda.synchronize()
+            finally:
+                _capi.set_option("bwd_ring", o1)
+                _capi.set_option("bwd_pred", o2)
+    base = res[(0, 0)]
+    scale = float(base[8].double().norm())
+    for key, g in res.items():
+        for i, (x, y) in enumerate(zip(g, base)):
+            if x is None:
+                continue
+            err = float((x.double() - y.double()).norm())
+            assert err <= harness.GRAD_REL_L2 * max(float(y.double().norm()), 1e-2 * scale), (key, harness.BWD_NAMES[i])
+
+
 def test_debug_mode_runs():
     inp = harness.build_inputs(device="cuda", **CASES["tiny"])
     e = inp["empty"]

@@ -107,3 +107,51 @@ def test_autograd_function_signature():
     assert list(gr.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "shs_p",
                                        "colors_precomp", "phasors_precomp", "scales", "rotations",
                                        "cov3D_precomp", "phase_offset", "dc_offset"]
+
+
+# ------------------------------------------------------------------------------------------------
+# batched views (gftorf_b200.views): host-side contract, no GPU
+# ------------------------------------------------------------------------------------------------
+def test_viewspec_from_settings_and_batch_limits():
+    from gftorf_b200 import views as V
+    s = rasterizer.GaussianRasterizationSettings(
+        image_height=48, image_width=64, tanfovx=0.5, tanfovy=0.4, bg=torch.zeros(7, 48, 64), scale_modifier=1.0,
+        viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=3, campos=torch.zeros(3), prefiltered=False,
+        debug=False, near_n=0.2, far_n=9.0, depth_range=15.0, use_view_dependent_phase=True)
+    v = V.ViewSpec.from_settings(s, phase_offset=torch.tensor([0.25]), dc_offset=0.5)
+    assert (v.image_height, v.image_width, v.near_n, v.far_n, v.depth_range) == (48, 64, 0.2, 9.0, 15.0)
+    assert v.use_view_dependent_phase is True and v.phase_offset == 0.25 and v.dc_offset == 0.5
+    assert V.MAX_VIEWS == 16
+    m = torch.zeros(5, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        V.forward_views(m, m[:, :1], m, torch.zeros(5, 4), torch.zeros(5, 16, 3), torch.zeros(5, 16, 2), [v], 3)
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        V.forward_views(torch.zeros(5, 2), m[:, :1], m, m, m, m, [v], 3)
+
+
+def test_rasterize_views_validation_matches_the_single_view_surface():
+    from gftorf_b200 import views as V
+    m = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        V.rasterize_views(m, m, m[:, :1], None, None, m, m, [], 3)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        V.rasterize_views(m, m, m[:, :1], torch.zeros(4, 16, 3), None, None, None, [], 3)
+
+
+def test_c_abi_rejects_bad_view_batches_without_a_gpu():
+    import ctypes as C
+    from gftorf_b200 import _capi
+    lib = _capi.lib()
+    a = _capi.GftForwardViewsArgs()
+    a.P, a.n_views = 10, 0
+    cb = _capi.ALLOC_FN(lambda ctx, n: 0)
+    assert lib.gft_forward_views(C.byref(a), cb, cb, cb, None, None) == -1
+    assert b"n_views" in lib.gft_last_error()
+    a.n_views = _capi.GFT_MAX_VIEWS + 1
+    assert lib.gft_forward_views(C.byref(a), cb, cb, cb, None, None) == -1
+    b = _capi.GftBackwardViewsArgs()
+    b.P, b.n_views = 10, 0
+    assert lib.gft_backward_views(C.byref(b), None) == -1
+    assert lib.gft_set_option(b"no_such_option", 1) < 0
+    old = lib.gft_set_option(b"sort_cap", 2048)
+    assert lib.gft_set_option(b"sort_cap", old) == 2048

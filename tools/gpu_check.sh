@@ -5,21 +5,21 @@
 tag=${1:-chk}
 out=gpurun_out
 mkdir -p $out
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=25 --tb=short > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k test_blend_backward_variants_agree > $out/ring_$tag.log 2>&1; echo "ring test rc=$?"; tail -3 $out/ring_$tag.log
+timeout 1500 python -m pytest tests -m gpu -q -rs --maxfail=25 --tb=short > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
 tail -40 $out/pytest_gpu_$tag.log
 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -3 $out/smoke_$tag.log
 for wl in c2 c1 c4; do
   python tools/stage_probe.py --workload $wl >> $out/stages_$tag.log 2>&1
   python tools/stage_probe.py --workload $wl --single >> $out/stages_$tag.log 2>&1
 done
-python tools/stage_probe.py --workload c2 --opt tile_order=0 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c4 --opt tile_order=0 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c2 --opt sort_radix=0 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c2 --opt sort_match=1 >> $out/stages_$tag.log 2>&1
+python tools/stage_probe.py --workload c2 --opt bwd_ring=1 >> $out/stages_$tag.log 2>&1
+python tools/stage_probe.py --workload c4 --opt bwd_ring=1 >> $out/stages_$tag.log 2>&1
+python tools/stage_probe.py --workload c2_init --opt bwd_ring=1 >> $out/stages_$tag.log 2>&1
+python tools/stage_probe.py --workload c1 --opt bwd_ring=1 >> $out/stages_$tag.log 2>&1
 python tools/stage_probe.py --workload c2 --opt sort_cap=2048 >> $out/stages_$tag.log 2>&1
 python tools/stage_probe.py --workload c2_init >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c2_init --opt sort_radix=0 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c5 --steps 8 >> $out/stages_$tag.log 2>&1
+
 cat $out/stages_$tag.log
 if [ "$2" == "bench" ]; then
 python bench.py --steps 20 --warmup 5 > $out/bench_ours_$tag.json 2> $out/bench_ours_$tag.err; echo "bench ours rc=$?"; tail -3 $out/bench_ours_$tag.err
