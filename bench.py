@@ -310,7 +310,10 @@ class Ours:
 
     def make_bucket(self, params):
         scal = [torch.zeros(1, device=self.dev), torch.zeros(1, device=self.dev)]
-        b = self.parallel.GradBucket(params, scal)
+        # N > 1: the bucket lives in symmetric memory and the exchange is whichever of NCCL and the
+        # library's NVLS kernels is fastest on this very buffer (timed once, at construction)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        b = self.parallel.GradBucket(params, scal, symmetric="auto" if multi else False)
         return b, b.grad_out()
 
     def forward(self, key, params, views, specs=None):
@@ -512,6 +515,8 @@ def run_gpu(args, impl):
         "views": {"V": Vs, "R": Rs},
         "blocks": blocks,
     }
+    if impl == "ours" and world > 1:
+        line["exchange"] = {"mode": bucket.mode, "autotune_ms": bucket.tuning, "bytes": bucket.nbytes()}
     Ns = [v["W"] * v["H"] for v in views]
     Ts = [((v["W"] + 15) // 16) * ((v["H"] + 15) // 16) for v in views]
     if impl == "ours":
@@ -792,6 +797,8 @@ def c4_block(arm, impl, dev, timer, rank, world):
     if rank == 0 and stats:
         Vs, Rs = view_stats(arm, stats, views)
         out["rank0_views"] = {"V": Vs[:2], "R": Rs[:2], "R_total": int(sum(Rs))}
+    if impl == "ours" and world > 1:
+        out["exchange"] = {"mode": bucket.mode, "autotune_ms": bucket.tuning, "bytes": bucket.nbytes()}
     del params, cams, views, bucket, stats
     torch.cuda.empty_cache()
     return out

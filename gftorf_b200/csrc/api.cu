@@ -221,7 +221,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"sub_bins", "GFT_SUB_BINS", 16},    // sub-counters per tile of the binning (power of two, <= 16)
     {"sort_match", "GFT_SORT_MATCH", 0}, // 1: MATCH.ANY instead of eight ballots for the radix ranking
     {"tile_order", "GFT_TILE_ORDER", 1}, // 0: blend blocks in tile index order instead of longest list first
-    {"bwd_ring", "GFT_BWD_RING", 0},     // 1: mbarrier ring of 32-Gaussian chunks in the blend backward
+    {"bwd_ring", "GFT_BWD_RING", 1},     // 0: block-wide double buffer instead of the mbarrier ring in the blend backward
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};

@@ -419,7 +419,7 @@ void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entr
   // network everywhere (A/B runs, tests of the long-segment path).
   const int forced = option(OPT_SORT_CAP);
   const int use_radix = option(OPT_SORT_RADIX) != 0 ? (option(OPT_SORT_MATCH) != 0 ? 2 : 1) : 0;
-  uint32_t cap = mean_len_hint > 700 ? 4096u : 2048u;
+  uint32_t cap = mean_len_hint > 1400 ? 4096u : 2048u;
   if (forced == 256 || forced == 1024 || forced == 2048 || forced == 4096 || forced == 8192) cap = (uint32_t)forced;
   const int smem = use_radix ? (int)cap * 16 + 8 * 256 * 4 : (int)cap * 8;
   static unsigned long long smem_ok = 0;

@@ -428,7 +428,8 @@ void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
   // block per SM (+4 %), replays with few contributing pixels sent straight to the record with
   // per-lane reductions (+4 %), a warp-autonomous variant like the forward's (+6 %), half-tile
   // blocks (+-1 %), the shuffle butterfly instead of the shared-memory transpose (+7 %).
-  // Options bwd_pred = 0 (branchy replay) and bwd_ring (mbarrier ring vs block double buffer) for A/B runs.
+  // Options bwd_pred = 0 (branchy replay) and bwd_ring = 0 (block double buffer instead of the mbarrier
+  // ring: +2.5 % at 640x480, +3.7 % at 1080p) for A/B runs.
   const bool pred = option(OPT_BWD_PRED) != 0, ring = option(OPT_BWD_RING) != 0;
   if (ring) {
     if (pred) launch_bwd_variant<3, true, true>(p, stream);
