@@ -320,9 +320,9 @@ class Ours:
         specs = specs or [view_spec(v) for v in views]
         f = self.V.forward_views(params["means3D"], params["opacities"], params["scales"], params["rotations"],
                                  params["shs"], params["shs_p"], specs, 3, R_hint=self.hints.get(key, 0))
-        # the previous step's instance count (+25 %) sizes the binning workspace, so the forward
-        # is enqueued without a host round trip in the middle
-        self.hints[key] = int(f.R * 1.25) + 4096
+        # the largest instance count seen under this key (+25 %) sizes the binning workspace, so the
+        # forward is enqueued without a host round trip in the middle
+        self.hints[key] = max(self.hints.get(key, 0), int(f.R * 1.25) + 4096)
         return f
 
     def fwd_bwd(self, key, params, views, bucket, go, accumulate=False, specs=None):
@@ -415,7 +415,10 @@ def run_gpu(args, impl):
 
     arm = Ours(dev) if impl == "ours" else Reference(dev)
     wl = WORKLOADS[args.workload]
-    params, views = build_scene(wl, seed=rank, device=dev)   # each rank: its own views of the batch
+    # weak scaling: every rank renders a camera pair of the SAME synthetic scene (seed 0), so the
+    # per-GPU work is identical at every N and the driver's efficiency measures the exchange, not
+    # the luck of the per-rank random clouds (round 1 seeded by rank: the slowest cloud set the pace)
+    params, views = build_scene(wl, seed=0, device=dev)
     P = wl["P"]
     npix = sum(v["W"] * v["H"] for v in views)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -497,7 +500,7 @@ def run_gpu(args, impl):
         "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}; trained-like cloud (SURVEY §8d), "
-                               "one camera pair per rank per step, fwd colour + fwd ToF + bwd both"
+                               "one camera pair per rank per step (the same scene on every rank), fwd colour + fwd ToF + bwd both"
                                + ("; + NCCL allreduce of the per-Gaussian gradients" if world > 1 else ""),
                    "P": P, "views_per_step_per_rank": len(views),
                    "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
@@ -760,7 +763,7 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
 def small_scene_block(arm, impl, dev, timer, rank, world):
     """BASELINE configs[0] shape on the GPU: 20k Gaussians, 320x240 x2 — launch-bound."""
     wl = WORKLOADS["c1"]
-    params, views = build_scene(wl, seed=rank, device=dev)
+    params, views = build_scene(wl, seed=0, device=dev)
     bucket, go = arm.make_bucket(params)
     ms, _ = timer.run(lambda: arm.fwd_bwd("c1", params, views, bucket, go), 30, 5)
     return {"workload": wl["desc"], "ms_per_step": round(ms / 30, 4), "step_ms_min_med_max": min_med_max(timer.steps_ms)}
@@ -820,7 +823,8 @@ def c5_block(arm, impl, dev, timer, rank, world, sizes):
         def sweep(n=None):
             fr = frames if n is None else frames[:n]
             for c0 in range(0, len(fr), B):
-                arm.render(("c5", P, c0), params, fr[c0:c0 + B], None if specs is None else specs[c0:c0 + B])
+                # one size hint for the whole sweep: the frames of a trajectory have similar instance counts
+                arm.render(("c5", P), params, fr[c0:c0 + B], None if specs is None else specs[c0:c0 + B])
         sweep(8)                       # warm-up: allocator, hints
         timer.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

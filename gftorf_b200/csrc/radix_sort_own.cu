@@ -145,8 +145,8 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
     const uint32_t g = wbase + i * 32 + lane;
     const bool ok = g < (uint32_t)R;
     const uint32_t d = ok ? ((uint32_t)(key[i] >> shift) & dmask) : 256u;  // 256 = padding
-    // eight ballots instead of MATCH.ANY (~1400 cycles on sm_100, common.cuh); padding lanes form
-    // their own group either way and never touch the histogram
+    // eight ballots instead of MATCH.ANY (common.cuh); padding lanes form their own group either
+    // way and never touch the histogram
     const uint32_t peers = match_digit8(d, ok) | (ok ? 0u : (1u << lane));
     const uint32_t leader = __ffs(peers) - 1;
     uint32_t old = 0;
