@@ -267,12 +267,16 @@ class Timer:
         torch.cuda.synchronize()
 
     def run(self, step_fn, K, W, flush=True, sampler=None):
+        # collect BEFORE the warm-up and keep the collector off from there on: a collection between
+        # the warm-up and the timed steps returns cached blocks to the allocator in a different
+        # order, and the first timed step then pays for fresh cudaMallocs (seen as one 1.5-2x
+        # straggler at the start of every timed region, in both arms)
+        gc.collect()
+        gc.disable()      # a cyclic-GC pause inside a 2 ms step would be charged to the step
         for _ in range(W):
             step_fn()
         self.barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        gc.collect()
-        gc.disable()      # a cyclic-GC pause inside a 2 ms step would be charged to the step
         t0 = time.perf_counter()
         out = None
         for i in range(K):
@@ -729,13 +733,13 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     # pipelined: whole region timed with one event pair on the compute stream, every copy inside
     for e in ev_comp + ev_down:
         e.record(comp)
+    gc.collect()
+    gc.disable()
     for i in range(W):
         one(i, True)
     comp.wait_stream(down)
     comp.wait_stream(up)
     timer.barrier()
-    gc.collect()
-    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(comp)
     for i in range(K):
@@ -825,7 +829,7 @@ def c5_block(arm, impl, dev, timer, rank, world, sizes):
             for c0 in range(0, len(fr), B):
                 # one size hint for the whole sweep: the frames of a trajectory have similar instance counts
                 arm.render(("c5", P), params, fr[c0:c0 + B], None if specs is None else specs[c0:c0 + B])
-        sweep(8)                       # warm-up: allocator, hints
+        sweep()                        # warm-up over the whole trajectory: allocator, largest instance count
         timer.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

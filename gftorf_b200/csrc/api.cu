@@ -222,6 +222,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"sort_match", "GFT_SORT_MATCH", 0}, // 1: MATCH.ANY instead of eight ballots for the radix ranking
     {"tile_order", "GFT_TILE_ORDER", 1}, // 0: blend blocks in tile index order instead of longest list first
     {"bwd_ring", "GFT_BWD_RING", 1},     // 0: block-wide double buffer instead of the mbarrier ring in the blend backward
+    {"pfwd_minb", "GFT_PFWD_MINB", 3},   // resident blocks per SM the preprocess forward is compiled for (3 or 4)
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};

@@ -118,7 +118,8 @@ __device__ __forceinline__ void eval_sh_pa(int D, const float* sp, const float* 
 //   pass A (colour SH rows of the warp staged in shared memory): geometry + colour per view
 //   pass B (phase/amplitude SH rows staged in the same buffer):   phasor per view
 // The arithmetic of every view is the single-view sequence pinned to the reference binary.
-__global__ void __launch_bounds__(GFT_BLOCK)
+template <int MINB>
+__global__ void __launch_bounds__(GFT_BLOCK, MINB)
 preprocess_fwd_kernel(const __grid_constant__ PreprocessParams p) {
   extern __shared__ float fwd_stage[];  // GFT_STAGE_FLOATS_PER_WARP floats per warp
 
@@ -410,9 +411,20 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
   const int blocks = (p.P + GFT_BLOCK - 1) / GFT_BLOCK;
   const int smem = (GFT_BLOCK / 32) * GFT_STAGE_FLOATS_PER_WARP * (int)sizeof(float);
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(preprocess_fwd_kernel, smem, &smem_ok);
-  preprocess_fwd_kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  // 3 resident blocks per SM (79 registers, no spills; the unbounded build took 83 and ran 2 per SM:
+  // ncu r2_g) or 4 (64 registers, 72 B spilled): option pfwd_minb.  The carveout preference lets
+  // 4 x 49 KB of staging fit.
+  static unsigned long long ok3 = 0, ok4 = 0;
+  auto go = [&](auto kernel, unsigned long long* ok) {
+    if (!(*ok & (1ull << 63))) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      __atomic_fetch_or(ok, 1ull << 63, __ATOMIC_RELAXED);
+    }
+    ensure_dynamic_smem(kernel, smem, ok);
+    kernel<<<blocks, GFT_BLOCK, smem, stream>>>(p);
+  };
+  if (option(OPT_PFWD_MINB) == 4) go(preprocess_fwd_kernel<4>, &ok4);
+  else go(preprocess_fwd_kernel<3>, &ok3);
   note_launches(1);
 }
 
