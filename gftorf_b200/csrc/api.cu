@@ -223,6 +223,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"tile_order", "GFT_TILE_ORDER", 1}, // 0: blend blocks in tile index order instead of longest list first
     {"bwd_ring", "GFT_BWD_RING", 1},     // 0: block-wide double buffer instead of the mbarrier ring in the blend backward
     {"pfwd_minb", "GFT_PFWD_MINB", 3},   // resident blocks per SM the preprocess forward is compiled for (3 or 4)
+    {"blend_half", "GFT_BLEND_HALF", 0}, // 1: blend warps walk their 8x4 patch as two independent 4x4 halves
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};

@@ -50,6 +50,10 @@ namespace {
 
 constexpr int RED_STRIDE = 36;
 constexpr int RED_FLOATS = 16 * RED_STRIDE;
+// HALF: 32 rows (15 values x 2 halves) of 16 lanes, 20-float stride, the right half's rows shifted by
+// 16 floats so the two halves' stores hit disjoint banks
+constexpr int REDH_STRIDE = 20;
+constexpr int REDH_FLOATS = 32 * REDH_STRIDE + 16;
 
 template <int BATCH>
 struct BwdBufT {
@@ -119,7 +123,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 // done with it, so a warp only ever waits for a chunk that has not arrived or for the slowest
 // warp falling more than 8 chunks behind — never for the block.  Every wait depends on strictly
 // earlier chunks only, so the protocol cannot deadlock.
-template <int MINB, bool PRED, bool RING>
+// HALF (with RING and PRED): the warp's 8x4 patch is replayed as two independent 4x4 halves, each
+// with its own candidate list, side by side in one instruction stream (see blend_fwd.cu); the two
+// halves' 15 partials are reduced by ONE transpose (32 rows of 16 lanes, lane j sums row j, no
+// shuffle) and leave with one reduction instruction for both Gaussians.
+template <int MINB, bool PRED, bool RING, bool HALF = false>
 __global__ void __launch_bounds__(GFT_BLOCK, MINB)
 blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   constexpr int WARPS = GFT_BLOCK / 32;
@@ -131,7 +139,7 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   __shared__ uint32_t s_wmax[WARPS];
   __shared__ __align__(8) unsigned long long s_full[RING_SLOTS], s_empty[RING_SLOTS];
   // per-warp transpose buffer, 16 value rows x 36 floats (32 lanes + 4 pad)
-  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * RED_FLOATS;
+  float* red = reinterpret_cast<float*>(bwd_smem_raw + 2 * sizeof(BwdBuf)) + (threadIdx.x >> 5) * (HALF ? REDH_FLOATS : RED_FLOATS);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile_g = p.order ? __ldg(p.order + blockIdx.x) : blockIdx.x;   // longest lists first
@@ -142,7 +150,9 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
-  const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
+  const uint32_t half = lane >> 4;                      // HALF: 0 = left 4x4, 1 = right 4x4
+  const uint32_t pix_x = HALF ? px0 + half * 4u + (lane & 3u) : px0 + (lane & 7u);
+  const uint32_t pix_y = HALF ? py0 + ((lane & 15u) >> 2) : py0 + (lane >> 3);
   const int W = vw.W, H = vw.H;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
@@ -205,7 +215,9 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
   // furthest contributor of the warp / of the tile
   uint32_t wmax = last_contributor;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  for (int o = 8; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  const uint32_t hmax = wmax;                            // furthest contributor of this lane's half
+  wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 16));
   if (lane == 0) s_wmax[warp] = wmax;
   if (RING && tid < RING_SLOTS) {
     mbar_init(&s_full[tid], 32);       // one arrive per lane of the requesting warp, when its copies land
@@ -359,6 +371,103 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
     }
   };
 
+  // ---- HALF: two candidates per step, one per 4x4 half ------------------------------------------
+  auto replay_half = [&](const auto& s, int k, bool contrib, float G, float alpha, float dx, float dy) {
+    const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
+    if (cb == 0u) return;
+    // a lane without a contributing pair replays alpha = G = 0: every partial is exactly 0 and
+    // T, X, Bp keep their values
+    alpha = contrib ? alpha : 0.f;
+    G = contrib ? G : 0.f;
+    float v[15];
+    {
+      const float4 g1 = s.r1[k];
+      const float4 g2 = s.r2[k];
+      const float4 g3 = s.r3[k];
+      const float4 g4 = s.r4[k];
+      const float om = 1.f - alpha;
+      const float inv_om = 1.0f / om;
+      T = T * inv_om;                 // backward.cu:756
+      const float w = alpha * T;
+      const float wp = w * T;
+      const float z = g4.w;
+      const float2 kd = fma2(make_float2(g2.z, g2.w), make_float2(gc2, gd),
+                             mul2(make_float2(g2.x, g2.y), make_float2(gc0, gc1)));
+      const float x_tot = (kd.x + kd.y) + (z * (z * k2 - k1) + k0);
+      const float2 pd = fma2(make_float2(g4.x, g4.y), make_float2(gp4, gp5),
+                             fma2(make_float2(g3.z, g3.w), make_float2(gp2, gp3),
+                                  mul2(make_float2(g3.x, g3.y), make_float2(gp0, gp1))));
+      const float pi = (pd.x + pd.y) + g4.z * gp6;
+      const float dL_dalpha = (x_tot - X) * T + (pi - 2.f * om * Bp) * (T * T) -
+                              (T_final * inv_om) * bgdot;
+      const float2 rec = fma2(make_float2(alpha, alpha), make_float2(x_tot, pi),
+                              mul2(make_float2(om, om * om), make_float2(X, Bp)));
+      X = rec.x;
+      Bp = rec.y;
+      const float h = g1.w * dL_dalpha * G;
+      const float2 dxy = make_float2(dx, dy);
+      const float2 hxy = mul2(make_float2(h, h), dxy);
+      const float2 hxx = mul2(make_float2(hxy.x, hxy.x), dxy);
+      v[0] = hxy.x; v[1] = hxy.y; v[2] = hxx.x; v[3] = hxx.y;
+      v[4] = hxy.y * dy;
+      v[5] = G * dL_dalpha;
+      const float2 w2 = make_float2(w, w), wp2 = make_float2(wp, wp);
+      const float2 v67 = mul2(w2, make_float2(gc0, gc1)), v89 = mul2(w2, make_float2(gc2, gd));
+      const float2 vAB = mul2(wp2, make_float2(gA, gB)), vCS = mul2(wp2, make_float2(gp2, gS));
+      v[6] = v67.x; v[7] = v67.y; v[8] = v89.x; v[9] = v89.y;
+      v[10] = w * (2.f * z * k2 - k1);
+      v[11] = vAB.x; v[12] = vAB.y; v[13] = vCS.x; v[14] = vCS.y;
+    }
+    // rows 0..14: the left half's values, rows 16..30 (+16 floats): the right half's
+    float* col = red + half * (16 * REDH_STRIDE + 16) + (lane & 15u);
+#pragma unroll
+    for (int i = 0; i < 15; ++i) col[i * REDH_STRIDE] = v[i];
+    __syncwarp();
+    const float4* rp = reinterpret_cast<const float4*>(red + lane * REDH_STRIDE + half * 16u);
+    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+    const float2 s0 = add2(make_float2(q0.x, q0.y), make_float2(q0.z, q0.w));
+    const float2 s1 = add2(make_float2(q1.x, q1.y), make_float2(q1.z, q1.w));
+    const float2 s2 = add2(make_float2(q2.x, q2.y), make_float2(q2.z, q2.w));
+    const float2 s3 = add2(make_float2(q3.x, q3.y), make_float2(q3.z, q3.w));
+    const float2 st = add2(add2(s0, s1), add2(s2, s3));
+    const float sum = st.x + st.y;
+    __syncwarp();
+    const uint32_t mine = half ? (cb >> 16) : (cb & 0xffffu);     // did this lane's half contribute at all
+    if (mine != 0u && (lane & 15u) != 15u)
+      atomicAdd(grad_rec + (size_t)s.id[k] * GFT_GRAD_FLOATS + (lane & 15u), sum);
+  };
+  auto walk_half = [&](const auto& s, int base, int m_w) {
+    bool hitL = false, hitR = false;
+    const int jj = (int)lane;
+    if (jj < m_w) {
+      const float4 g0 = s.r0[jj];
+      const bool ymiss = g0.y + g0.w < patch_y0 || g0.y - g0.w > patch_y1;
+      hitL = !(ymiss || g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x0 + 3.f);
+      hitR = !(ymiss || g0.x + g0.z < patch_x0 + 4.f || g0.x - g0.z > patch_x1);
+    }
+    // positions >= the half's furthest contributor contribute nothing for that half
+    const uint32_t hmL = __shfl_sync(0xffffffffu, hmax, 0), hmR = __shfl_sync(0xffffffffu, hmax, 16);
+    hitL = hitL && (uint32_t)(base + jj) < hmL;
+    hitR = hitR && (uint32_t)(base + jj) < hmR;
+    uint32_t mL = __ballot_sync(0xffffffffu, hitL), mR = __ballot_sync(0xffffffffu, hitR);
+    while (mL | mR) {
+      const int kL1 = mL ? 31 - __clz(mL) : -1;
+      if (mL) mL &= ~(1u << kL1);
+      const int kR1 = mR ? 31 - __clz(mR) : -1;
+      if (mR) mR &= ~(1u << kR1);
+      const int kL2 = mL ? 31 - __clz(mL) : -1;
+      if (mL) mL &= ~(1u << kL2);
+      const int kR2 = mR ? 31 - __clz(mR) : -1;
+      if (mR) mR &= ~(1u << kR2);
+      const int k1 = half ? kR1 : kL1, k2 = half ? kR2 : kL2;
+      float G1 = 0.f, G2 = 0.f, al1 = 0.f, al2 = 0.f, dx1 = 0.f, dy1 = 0.f, dx2 = 0.f, dy2 = 0.f;
+      const bool c1 = k1 >= 0 && eval_pair(s, base, k1, G1, al1, dx1, dy1);
+      const bool c2 = k2 >= 0 && eval_pair(s, base, k2, G2, al2, dx2, dy2);
+      replay_half(s, max(k1, 0), c1, G1, al1, dx1, dy1);
+      if (kL2 >= 0 || kR2 >= 0) replay_half(s, max(k2, 0), c2, G2, al2, dx2, dy2);
+    }
+  };
+
   if (RING) {
     const int nc = (n_eff + 31) >> 5;                 // chunks, processed from the last to the first
     auto request = [&](int q) {                       // whole warp; sequence number q <-> chunk nc-1-q
@@ -387,7 +496,10 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
       mbar_wait(&s_full[slot], (uint32_t)(q / RING_SLOTS) & 1u);
       const int base = (nc - 1 - q) * 32;
       const int m_w = min(min(32, n_eff - base), (int)wmax - base);   // positions >= wmax: nothing for this warp
-      if (m_w > 0) walk(ring[slot], base, 0, m_w);
+      if (m_w > 0) {
+        if (HALF) walk_half(ring[slot], base, m_w);
+        else walk(ring[slot], base, 0, m_w);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[slot]);
     }
@@ -411,12 +523,12 @@ blend_bwd_kernel(const __grid_constant__ BlendBwdParams p) {
 }
 
 namespace {
-template <int MINB, bool PRED, bool RING>
+template <int MINB, bool PRED, bool RING, bool HALF = false>
 void launch_bwd_variant(const BlendBwdParams& p, cudaStream_t stream) {
-  const int smem = 2 * (int)sizeof(BwdBufT<GFT_BLOCK>) + (GFT_BLOCK / 32) * RED_FLOATS * 4;
+  const int smem = 2 * (int)sizeof(BwdBufT<GFT_BLOCK>) + (GFT_BLOCK / 32) * (HALF ? REDH_FLOATS : RED_FLOATS) * 4;
   static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_bwd_kernel<MINB, PRED, RING>, smem, &smem_ok);
-  blend_bwd_kernel<MINB, PRED, RING><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
+  ensure_dynamic_smem(blend_bwd_kernel<MINB, PRED, RING, HALF>, smem, &smem_ok);
+  blend_bwd_kernel<MINB, PRED, RING, HALF><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
 }
 }  // namespace
 
@@ -431,7 +543,9 @@ void launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
   // Options bwd_pred = 0 (branchy replay) and bwd_ring = 0 (block double buffer instead of the mbarrier
   // ring: +2.5 % at 640x480, +3.7 % at 1080p) for A/B runs.
   const bool pred = option(OPT_BWD_PRED) != 0, ring = option(OPT_BWD_RING) != 0;
-  if (ring) {
+  if (option(OPT_BLEND_HALF) != 0) {
+    launch_bwd_variant<3, true, true, true>(p, stream);
+  } else if (ring) {
     if (pred) launch_bwd_variant<3, true, true>(p, stream);
     else launch_bwd_variant<3, false, true>(p, stream);
   } else {

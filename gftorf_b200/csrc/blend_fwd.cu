@@ -55,7 +55,12 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 
 }  // namespace
 
-template <int MINB>
+// HALF: the warp's 8x4 patch is walked as two independent 4x4 halves (lanes 0-15 / 16-31).  Each
+// half has its own list of candidates that can reach it and the two lists are walked side by side,
+// so one instruction stream blends two (half-patch, Gaussian) pairs at once: a 4x4 half is hit by
+// fewer Gaussians than the 8x4 patch and a larger share of its 16 lanes contributes.  Per pixel
+// the candidates still arrive in list order with the same arithmetic: results are unchanged.
+template <int MINB, bool HALF>
 __global__ void __launch_bounds__(GFT_BLOCK, MINB)
 blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
   extern __shared__ __align__(16) unsigned char fwd_smem_raw[];
@@ -70,7 +75,9 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
   const uint32_t tile_x = tile % (uint32_t)vw.grid_x, tile_y = tile / (uint32_t)vw.grid_x;
   const uint32_t px0 = tile_x * GFT_TILE_X + (warp & 1u) * 8u;
   const uint32_t py0 = tile_y * GFT_TILE_Y + (warp >> 1) * 4u;
-  const uint32_t pix_x = px0 + (lane & 7u), pix_y = py0 + (lane >> 3);
+  const uint32_t half = lane >> 4;                      // HALF: 0 = left 4x4, 1 = right 4x4
+  const uint32_t pix_x = HALF ? px0 + half * 4u + (lane & 3u) : px0 + (lane & 7u);
+  const uint32_t pix_y = HALF ? py0 + ((lane & 15u) >> 2) : py0 + (lane >> 3);
   const int W = vw.W, H = vw.H;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const uint32_t pix_id = (uint32_t)W * pix_y + pix_x;
@@ -123,14 +130,6 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
       const WarpStage& s = ring[b % WSTAGES];
       const int base = b * 32;
       const int m = min(32, n - base);
-      bool hit = false;
-      if ((int)lane < m) {
-        const float4 g0 = s.r0[lane];
-        // written so that NaN extents mean "not culled"
-        hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
-                g0.y - g0.w > patch_y1);
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
       int mycnt = 0;
       // alpha of one pair (forward.cu:524-537), independent of the pixel's running state, so two
       // Gaussians are evaluated side by side to overlap their expf latency chains
@@ -145,8 +144,10 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
         return neg && !(alpha < 1.0f / 255.0f);
       };
       // One (pixel, Gaussian) pair, after its alpha has been evaluated.  Sequential per pixel: the
-      // transmittance test and the accumulators depend on every earlier Gaussian.
-      auto apply = [&](int k, float alpha, bool pass) {
+      // transmittance test and the accumulators depend on every earlier Gaussian.  kL / kR: the
+      // candidates of the left / right half in this step (the same candidate without HALF); the
+      // lane that staged a candidate collects its pixel count.
+      auto apply = [&](int k, int kL, int kR, float alpha, bool pass) {
         bool contrib = !done && pass;
         float test_T = 0.f;
         if (contrib) {
@@ -154,7 +155,12 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
           if (test_T < 0.0001f) { done = true; contrib = false; }   // forward.cu:538-543
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, contrib);
-        if ((int)lane == k) mycnt = __popc(bal);
+        if (HALF) {
+          if ((int)lane == kL) mycnt += __popc(bal & 0xffffu);
+          if ((int)lane == kR) mycnt += __popc(bal >> 16);
+        } else {
+          if ((int)lane == k) mycnt = __popc(bal);
+        }
         if (contrib) {
           const float4 g2 = s.r2[k];
           const float4 g3 = s.r3[k];
@@ -184,17 +190,56 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
           last_contributor = (uint32_t)(base + k + 1);
         }
       };
-      while (mask) {
-        const int b1 = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const bool two = mask != 0u;
-        const int b2 = two ? (__ffs(mask) - 1) : b1;
-        if (two) mask &= mask - 1;
-        float alpha1, alpha2;
-        const bool pass1 = eval_alpha(b1, alpha1);
-        const bool pass2 = eval_alpha(b2, alpha2);
-        apply(b1, alpha1, pass1);
-        if (two) apply(b2, alpha2, pass2);
+      if (HALF) {
+        bool hitL = false, hitR = false;
+        if ((int)lane < m) {
+          const float4 g0 = s.r0[lane];
+          // written so that NaN extents mean "not culled"
+          const bool ymiss = g0.y + g0.w < patch_y0 || g0.y - g0.w > patch_y1;
+          hitL = !(ymiss || g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x0 + 3.f);
+          hitR = !(ymiss || g0.x + g0.z < patch_x0 + 4.f || g0.x - g0.z > patch_x1);
+        }
+        uint32_t mL = __ballot_sync(0xffffffffu, hitL), mR = __ballot_sync(0xffffffffu, hitR);
+        const uint32_t dn = __ballot_sync(0xffffffffu, done);
+        if ((dn & 0xffffu) == 0xffffu) mL = 0u;        // a half whose pixels are all done stops walking
+        if ((dn >> 16) == 0xffffu) mR = 0u;
+        while (mL | mR) {
+          const int kL1 = mL ? __ffs(mL) - 1 : -1;
+          if (mL) mL &= mL - 1;
+          const int kR1 = mR ? __ffs(mR) - 1 : -1;
+          if (mR) mR &= mR - 1;
+          const int kL2 = mL ? __ffs(mL) - 1 : -1;
+          if (mL) mL &= mL - 1;
+          const int kR2 = mR ? __ffs(mR) - 1 : -1;
+          if (mR) mR &= mR - 1;
+          const int k1 = half ? kR1 : kL1, k2 = half ? kR2 : kL2;
+          float alpha1 = 0.f, alpha2 = 0.f;
+          const bool pass1 = k1 >= 0 && eval_alpha(k1, alpha1);
+          const bool pass2 = k2 >= 0 && eval_alpha(k2, alpha2);
+          apply(max(k1, 0), kL1, kR1, alpha1, pass1);
+          if (kL2 >= 0 || kR2 >= 0) apply(max(k2, 0), kL2, kR2, alpha2, pass2);
+        }
+      } else {
+        bool hit = false;
+        if ((int)lane < m) {
+          const float4 g0 = s.r0[lane];
+          // written so that NaN extents mean "not culled"
+          hit = !(g0.x + g0.z < patch_x0 || g0.x - g0.z > patch_x1 || g0.y + g0.w < patch_y0 ||
+                  g0.y - g0.w > patch_y1);
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int b1 = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const bool two = mask != 0u;
+          const int b2 = two ? (__ffs(mask) - 1) : b1;
+          if (two) mask &= mask - 1;
+          float alpha1, alpha2;
+          const bool pass1 = eval_alpha(b1, alpha1);
+          const bool pass2 = eval_alpha(b2, alpha2);
+          apply(b1, b1, b1, alpha1, pass1);
+          if (two) apply(b2, b2, b2, alpha2, pass2);
+        }
       }
       // `pixels` (forward.cu:629: one float atomic per contributing pair) counted by ballot and
       // flushed once per (warp, Gaussian); integer-valued floats < 2^24, exact in any order
@@ -247,11 +292,16 @@ blend_fwd_warp_kernel(const __grid_constant__ BlendFwdParams p) {
 void launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream) {
   if (p.T_total <= 0) return;
   const int smem = (GFT_BLOCK / 32) * WSTAGES * (int)sizeof(WarpStage);
-  // 4 resident blocks per SM (55 registers): 3 (67 registers) is 4-7 % slower, 5 (48 registers,
-  // 8 B spilled) 10-15 % slower on B200
-  static unsigned long long smem_ok = 0;
-  ensure_dynamic_smem(blend_fwd_warp_kernel<4>, smem, &smem_ok);
-  blend_fwd_warp_kernel<4><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
+  // 4 resident blocks per SM: 3 (67 registers) is 4-7 % slower, 5 (48 registers, 8 B spilled)
+  // 10-15 % slower on B200.  Option blend_half selects the two-halves walk.
+  static unsigned long long ok_full = 0, ok_half = 0;
+  if (option(OPT_BLEND_HALF) != 0) {
+    ensure_dynamic_smem(blend_fwd_warp_kernel<4, true>, smem, &ok_half);
+    blend_fwd_warp_kernel<4, true><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
+  } else {
+    ensure_dynamic_smem(blend_fwd_warp_kernel<4, false>, smem, &ok_full);
+    blend_fwd_warp_kernel<4, false><<<p.T_total, GFT_BLOCK, smem, stream>>>(p);
+  }
   note_launches(1);
 }
 

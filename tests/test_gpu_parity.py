@@ -541,6 +541,36 @@ def test_blend_backward_variants_agree(name):
             assert err <= harness.GRAD_REL_L2 * max(float(y.double().norm()), 1e-2 * scale), (key, harness.BWD_NAMES[i])
 
 
+@pytest.mark.parametrize("name", ["tiny", "ragged", "c1", "c1_init", "c1_dense", "c2"])
+def test_half_patch_blend_is_exact(name):
+    """Option blend_half: the blend warps walk their 8x4 patch as two independent 4x4 halves.  Per
+    pixel the same candidates arrive in the same order with the same arithmetic: every forward
+    output bit for bit (images, pixels counts, n_contrib), gradients up to atomic order."""
+    from gftorf_b200 import _capi
+    inp = harness.build_inputs(device="cuda", **CASES[name])
+    f0 = harness.call_forward(rasterizer._C, inp)
+    g0 = harness.call_backward(rasterizer._C, inp, f0)
+    old = _capi.set_option("blend_half", 1 - _capi.set_option("blend_half", 0))
+    try:
+        f1 = harness.call_forward(rasterizer._C, inp)
+        g1 = harness.call_backward(rasterizer._C, inp, f1)
+        torch.cuda.synchronize()
+    finally:
+        _capi.set_option("blend_half", old)
+    for i in range(1, 12):
+        assert torch.equal(f0[i], f1[i]), harness.FWD_NAMES[i]
+    d0 = debug.decode_buffers(f0[12], f0[13], f0[14], inp["P"], f0[0], inp["W"], inp["H"])
+    d1 = debug.decode_buffers(f1[12], f1[13], f1[14], inp["P"], f1[0], inp["W"], inp["H"])
+    for k in ("n_contrib", "final_T", "w_z_total", "w_z2_total"):
+        assert torch.equal(d0[k], d1[k]), k
+    scale = float(g0[8].double().norm())
+    for i, (x, y) in enumerate(zip(g1, g0)):
+        if x is None:
+            continue
+        err = float((x.double() - y.double()).norm())
+        assert err <= harness.GRAD_REL_L2 * max(float(y.double().norm()), 1e-2 * scale), harness.BWD_NAMES[i]
+
+
 def test_debug_mode_runs():
     inp = harness.build_inputs(device="cuda", **CASES["tiny"])
     e = inp["empty"]
