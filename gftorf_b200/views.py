@@ -31,7 +31,9 @@ MAX_VIEWS = _capi.GFT_MAX_VIEWS
 
 class ViewSpec(NamedTuple):
     """The per-camera fields of GaussianRasterizationSettings (__init__.py:22-40) plus the two
-    scalar ToF offsets that the reference passes per call."""
+    scalar ToF offsets that the reference passes per call.  `phase_offset` / `dc_offset` = None
+    means "the phase_offset / dc_offset argument of rasterize_views" (the optimised Parameters of
+    gaussian_renderer/__init__.py:126-127, which the reference hands to the ToF call only)."""
     image_height: int
     image_width: int
     tanfovx: float
@@ -44,15 +46,16 @@ class ViewSpec(NamedTuple):
     far_n: float = 100.0
     depth_range: float = 100.0
     use_view_dependent_phase: bool = False
-    phase_offset: float = 0.0
-    dc_offset: float = 0.0
+    phase_offset: Optional[float] = 0.0
+    dc_offset: Optional[float] = 0.0
 
     @classmethod
     def from_settings(cls, s, phase_offset=0.0, dc_offset=0.0):
         return cls(int(s.image_height), int(s.image_width), float(s.tanfovx), float(s.tanfovy), s.bg,
                    s.viewmatrix, s.projmatrix, s.campos, float(s.near_n), float(s.far_n),
-                   float(s.depth_range), bool(s.use_view_dependent_phase), _as_float(phase_offset),
-                   _as_float(dc_offset))
+                   float(s.depth_range), bool(s.use_view_dependent_phase),
+                   None if phase_offset is None else _as_float(phase_offset),
+                   None if dc_offset is None else _as_float(dc_offset))
 
 
 class ViewsForward:
@@ -75,7 +78,8 @@ def _fill_view(va, v, keep):
     va.tan_fovx, va.tan_fovy = float(v.tanfovx), float(v.tanfovy)
     va.near_n, va.far_n, va.depth_range = float(v.near_n), float(v.far_n), float(v.depth_range)
     va.use_view_dependent_phase = int(bool(v.use_view_dependent_phase))
-    va.phase_offset, va.dc_offset = _as_float(v.phase_offset), _as_float(v.dc_offset)
+    va.phase_offset = 0.0 if v.phase_offset is None else _as_float(v.phase_offset)
+    va.dc_offset = 0.0 if v.dc_offset is None else _as_float(v.dc_offset)
 
 
 def forward_views(means3D, opacities, scales, rotations, shs, shs_p, views: Sequence[ViewSpec],
@@ -308,7 +312,8 @@ class _RasterizeViews(torch.autograd.Function):
                 cov3Ds_precomp, phase_offset, dc_offset, views, sh_degree, scale_modifier,
                 optimize_phase_offset, optimize_dc_offset, debug):
         phase_f, dc_f = _as_float(phase_offset), _as_float(dc_offset)
-        specs = [v._replace(phase_offset=phase_f, dc_offset=dc_f) for v in views]
+        specs = [v._replace(phase_offset=phase_f if v.phase_offset is None else v.phase_offset,
+                            dc_offset=dc_f if v.dc_offset is None else v.dc_offset) for v in views]
         key = (means3D.device.index, int(means3D.shape[0]),
                tuple((int(v.image_height), int(v.image_width)) for v in specs))
         fwd = forward_views(means3D, opacities, scales, rotations, sh, sh_p, specs, sh_degree,
@@ -357,7 +362,9 @@ def rasterize_views(means3D, means2D, opacities, shs, shs_p, scales, rotations,
                     optimize_phase_offset=False, optimize_dc_offset=False, debug=False):
     """Differentiable batched call.  `means2D`: [V,P,3] dummy leaf (zeros) whose .grad receives the
     per-view screen-space gradients, the batched form of the reference's `screenspace_points`
-    (gaussian_renderer/__init__.py:27-31).  Returns a list of V tuples of the reference's 11
+    (gaussian_renderer/__init__.py:27-31).  `phase_offset` / `dc_offset` (floats, or 1-element
+    Parameters with optimize_*_offset) apply to the views whose ViewSpec leaves them None; their
+    gradient is the sum over all views.  Returns a list of V tuples of the reference's 11
     outputs."""
     if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')

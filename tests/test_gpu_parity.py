@@ -1143,6 +1143,43 @@ def test_rasterize_views_autograd_matches_two_reference_calls():
         assert harness.rel_l2(m2d.grad[v], rbs[v][0]) <= harness.GRAD_REL_L2
 
 
+@needs_ref
+def test_rasterize_views_optimised_offsets_go_to_the_tof_view_only():
+    """gaussian_renderer/__init__.py:126-127 hands the optimised phase / dc offsets to the ToF call
+    only.  In the batched surface the ToF view leaves its offsets None (= the call's Parameters),
+    the colour view keeps 0: outputs and the two scalar gradients equal the reference's calls."""
+    from gftorf_b200 import views as V
+    a, b = _two_camera_inputs(5000, (128, 96), (96, 64), 73, zero_shp_rest=True)
+    phase = torch.nn.Parameter(torch.tensor([0.25], device="cuda"))
+    dc = torch.nn.Parameter(torch.tensor([0.05], device="cuda"))
+    names = ("means3D", "opacities", "shs", "shs_p", "scales", "rotations")
+    leaves = {k: a[k].clone().requires_grad_(True) for k in names}
+    m2d = torch.zeros((2, 5000, 3), device="cuda", requires_grad=True)
+    specs = [_spec(a), _spec(b)._replace(phase_offset=None, dc_offset=None)]
+    outs = V.rasterize_views(leaves["means3D"], m2d, leaves["opacities"], leaves["shs"], leaves["shs_p"],
+                             leaves["scales"], leaves["rotations"], specs, 3, phase_offset=phase, dc_offset=dc,
+                             optimize_phase_offset=True, optimize_dc_offset=True)
+    # as in render(): the colour call's phasor image is discarded, the ToF call's colour image too
+    loss = (outs[0][0] * a["grads"]["color"]).sum() + (outs[0][2] * a["grads"]["depth"]).sum() \
+        + (outs[1][1] * b["grads"]["phasor"]).sum() + (outs[1][2] * b["grads"]["depth"]).sum()
+    loss.backward()
+    b2 = dict(b, phase_offset=0.25, dc_offset=0.05)
+    refs = [harness.call_forward(ref_driver.RefModule, inp) for inp in (a, b2)]
+    for o, r in zip(outs, refs):
+        for i in range(1, 10):
+            assert torch.equal(o[i], r[i + 1]), harness.FWD_NAMES[i + 1]
+    rbs = []
+    for vi, (inp, r) in enumerate(zip((a, b2), refs)):
+        g = dict(inp["grads"], acc=torch.zeros_like(inp["grads"]["acc"]),
+                 depth_distortion=torch.zeros_like(inp["grads"]["depth_distortion"]))
+        g["phasor" if vi == 0 else "color"] = torch.zeros_like(g["phasor" if vi == 0 else "color"])
+        rbs.append(harness.call_backward(ref_driver.RefModule, dict(inp, grads=g), r))
+    assert float(rbs[0][10].abs().sum()) == 0.0
+    assert harness.rel_l2(phase.grad, rbs[0][10] + rbs[1][10]) <= 1e-3
+    assert harness.rel_l2(dc.grad, rbs[0][11] + rbs[1][11]) <= 1e-3
+    assert harness.rel_l2(leaves["means3D"].grad, rbs[0][4] + rbs[1][4]) <= harness.GRAD_REL_L2
+
+
 def test_public_outputs_are_independent_tensors():
     """In-place edits of a returned image must be legal under autograd (the reference returns
     separate tensors), and the screen-space gradient must not pin the scratch allocation."""
