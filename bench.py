@@ -605,7 +605,7 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     h2d_bytes = sum(t.numel() * 4 for t in host_params.values()) + host_bg.numel() * 4 + sum(
         sum(t.numel() * 4 for t in (hv["viewmatrix"], hv["projmatrix"], hv["campos"])) +
         sum(g.numel() * 4 for g in hv["grads"].values()) for hv in host_views)
-    NB = 2 if impl == "ours" else 1
+    NB = 3 if impl == "ours" else 1      # staging sets in flight: the host enqueues up to two steps ahead of the link
     host_out_grads = [{k: torch.empty_like(host_params[k]).pin_memory() for k in names} for _ in range(NB)]
     host_imgs = [[torch.empty((11, v["H"], v["W"]), dtype=torch.float32).pin_memory() for v in views] for _ in range(NB)]
     d2h_bytes = sum(t.numel() * 4 for t in host_out_grads[0].values()) + sum(t.numel() * 4 for t in host_imgs[0])
@@ -720,6 +720,33 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
         if not pipelined:
             comp.synchronize()
 
+    # what the host link allows: the step's copies alone, each direction by itself and both at once
+    dimgs = [torch.empty((11, v["H"], v["W"]), dtype=torch.float32, device=dev) for v in views]
+
+    def copies(do_up, do_down, n=8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(comp)
+        up.wait_event(e0)
+        down.wait_event(e0)
+        for _ in range(n):
+            if do_up:
+                with torch.cuda.stream(up):
+                    upload(stage[0])
+            if do_down:
+                with torch.cuda.stream(down), torch.no_grad():
+                    for d, himg in zip(dimgs, host_imgs[0]):
+                        himg.copy_(d, non_blocking=True)
+                    for k in names:
+                        host_out_grads[0][k].copy_(stage[0]["params"][k].detach(), non_blocking=True)
+        comp.wait_stream(up)
+        comp.wait_stream(down)
+        e1.record(comp)
+        torch.cuda.synchronize(dev)
+        return round(e0.elapsed_time(e1) / n, 4)
+    copies(True, True, 2)
+    link = {"h2d_ms": copies(True, False), "d2h_ms": copies(False, True), "both_ms": copies(True, True)}
+
     # serial: upload -> compute -> download, one step at a time (round 1's e2e shape)
     it = [0]
 
@@ -756,10 +783,12 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     return {"value": round(npix_all / 1e6 * K / (ms / 1e3), 3), "unit": "Mpix/s", "ms_per_step": round(ms / K, 4),
             "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
             "serial_ms_per_step": round(serial_ms, 4),
+            "host_link_copies_only": dict(link, note="the same H2D / D2H copies of one step with no kernels between them: "
+                                                     "each direction alone, then both concurrently (the floor of the pipelined step)"),
             "l2": "every step's inputs arrive from the host (150 MB) and its results leave for it (136 MB): "
                   "the working set of a step exceeds the 126 MB L2; no extra flush in the pipelined region",
             "api": "gftorf_b200.rasterize_views(...) + torch.autograd.backward; H2D of step i+1 and D2H of step i-1 "
-                   "overlap the kernels of step i (3 streams, double-buffered pinned and device staging); "
+                   "overlap the kernels of step i (3 streams, triple-buffered pinned and device staging); "
                    "serial_ms_per_step = the same calls with upload -> compute -> download one after the other"}
 
 

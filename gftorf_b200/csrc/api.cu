@@ -464,7 +464,7 @@ int gft_forward_views(const GftForwardViewsArgs* a, gft_alloc_fn geom_alloc,
     unsigned long long* entries = reinterpret_cast<unsigned long long*>(bin + bl.entries);
     if (cap > 0) {
       { Stage st("scatter_entries", stream);
-        gft::launch_scatter_entries(pp, starts, cursors, entries, stream); }
+        gft::launch_scatter_entries(pp, starts, cursors, entries, (uint32_t)cap, stream); }
       GFT_CUDA_OK("scatter_entries");
       { Stage st("tile_sort", stream);
         gft::launch_tile_sort(ranges, (int)T_total, entries, point_list, (int)((size_t)cap / T_total), stream); }

@@ -168,7 +168,7 @@ tile_ranges_kernel(const uint32_t* __restrict__ starts, int T, int S, uint2* __r
 // grid: (ceil(P/256), nviews).  Same tile enumeration as the counting in the preprocess kernel.
 __global__ void __launch_bounds__(GFT_BLOCK)
 scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint32_t* __restrict__ starts,
-                       uint32_t* __restrict__ cursors, u64* __restrict__ entries) {
+                       uint32_t* __restrict__ cursors, u64* __restrict__ entries, uint32_t capacity) {
   const int v = blockIdx.y;
   const ViewCam& vc = p.views[v];
   const int idx = (int)(blockIdx.x * GFT_BLOCK + threadIdx.x);
@@ -183,13 +183,21 @@ scatter_entries_kernel(const __grid_constant__ PreprocessParams p, const uint32_
   }
   const uint32_t gx = (uint32_t)vc.grid_x, tb = (uint32_t)vc.tile_base;
   const uint32_t S = (uint32_t)p.sub_bins;
-  const float* __restrict__ depths = p.g.depths + v * P;
-  for_each_tile(rx0, ry0, rx1, tiles, (uint32_t)idx, lane, [&](uint32_t tx, uint32_t ty, uint32_t g) {
-    const uint32_t i = (tb + ty * gx + tx) * S + (g & (S - 1u));
-    const uint32_t slot = __ldg(starts + i) + atomicAdd(cursors + i, 1u);
-    if (slot < __ldg(starts + i + 1))   // only ever false when a caller's size hint was too small
-      entries[slot] = ((u64)__float_as_uint(__ldg(depths + g)) << 32) | (u64)g;
-  });
+  const uint32_t zbits = tiles ? __float_as_uint(__ldg(p.g.depths + v * P + idx)) : 0u;
+  // slot = start of the (tile, sub-bin) + the cursor's old value.  The starts are clamped to
+  // `capacity` by the scan, so slot >= capacity can only happen when a caller's size hint was too
+  // small (the call is then redone with the exact size); otherwise slot < starts[i + 1] holds by
+  // construction (a sub-bin hands out exactly as many slots as the preprocess counted).
+  for_each_tile_2phase(
+      rx0, ry0, rx1, tiles, (uint32_t)idx, zbits, lane,
+      [&](uint32_t tx, uint32_t ty, uint32_t g) {
+        const uint32_t i = (tb + ty * gx + tx) * S + (g & (S - 1u));
+        return make_uint2(__ldg(starts + i), atomicAdd(cursors + i, 1u));
+      },
+      [&](uint32_t g, uint32_t z, uint2 h) {
+        const uint32_t slot = h.x + h.y;
+        if (slot < capacity) entries[slot] = ((u64)z << 32) | (u64)g;
+      });
 }
 
 // ---- per-segment sort ----------------------------------------------------------------------
@@ -403,10 +411,10 @@ void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, ui
 }
 
 void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
-                            unsigned long long* entries, cudaStream_t stream) {
+                            unsigned long long* entries, uint32_t capacity, cudaStream_t stream) {
   if (pp.P <= 0) return;
   const dim3 grid((pp.P + GFT_BLOCK - 1) / GFT_BLOCK, pp.nviews);
-  scatter_entries_kernel<<<grid, GFT_BLOCK, 0, stream>>>(pp, starts, cursors, entries);
+  scatter_entries_kernel<<<grid, GFT_BLOCK, 0, stream>>>(pp, starts, cursors, entries, capacity);
   note_launches(1);
 }
 

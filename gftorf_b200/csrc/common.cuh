@@ -239,6 +239,51 @@ __device__ __forceinline__ void for_each_tile(uint32_t rx0, uint32_t ry0, uint32
   }
 }
 
+// The same walk in two phases, four tiles at a time: `acquire(tx, ty, payload)` returns two 32-bit
+// words (a loaded base and the old value of an atomic cursor) that `commit(payload, payload2, words)` uses.
+// The four acquires are issued before the first word is consumed, so four atomics are in flight
+// per lane instead of one (the scatter is bound by the round trip of the returning atomic).
+template <typename A, typename C>
+__device__ __forceinline__ void for_each_tile_2phase(uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t tiles,
+                                                     uint32_t payload, uint32_t payload2, uint32_t lane, A&& acquire,
+                                                     C&& commit) {
+  const uint32_t w = rx1 - rx0;
+  const uint32_t big = __ballot_sync(0xffffffffu, tiles > 32u);
+  if (tiles != 0u && tiles <= 32u) {
+    uint32_t tx = rx0, ty = ry0;
+    for (uint32_t k = 0; k < tiles; k += 4u) {
+      uint2 h[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u) {
+        h[u] = (k + u < tiles) ? acquire(tx, ty, payload) : make_uint2(0u, 0u);
+        if (++tx == rx1) { tx = rx0; ++ty; }
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u)
+        if (k + u < tiles) commit(payload, payload2, h[u]);
+    }
+  }
+  uint32_t m = big;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t bx0 = __shfl_sync(0xffffffffu, rx0, src), by0 = __shfl_sync(0xffffffffu, ry0, src);
+    const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, tiles, src);
+    const uint32_t bp = __shfl_sync(0xffffffffu, payload, src), bp2 = __shfl_sync(0xffffffffu, payload2, src);
+    for (uint32_t k = lane; k < bn; k += 128u) {
+      uint2 h[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u) {
+        const uint32_t kk = k + 32u * u;
+        h[u] = (kk < bn) ? acquire(bx0 + kk % bw, by0 + kk / bw, bp) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < 4u; ++u)
+        if (k + 32u * u < bn) commit(bp, bp2, h[u]);
+    }
+  }
+}
+
 // Lanes of the warp whose 8-bit digit equals this lane's, among the lanes with `ok` set: eight
 // ballots, one per digit bit (independent, pipelined).  The MATCH.ANY instruction gives the same
 // mask; measured on B200 the ballots make the per-tile radix sort 12 % faster (0.104 vs 0.117 ms

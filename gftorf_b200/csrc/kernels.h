@@ -107,8 +107,9 @@ void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, ui
                       unsigned long long* scan_state, cudaStream_t stream);
 // Every (view, Gaussian, tile) instance writes its entry (float_bits(view_z) << 32 | Gaussian id)
 // into its tile's segment, at a slot handed out by its sub-bin's atomic cursor (any order).
+// `capacity` is the clamp the scan was run with (= the number of entries the buffer holds).
 void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
-                            unsigned long long* entries, cudaStream_t stream);
+                            unsigned long long* entries, uint32_t capacity, cudaStream_t stream);
 // Sorts every tile segment on the 64-bit entry (depth bits, then Gaussian id): exactly the order
 // of the reference's stable radix sort of (tile << 32 | depth) keys over instances emitted in
 // ascending Gaussian order (rasterizer_impl.cu:90-110,334-339).  Writes the sorted entries back

@@ -273,6 +273,29 @@ def test_everything_culled_renders_background():
 
 
 @needs_ref
+def test_non_finite_positions_are_dropped_like_the_reference():
+    """NaN / inf positions never reach the sort: their radius converts to 0 (forward.cu:272-278) and
+    the Gaussian is dropped; everything else must stay bit-identical and their gradient rows zero."""
+    inp = harness.build_inputs(device="cuda", P=3000, W=96, H=64, seed=12)
+    bad = torch.arange(0, 3000, 37, device="cuda")
+    inp["means3D"] = inp["means3D"].clone()
+    inp["means3D"][bad[0::3]] = float("nan")
+    inp["means3D"][bad[1::3], 2] = float("inf")
+    inp["means3D"][bad[2::3], 0] = float("nan")
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    od, rd = decoded(inp, ours, ref)
+    harness.assert_forward_parity(harness.compare_forward(ours, ref, od, rd))
+    assert int((ours[11][bad] != 0).sum()) == 0 and ours[0] > 0
+    for i in range(1, 11):
+        assert bool(torch.isfinite(ours[i]).all())
+    ob = harness.call_backward(rasterizer._C, inp, ours)
+    for g in ob:
+        if g is not None and g.dim() >= 1 and g.shape[0] == 3000:
+            assert bool(torch.isfinite(g).all()) and float(g[bad].abs().sum()) == 0.0
+
+
+@needs_ref
 def test_single_gaussian():
     inp = harness.build_inputs(device="cuda", P=1, W=33, H=17, seed=9, sigma_px=6.0)
     inp["means3D"] = torch.tensor([[0.02, -0.01, 2.0]], device="cuda")

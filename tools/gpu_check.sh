@@ -13,11 +13,6 @@ for wl in c2 c1 c4; do
   python tools/stage_probe.py --workload $wl >> $out/stages_$tag.log 2>&1
   python tools/stage_probe.py --workload $wl --single >> $out/stages_$tag.log 2>&1
 done
-python tools/stage_probe.py --workload c2 --opt blend_half=1 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c4 --opt blend_half=1 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c2_init --opt blend_half=1 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c1 --opt blend_half=1 >> $out/stages_$tag.log 2>&1
-python tools/stage_probe.py --workload c2 --opt pfwd_minb=4 >> $out/stages_$tag.log 2>&1
 python tools/stage_probe.py --workload c2_init >> $out/stages_$tag.log 2>&1
 
 cat $out/stages_$tag.log
