@@ -266,7 +266,7 @@ class Timer:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(self, step_fn, K, W, flush=True, sampler=None):
+    def run(self, step_fn, K, W, flush=True, sampler=None, after_warmup=None):
         # collect BEFORE the warm-up and keep the collector off from there on: a collection between
         # the warm-up and the timed steps returns cached blocks to the allocator in a different
         # order, and the first timed step then pays for fresh cudaMallocs (seen as one 1.5-2x
@@ -276,7 +276,10 @@ class Timer:
         for _ in range(W):
             step_fn()
         self.barrier()
+        if after_warmup is not None:
+            after_warmup()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        host = []
         t0 = time.perf_counter()
         out = None
         for i in range(K):
@@ -285,13 +288,16 @@ class Timer:
             if flush:
                 self.flush.zero_()             # 256 MiB > 126 MB L2, untimed
             evs[i][0].record()
+            h0 = time.perf_counter()
             out = step_fn()
+            host.append((time.perf_counter() - h0) * 1e3)
             evs[i][1].record()
         self.barrier()
         self.wall_ms = (time.perf_counter() - t0) * 1e3
         gc.enable()
         ms = [a.elapsed_time(b) for a, b in evs]
         self.steps_ms = ms
+        self.host_ms = host                    # host time spent inside step_fn (enqueue + its own waits)
         total = torch.tensor([sum(ms)], dtype=torch.float64, device=self.dev)
         if self.world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
@@ -437,12 +443,16 @@ def run_gpu(args, impl):
 
     K, W = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local, every=max(1, K // 64)) if (rank == 0 and not args.no_clocks) else None
-    for _ in range(W):        # launch counting starts after the warm-up (smem attribute calls etc.)
-        step_resident()
-    n0 = arm.capi.launch_count() if impl == "ours" else 0
-    total_ms, stats = timer.run(step_resident, K, 0, sampler=sampler)
-    launches = (arm.capi.launch_count() - n0) if impl == "ours" else None
+    n0 = [0]
+
+    def mark():               # launch counting starts after the warm-up (smem attribute calls etc.)
+        n0[0] = arm.capi.launch_count() if impl == "ours" else 0
+    total_ms, stats = timer.run(step_resident, K, W, sampler=sampler, after_warmup=mark)
+    launches = (arm.capi.launch_count() - n0[0]) if impl == "ours" else None
     step_ms = list(timer.steps_ms)
+    worst = max(range(K), key=lambda i: step_ms[i])
+    slowest = {"index": worst, "gpu_ms": round(step_ms[worst], 4), "host_ms_in_step_fn": round(timer.host_ms[worst], 4),
+               "median_host_ms_in_step_fn": round(sorted(timer.host_ms)[K // 2], 4)}
     wall_ms = timer.wall_ms
     clocks = sampler.result() if sampler is not None else None
 
@@ -513,6 +523,7 @@ def run_gpu(args, impl):
                        if impl == "ours" else "one call per view, default stream (the reference's call shape)"),
         "fwd_bwd_ms_per_iter": round(total_ms / K, 4),
         "step_ms_min_med_max": min_med_max(step_ms),
+        "slowest_step": slowest,
         "wall_ms_total_incl_flush": round(wall_ms, 2),
         "render_mpix_s": round(mpix * K / (render_ms / 1e3), 3),
         "render_ms_per_step": round(render_ms / K, 4),
@@ -676,14 +687,22 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     ev_comp = [torch.cuda.Event() for _ in range(NB)]
     ev_down = [torch.cuda.Event() for _ in range(NB)]
 
-    def one(i, pipelined):
+    def prefetch(i):
+        """Enqueue the upload of step i's inputs (pipelined mode)."""
+        b = i % NB
+        up.wait_event(ev_comp[b])          # the staging set is free once its previous compute is done
+        with torch.cuda.stream(up):
+            upload(stage[b])
+            ev_up[b].record(up)
+
+    def one(i, pipelined, more=True):
         b = i % NB if pipelined else 0
         s = stage[b]
         if pipelined:
-            up.wait_event(ev_comp[b])          # the staging set is free once its previous compute is done
-            with torch.cuda.stream(up):
-                upload(s)
-                ev_up[b].record(up)
+            # the forward call blocks the host until the GPU has counted the tile instances, so the
+            # NEXT step's upload is enqueued first: the link never waits for the host
+            if more:
+                prefetch(i + 1)
             comp.wait_event(ev_up[b])
         else:
             upload(s)
@@ -762,15 +781,18 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
         e.record(comp)
     gc.collect()
     gc.disable()
+    prefetch(0)
     for i in range(W):
-        one(i, True)
+        one(i, True, more=i + 1 < W)
     comp.wait_stream(down)
     comp.wait_stream(up)
     timer.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(comp)
+    up.wait_event(e0)                      # every copy of the K timed steps lies between the two events
+    prefetch(W)
     for i in range(K):
-        one(W + i, True)
+        one(W + i, True, more=i + 1 < K)
     comp.wait_stream(down)
     comp.wait_stream(up)
     e1.record(comp)
@@ -788,7 +810,8 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
             "l2": "every step's inputs arrive from the host (150 MB) and its results leave for it (136 MB): "
                   "the working set of a step exceeds the 126 MB L2; no extra flush in the pipelined region",
             "api": "gftorf_b200.rasterize_views(...) + torch.autograd.backward; H2D of step i+1 and D2H of step i-1 "
-                   "overlap the kernels of step i (3 streams, triple-buffered pinned and device staging); "
+                   "overlap the kernels of step i (3 streams, triple-buffered pinned and device staging; the upload of step i+1 is "
+                   "enqueued before the forward call of step i, which blocks the host while it learns the instance count); "
                    "serial_ms_per_step = the same calls with upload -> compute -> download one after the other"}
 
 

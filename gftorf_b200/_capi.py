@@ -238,6 +238,6 @@ def launch_count():
 def set_option(name, value):
     """Flip a kernel tunable / A-B switch (include/gftorf.h: gft_set_option); returns the old value."""
     old = lib().gft_set_option(name.encode(), int(value))
-    if old < 0 and name not in ("sort_cap", "sort_radix", "sub_bins", "sort_match", "tile_order", "bwd_ring", "pfwd_minb", "blend_half", "bwd_pred", "pbwd_minb", "no_cull"):
+    if old < 0 and name not in ("sort_cap", "sort_radix", "sub_bins", "sort_match", "tile_order", "bwd_ring", "pfwd_minb", "blend_half", "sort_adapt", "bwd_pred", "pbwd_minb", "no_cull"):
         raise KeyError(name)
     return old

@@ -224,6 +224,7 @@ const OptDef kOpts[OPT_COUNT] = {
     {"bwd_ring", "GFT_BWD_RING", 1},     // 0: block-wide double buffer instead of the mbarrier ring in the blend backward
     {"pfwd_minb", "GFT_PFWD_MINB", 3},   // resident blocks per SM the preprocess forward is compiled for (3 or 4)
     {"blend_half", "GFT_BLEND_HALF", 0}, // 1: blend warps walk their 8x4 patch as two independent 4x4 halves
+    {"sort_adapt", "GFT_SORT_ADAPT", 1}, // 0: four radix passes over all 32 depth bits instead of <= 3 over the bits that vary in the tile
 };
 std::atomic<int> g_opt[OPT_COUNT];
 std::atomic<bool> g_opt_init{false};

@@ -244,15 +244,20 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
   return n <= 1u ? 1u : (1u << (32 - __clz(n - 1u)));
 }
 
-// Stable LSD radix sort of s_a[0,n) on bits [32,64) (the depth bits), 8 bits per pass, ping-pong
-// between s_a and s_b; the result is back in s_a.  256 threads = 256 digit bins.  Warp w owns the
-// contiguous span [w*span, (w+1)*span) and walks it 32 entries at a time, so ranks follow the
-// current order (stability): per pass a per-warp digit histogram (shared-memory atomics), an
-// exclusive scan over (digit, warp), then every 32-entry row is ranked with match_any against the
-// warp's running digit offsets and scattered into the other buffer.
+// Stable LSD radix sort of s_a[0,n) on `passes` 8-bit digits of (depth_bits - kmin) >> sh0, ping-pong
+// between s_a and s_b; returns the buffer that holds the result.  kmin is the segment's smallest
+// depth word, so only the bits in which the segment's depths actually differ are sorted: at most
+// the top 24 of them (3 passes; 2 or 1 when the depths of a tile span fewer bits) — whatever
+// order the remaining low bits and the index ties need is restored by the caller's fix-up.
+// 256 threads = 256 digit bins.  Warp w owns the contiguous span [w*span, (w+1)*span) and walks it
+// 32 entries at a time, so ranks follow the current order (stability): per pass a per-warp digit
+// histogram (shared-memory atomics), an exclusive scan over (digit, warp), then every 32-entry
+// row is ranked by digit matching against the warp's running digit offsets and scattered into
+// the other buffer.
 template <bool HW_MATCH>
-__device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint32_t* s_hist,
-                                                        uint32_t* s_wtot, uint32_t n) {
+__device__ __forceinline__ u64* radix_depth_sort_shared(u64* s_a, u64* s_b, uint32_t* s_hist,
+                                                        uint32_t* s_wtot, uint32_t n, uint32_t kmin,
+                                                        uint32_t sh0, int passes) {
   constexpr int WARPS = SORT_THREADS / 32;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t items = (n + SORT_THREADS - 1) / SORT_THREADS;
@@ -260,13 +265,13 @@ __device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint
   const uint32_t w0 = warp * span;
   u64* src = s_a;
   u64* dst = s_b;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 32 + 8 * pass;
+  for (int pass = 0; pass < passes; ++pass) {
+    const uint32_t shift = sh0 + 8u * (uint32_t)pass;
     for (uint32_t i = tid; i < WARPS * 256u; i += SORT_THREADS) s_hist[i] = 0u;
     __syncthreads();
     for (uint32_t i = 0; i < items; ++i) {
       const uint32_t e = w0 + i * 32u + lane;
-      if (e < n) atomicAdd(&s_hist[warp * 256u + ((uint32_t)(src[e] >> shift) & 0xffu)], 1u);
+      if (e < n) atomicAdd(&s_hist[warp * 256u + ((((uint32_t)(src[e] >> 32) - kmin) >> shift) & 0xffu)], 1u);
     }
     __syncthreads();
     {
@@ -297,7 +302,7 @@ __device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint
       const uint32_t e = w0 + i * 32u + lane;
       const bool ok = e < n;
       const u64 key = ok ? src[e] : 0ull;
-      const uint32_t d = ok ? ((uint32_t)(key >> shift) & 0xffu) : 0x100u + lane;   // padding lanes match nobody
+      const uint32_t d = ok ? ((((uint32_t)(key >> 32) - kmin) >> shift) & 0xffu) : 0x100u + lane;   // padding lanes match nobody
       const uint32_t peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit8(d, ok);
       const uint32_t leader = __ffs(peers) - 1;
       uint32_t old = 0;
@@ -312,14 +317,15 @@ __device__ __forceinline__ void radix_depth_sort_shared(u64* s_a, u64* s_b, uint
     __syncthreads();
     u64* t = src; src = dst; dst = t;
   }
+  return src;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
-                 uint32_t* __restrict__ point_list, uint32_t cap, int use_radix) {
+                 uint32_t* __restrict__ point_list, uint32_t cap, int use_radix, int adapt) {
   extern __shared__ __align__(16) unsigned char sort_smem_raw[];
   u64* s = reinterpret_cast<u64*>(sort_smem_raw);
-  __shared__ uint32_t s_wtot[SORT_THREADS / 32];
+  __shared__ uint32_t s_wtot[SORT_THREADS / 32], s_wmax[SORT_THREADS / 32];
   const uint2 rg = ranges[blockIdx.x];
   const uint32_t n = rg.y - rg.x;
   if (n == 0u) return;
@@ -328,26 +334,66 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
   const uint32_t tid = threadIdx.x;
 
   if (n <= cap) {
-    for (uint32_t i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
-    __syncthreads();
-    bool need_full = true;
-    if (use_radix && n > 32u) {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    uint32_t zlo = 0xffffffffu, zhi = 0u;
+    for (uint32_t i = tid; i < n; i += SORT_THREADS) {
+      const u64 e = g[i];
+      s[i] = e;
+      zlo = min(zlo, (uint32_t)(e >> 32));
+      zhi = max(zhi, (uint32_t)(e >> 32));
+    }
+    u64* cur = s;
+    bool unsorted = true, try_fixup = false;
+    const bool radix = use_radix && n > 32u;
+    if (radix) {
+      zlo = __reduce_min_sync(0xffffffffu, zlo);
+      zhi = __reduce_max_sync(0xffffffffu, zhi);
+      if (lane == 0) { s_wtot[warp] = zlo; s_wmax[warp] = zhi; }
+    }
+    __syncthreads();                                       // the segment (and the warps' min / max) are in shared memory
+    if (radix) {
+#pragma unroll
+      for (int w = 0; w < SORT_THREADS / 32; ++w) { zlo = min(zlo, s_wtot[w]); zhi = max(zhi, s_wmax[w]); }
+      __syncthreads();                                     // s_wtot is reused by the radix passes
+      // the depth words of this tile differ in their low `bits` bits only (after subtracting the
+      // smallest): sort on the top min(bits, 24) of those
+      if (!adapt) { zlo = 0u; zhi = 0xffffffffu; }         // A/B: all 32 bits in four passes
+      const uint32_t bits = 32u - (uint32_t)__clz(zhi - zlo);
+      const int passes = adapt ? (int)min(3u, (bits + 7u) >> 3) : 4;
+      const uint32_t sh0 = (adapt && bits > 24u) ? bits - 24u : 0u;
       u64* s_b = s + cap;
       uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_b + cap);
-      if (use_radix == 2) radix_depth_sort_shared<true>(s, s_b, s_hist, s_wtot, n);
-      else radix_depth_sort_shared<false>(s, s_b, s_hist, s_wtot, n);
-      // equal depths must be in ascending index order; the slots came from atomics, so a tie may
-      // be the wrong way round — then (and only then) the whole 64-bit entries are sorted
+      cur = use_radix == 2 ? radix_depth_sort_shared<true>(s, s_b, s_hist, s_wtot, n, zlo, sh0, passes)
+                           : radix_depth_sort_shared<false>(s, s_b, s_hist, s_wtot, n, zlo, sh0, passes);
+      // What is left: entries that agree in the sorted bits (a few low depth bits when the tile's
+      // depths span more than 24 bits; equal depths, whose slots came from atomics in any order)
+      // may be the wrong way round.  Such runs are short, so an odd-even transposition on the
+      // whole 64-bit entries restores (depth bits, index) order in one or two rounds; only a tile
+      // that still moves after 8 rounds takes the bitonic network.
       int bad = 0;
-      for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS) bad |= (s[i] > s[i + 1]) ? 1 : 0;
-      need_full = __syncthreads_or(bad) != 0;
+      for (uint32_t i = tid; i + 1 < n; i += SORT_THREADS) bad |= (cur[i] > cur[i + 1]) ? 1 : 0;
+      unsorted = __syncthreads_or(bad) != 0;
+      try_fixup = unsorted;
     }
-    if (need_full) {
+    for (int round = 0; try_fixup && unsorted && round < 8; ++round) {
+      int moved = 0;
+      for (uint32_t a = 2u * tid; a + 1u < n; a += 2u * SORT_THREADS) {
+        const u64 x = cur[a], y = cur[a + 1];
+        if (x > y) { cur[a] = y; cur[a + 1] = x; moved = 1; }
+      }
+      __syncthreads();
+      for (uint32_t a = 2u * tid + 1u; a + 1u < n; a += 2u * SORT_THREADS) {
+        const u64 x = cur[a], y = cur[a + 1];
+        if (x > y) { cur[a] = y; cur[a + 1] = x; moved = 1; }
+      }
+      unsorted = __syncthreads_or(moved) != 0;
+    }
+    if (unsorted) {
       const uint32_t m = next_pow2(n);
-      for (uint32_t k = 2; k <= m; k <<= 1) level_in_shared(s, n, k, true, m >> 1);
+      for (uint32_t k = 2; k <= m; k <<= 1) level_in_shared(cur, n, k, true, m >> 1);
     }
     for (uint32_t i = tid; i < n; i += SORT_THREADS) {
-      const u64 e = s[i];
+      const u64 e = cur[i];
       g[i] = e;
       pl[i] = (uint32_t)e;
     }
@@ -432,7 +478,8 @@ void launch_tile_sort(const uint2* ranges, int T_total, unsigned long long* entr
   const int smem = use_radix ? (int)cap * 16 + 8 * 256 * 4 : (int)cap * 8;
   static unsigned long long smem_ok = 0;
   ensure_dynamic_smem(tile_sort_kernel, 8192 * 16 + 8 * 256 * 4, &smem_ok);
-  tile_sort_kernel<<<T_total, SORT_THREADS, smem, stream>>>(ranges, entries, point_list, cap, use_radix);
+  tile_sort_kernel<<<T_total, SORT_THREADS, smem, stream>>>(ranges, entries, point_list, cap, use_radix,
+                                                            option(OPT_SORT_ADAPT) != 0 ? 1 : 0);
   note_launches(1);
 }
 

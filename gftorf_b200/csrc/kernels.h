@@ -34,7 +34,7 @@ inline void ensure_dynamic_smem(K kernel, int bytes, unsigned long long* done_ma
 int sm_count();
 
 // Tunables / A-B switches (gft_set_option in the C ABI; defaults from the environment, read once).
-enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_SORT_RADIX, OPT_SUB_BINS, OPT_SORT_MATCH, OPT_TILE_ORDER, OPT_BWD_RING, OPT_PFWD_MINB, OPT_BLEND_HALF, OPT_COUNT };
+enum { OPT_SORT_CAP = 0, OPT_BWD_PRED, OPT_PBWD_MINB, OPT_NO_CULL, OPT_SORT_RADIX, OPT_SUB_BINS, OPT_SORT_MATCH, OPT_TILE_ORDER, OPT_BWD_RING, OPT_PFWD_MINB, OPT_BLEND_HALF, OPT_SORT_ADAPT, OPT_COUNT };
 int option(int id);
 
 // Records the thread-local error string behind gft_last_error() and returns `code` (api.cu).

@@ -365,7 +365,7 @@ int gft_profile_read(float* ms, const char** names, int cap);
 unsigned long long gft_launch_count(void);
 
 /* Tunables / A-B switches of the kernels ("sort_cap", "sort_radix", "sort_match", "sub_bins",
- * "tile_order", "bwd_pred", "bwd_ring", "pbwd_minb", "no_cull"; defaults
+ * "sort_adapt", "tile_order", "bwd_pred", "bwd_ring", "pbwd_minb", "pfwd_minb", "blend_half", "no_cull"; defaults
  * come from the environment variables GFT_SORT_CAP, ... read once).  Returns the previous value,
  * <0 for an unknown name.  Results never depend on them, only speed. */
 int gft_set_option(const char* name, int value);

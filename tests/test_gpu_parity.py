@@ -4,6 +4,7 @@
   (3) the CPU restatement (oracle/libgft_oracle.so) where the reference itself is undefined.
 Tolerances are north_star's: integers bit-exact, images <= 1e-5 abs, gradients <= 1e-4 rel-L2.
 """
+import math
 import os
 
 import pytest
@@ -464,21 +465,62 @@ def test_tile_sort_paths_agree_bitwise(name):
     from gftorf_b200 import _capi
     inp = harness.build_inputs(device="cuda", **CASES[name])
     outs = {}
-    configs = [(0, 1), (256, 1), (1024, 1), (8192, 1), (0, 0), (256, 0)]     # (sort_cap, sort_radix)
-    for cap, radix in configs:
+    # (sort_cap, sort_radix, sort_adapt)
+    configs = [(0, 1, 1), (256, 1, 1), (1024, 1, 1), (8192, 1, 1), (0, 0, 1), (256, 0, 1), (0, 1, 0), (8192, 1, 0)]
+    for cap, radix, adapt in configs:
         old = _capi.set_option("sort_cap", cap)
         old_r = _capi.set_option("sort_radix", radix)
+        old_a = _capi.set_option("sort_adapt", adapt)
         try:
             f = harness.call_forward(rasterizer._C, inp)
             d = debug.decode_buffers(f[12], f[13], f[14], inp["P"], f[0], inp["W"], inp["H"])
-            outs[(cap, radix)] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone(), f[2].clone())
+            outs[(cap, radix, adapt)] = (d["keys"].clone(), d["point_list"].clone(), f[1].clone(), f[2].clone())
         finally:
             _capi.set_option("sort_cap", old)
             _capi.set_option("sort_radix", old_r)
+            _capi.set_option("sort_adapt", old_a)
     assert int(d["tile_counts"].max()) > 256
     for cfg in configs[1:]:
         for a, b in zip(outs[configs[0]], outs[cfg]):
             assert torch.equal(a, b), cfg
+
+
+@needs_ref
+@pytest.mark.parametrize("spread", ["wide", "narrow", "clustered", "two_values"])
+def test_tile_sort_over_depth_spreads(spread):
+    """The per-tile radix sort looks only at the bits in which a tile's depths differ (at most the
+    top 24 of them) and leaves the rest to a short odd-even fix-up; depth distributions that
+    stress each branch: depths over nine binades (more than 24 varying bits, low bits left to the
+    fix-up), depths a few ulps apart (one or two passes), thousands of depths inside one bucket
+    next to far outliers (the fix-up gives up and the bitonic network sorts), and two distinct
+    values only.  The lists must be the reference's, bit for bit."""
+    inp = harness.build_inputs(device="cuda", P=40000, W=160, H=120, kind="trained", seed=82, sigma_px=3.0)
+    P = inp["P"]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    z0 = inp["means3D"][:, 2].clone()
+    if spread == "wide":
+        zt = torch.exp(torch.empty(P).uniform_(math.log(0.25), math.log(120.0), generator=g)).cuda()
+    elif spread == "narrow":
+        zt = (2.0 + torch.randint(0, 3000, (P,), generator=g).float() * 2.3841858e-07).cuda()
+    elif spread == "clustered":
+        zt = (3.0 + torch.randint(0, 6, (P,), generator=g).float() * 2.3841858e-07).cuda()
+        far = torch.arange(P, device="cuda") % 50 == 0
+        zt = torch.where(far, torch.full_like(zt, 90.0), zt)
+        zt = torch.where(torch.arange(P, device="cuda") % 50 == 1, torch.full_like(zt, 0.3), zt)
+    else:
+        zt = torch.where(torch.arange(P, device="cuda") % 2 == 0, torch.tensor(1.5, device="cuda"),
+                         torch.tensor(1.5000001, device="cuda"))
+    f = (zt / z0).unsqueeze(1)
+    inp["means3D"] = inp["means3D"] * f              # same pixel, new depth (identity camera)
+    inp["scales"] = inp["scales"] * f
+    ours = harness.call_forward(rasterizer._C, inp)
+    ref = harness.call_forward(ref_driver.RefModule, inp)
+    od, rd = decoded(inp, ours, ref)
+    assert ours[0] == ref[0] and ours[0] > 20000
+    assert torch.equal(od["point_list"], rd["point_list"])
+    assert torch.equal(od["keys"], rd["keys"])
+    for i in range(1, 12):
+        assert torch.equal(ours[i], ref[i]), harness.FWD_NAMES[i]
 
 
 def test_equal_depths_keep_ascending_index_order():

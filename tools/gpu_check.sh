@@ -5,7 +5,7 @@
 tag=${1:-chk}
 out=gpurun_out
 mkdir -p $out
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "test_blend_backward_variants_agree or test_half_patch" > $out/ring_$tag.log 2>&1; echo "ring test rc=$?"; tail -3 $out/ring_$tag.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "test_blend_backward_variants_agree or test_tile_sort or test_equal_depths" > $out/ring_$tag.log 2>&1; echo "ring test rc=$?"; tail -3 $out/ring_$tag.log
 timeout 1500 python -m pytest tests -m gpu -q -rs --maxfail=25 --tb=short > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
 tail -40 $out/pytest_gpu_$tag.log
 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -3 $out/smoke_$tag.log
@@ -14,6 +14,8 @@ for wl in c2 c1 c4; do
   python tools/stage_probe.py --workload $wl --single >> $out/stages_$tag.log 2>&1
 done
 python tools/stage_probe.py --workload c2_init >> $out/stages_$tag.log 2>&1
+python tools/stage_probe.py --workload c5 >> $out/stages_$tag.log 2>&1
+for wl in c2 c4 c2_init; do python tools/stage_probe.py --workload $wl --opt sort_adapt=0 >> $out/stages_$tag.log 2>&1; done
 
 cat $out/stages_$tag.log
 if [ "$2" == "bench" ]; then
