@@ -304,6 +304,14 @@ class Timer:
         return float(total.item()), out
 
 
+def slowest_step(timer):
+    """Which timed step was the slowest, its device time and the host time spent inside step_fn."""
+    ms, host = timer.steps_ms, timer.host_ms
+    w = max(range(len(ms)), key=lambda i: ms[i])
+    return {"index": w, "gpu_ms": round(ms[w], 4), "host_ms_in_step_fn": round(host[w], 4),
+            "median_host_ms_in_step_fn": round(sorted(host)[len(host) // 2], 4)}
+
+
 def min_med_max(ms):
     s = sorted(ms)
     return [round(s[0], 4), round(s[len(s) // 2], 4), round(s[-1], 4)]
@@ -450,9 +458,7 @@ def run_gpu(args, impl):
     total_ms, stats = timer.run(step_resident, K, W, sampler=sampler, after_warmup=mark)
     launches = (arm.capi.launch_count() - n0[0]) if impl == "ours" else None
     step_ms = list(timer.steps_ms)
-    worst = max(range(K), key=lambda i: step_ms[i])
-    slowest = {"index": worst, "gpu_ms": round(step_ms[worst], 4), "host_ms_in_step_fn": round(timer.host_ms[worst], 4),
-               "median_host_ms_in_step_fn": round(sorted(timer.host_ms)[K // 2], 4)}
+    slowest = slowest_step(timer)
     wall_ms = timer.wall_ms
     clocks = sampler.result() if sampler is not None else None
 
@@ -687,13 +693,23 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     ev_comp = [torch.cuda.Event() for _ in range(NB)]
     ev_down = [torch.cuda.Event() for _ in range(NB)]
 
+    trace = [] if os.environ.get("GFT_E2E_TRACE") else None
+
+    def mark(stream, tag, i):
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            trace.append((tag, i, e, time.perf_counter()))
+
     def prefetch(i):
         """Enqueue the upload of step i's inputs (pipelined mode)."""
         b = i % NB
         up.wait_event(ev_comp[b])          # the staging set is free once its previous compute is done
         with torch.cuda.stream(up):
+            mark(up, "U0", i)
             upload(stage[b])
             ev_up[b].record(up)
+            mark(up, "U1", i)
 
     def one(i, pipelined, more=True):
         b = i % NB if pipelined else 0
@@ -704,6 +720,7 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
             if more:
                 prefetch(i + 1)
             comp.wait_event(ev_up[b])
+            mark(comp, "C0", i)
         else:
             upload(s)
         for k in names:
@@ -718,12 +735,16 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
             g = dv["grads"]
             tens += [o[0], o[1], o[2], o[4], o[6]]
             gr += [g["color"], g["phasor"], g["depth"], g["acc"], g["depth_distortion"]]
+        if pipelined:
+            mark(comp, "Cf", i)
         torch.autograd.backward(tens, gr)
         ev_comp[b].record(comp)
         tgt = down if pipelined else comp
         if pipelined:
+            mark(comp, "C1", i)
             ev_down[b].synchronize()           # host: the previous results in this host set have landed
             down.wait_event(ev_comp[b])
+            mark(down, "D0", i)
         with torch.cuda.stream(tgt), torch.no_grad():
             for o, himg in zip(outs, host_imgs[b]):
                 himg[0:3].copy_(o[0], non_blocking=True)
@@ -736,6 +757,8 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
                 host_out_grads[b][k].copy_(gk, non_blocking=True)
                 gk.record_stream(tgt)
             ev_down[b].record(tgt)
+            if pipelined:
+                mark(tgt, "D1", i)
         if not pipelined:
             comp.synchronize()
 
@@ -802,6 +825,14 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     ms = float(tot.item())
+    if trace is not None:      # GPU and host timeline of the timed steps (ms since the first event), for diagnosis
+        t_host0 = None
+        for tag, i, e, th in trace:
+            if i < W or i > W + 6:
+                continue
+            t_host0 = th if t_host0 is None else t_host0
+            print(f"e2e-trace step {i - W} {tag}: gpu {e0.elapsed_time(e):8.3f} ms   host-enqueue {(th - t_host0) * 1e3:8.3f} ms",
+                  file=sys.stderr)
     return {"value": round(npix_all / 1e6 * K / (ms / 1e3), 3), "unit": "Mpix/s", "ms_per_step": round(ms / K, 4),
             "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
             "serial_ms_per_step": round(serial_ms, 4),
@@ -851,7 +882,7 @@ def c4_block(arm, impl, dev, timer, rank, world):
                        f"{len(mine)} camera(s) on this rank, fwd+bwd of all views + gradient allreduce",
            "scaling": "strong", "cameras_per_iter": 8, "n_gpus": world,
            "ms_per_iter": round(ms / K, 3), "ms_per_iter_median": min_med_max(timer.steps_ms)[1],
-           "iter_ms_min_med_max": min_med_max(timer.steps_ms),
+           "iter_ms_min_med_max": min_med_max(timer.steps_ms), "slowest_iter": slowest_step(timer),
            "mpix_s": round(8 * (1920 * 1080 + 640 * 480) / 1e6 * K / (ms / 1e3), 2)}
     if rank == 0 and stats:
         Vs, Rs = view_stats(arm, stats, views)

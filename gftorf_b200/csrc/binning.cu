@@ -46,7 +46,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_starts_kernel(const uint32_t* __restrict__ counts, int n, uint32_t capacity,
                    uint32_t* __restrict__ starts, uint32_t* __restrict__ hdr,
-                   unsigned long long* __restrict__ state) {
+                   unsigned long long* __restrict__ state, uint32_t* __restrict__ host_R) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
   __shared__ uint32_t s_bid, s_prefix;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,6 +121,9 @@ scan_starts_kernel(const uint32_t* __restrict__ counts, int n, uint32_t capacity
     const uint32_t R = s_prefix + total;
     starts[n] = min(R, capacity);
     hdr[1] = R;   // num_rendered
+    // ... and straight into the caller's mapped pinned word: the host learns R from this store
+    // plus an event, with no copy-engine transfer behind whatever bulk copies other streams queued
+    if (host_R) { *reinterpret_cast<volatile uint32_t*>(host_R) = R; __threadfence_system(); }
   }
 }
 
@@ -448,10 +451,10 @@ tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ entries,
 
 void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
                       uint32_t* starts, uint2* ranges, uint32_t* order, uint32_t* hdr,
-                      unsigned long long* scan_state, cudaStream_t stream) {
+                      unsigned long long* scan_state, uint32_t* host_R, cudaStream_t stream) {
   const int n = T_total * sub_bins;
   scan_starts_kernel<<<(n + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, stream>>>(tile_counts, n, capacity, starts,
-                                                                                  hdr, scan_state);
+                                                                                  hdr, scan_state, host_R);
   tile_ranges_kernel<<<1, SCAN_THREADS, 0, stream>>>(starts, T_total, sub_bins, ranges, order);
   note_launches(2);
 }

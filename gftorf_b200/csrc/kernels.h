@@ -104,7 +104,7 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
 // (only ever effective when a caller's size hint was too small; the forward is then repeated).
 void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, uint32_t capacity,
                       uint32_t* starts, uint2* ranges, uint32_t* order, uint32_t* hdr,
-                      unsigned long long* scan_state, cudaStream_t stream);
+                      unsigned long long* scan_state, uint32_t* host_R, cudaStream_t stream);
 // Every (view, Gaussian, tile) instance writes its entry (float_bits(view_z) << 32 | Gaussian id)
 // into its tile's segment, at a slot handed out by its sub-bin's atomic cursor (any order).
 // `capacity` is the clamp the scan was run with (= the number of entries the buffer holds).
