@@ -273,15 +273,19 @@ class Timer:
         # straggler at the start of every timed region, in both arms)
         gc.collect()
         gc.disable()      # a cyclic-GC pause inside a 2 ms step would be charged to the step
+        out = None
         for _ in range(W):
-            step_fn()
+            # keep the previous step's result alive while the next one runs, exactly like the timed
+            # loop below: the allocator then owns two sets of workspaces before the timing starts
+            # (otherwise the SECOND timed step pays the cudaMalloc of the second set: 5-240 ms,
+            # the "one straggler per run" of round 1)
+            out = step_fn()
         self.barrier()
         if after_warmup is not None:
             after_warmup()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         host = []
         t0 = time.perf_counter()
-        out = None
         for i in range(K):
             if sampler is not None:
                 sampler.sample()               # clocks under load, outside the step's events
