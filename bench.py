@@ -208,7 +208,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": "nvml"}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
                 "sm_mhz_min": float(min(self.sm)), "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "source": "nvml, sampled by the timing thread before every timed step"}
+                "source": "nvml, sampled by the timing thread right after enqueuing every timed step (its kernels still running)"}
 
 
 def stage_bytes(stage, P, V, R, N, T, nviews=1):
@@ -287,8 +287,6 @@ class Timer:
         host = []
         t0 = time.perf_counter()
         for i in range(K):
-            if sampler is not None:
-                sampler.sample()               # clocks under load, outside the step's events
             if flush:
                 self.flush.zero_()             # 256 MiB > 126 MB L2, untimed
             evs[i][0].record()
@@ -296,6 +294,11 @@ class Timer:
             out = step_fn()
             host.append((time.perf_counter() - h0) * 1e3)
             evs[i][1].record()
+            if sampler is not None:
+                # clocks under load: the step's last kernels (and its exchange) are still running
+                # when the host gets here.  Sampling BEFORE the step delayed rank 0's start by the
+                # NVML call, and the other ranks measured that delay inside their allreduce.
+                sampler.sample()
         self.barrier()
         self.wall_ms = (time.perf_counter() - t0) * 1e3
         gc.enable()

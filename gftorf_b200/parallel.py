@@ -126,6 +126,7 @@ class GradBucket:
             cur += (n + 3) // 4 * 4  # 16-byte aligned slices
         self.sizes = sizes
         self._symm = None
+        self.fused_shape = (64, 2)   # (blocks, unroll) of the one-kernel NVLS allreduce: best of the sweep at 4 and 8 GPUs
         self.mode = "nccl"
         self.tuning = None
         if symmetric:
@@ -167,8 +168,12 @@ class GradBucket:
             return
         keep = self.flat.clone()
         res = {}
-        for mode in ("nccl", "nvls", "nvls_fused"):
+        shapes = {"nvls_fused": (64, 2), "nvls_fused_148": (148, 2), "nvls_fused_u4": (64, 4)}
+        for key in ("nccl", "nvls", "nvls_fused", "nvls_fused_148", "nvls_fused_u4"):
+            mode = "nvls_fused" if key in shapes else key
             self.mode = mode
+            if key in shapes:
+                self.fused_shape = shapes[key]
             try:
                 for _ in range(3):
                     self.allreduce(group)
@@ -184,8 +189,10 @@ class GradBucket:
             except Exception:
                 t = torch.tensor([float("inf")], device=self.flat.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            res[mode] = float(t)
-        self.mode = min(res, key=res.get)
+            res[key] = float(t)
+        best = min(res, key=res.get)
+        self.mode = "nvls_fused" if best in shapes else best
+        self.fused_shape = shapes.get(best, (64, 2))
         self.tuning = {k: round(v, 4) for k, v in res.items()}
         self.flat.copy_(keep)
 
@@ -232,7 +239,8 @@ class GradBucket:
                 with torch.cuda.device(self.flat.device):
                     rc = lib.gft_nvls_allreduce_fused(C.c_void_p(mc), C.c_longlong(self.flat.numel()), hdl.rank,
                                                       hdl.world_size, C.c_void_p(int(hdl.signal_pad_ptrs_dev)),
-                                                      int(hdl.signal_pad_size) // 4, 0, 4, stream)
+                                                      int(hdl.signal_pad_size) // 4, int(self.fused_shape[0]),
+                                                      int(self.fused_shape[1]), stream)
                 train_ops._check(rc, "gft_nvls_allreduce_fused")
             else:
                 # host-launched barrier, one kernel, barrier — all on the current stream

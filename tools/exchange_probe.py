@@ -59,7 +59,7 @@ if b._symm is not None:
     hdl = b._symm
     lib = train_ops._lib()
     mc = int(hdl.multicast_ptr) + int(b.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])
-    for blocks in (64, 148, 296, 592):
+    for blocks in (16, 32, 48, 64, 96, 148, 296):
         for unroll in (2, 4, 8):
             def f():
                 rc = lib.gft_nvls_allreduce_fused(C.c_void_p(mc), C.c_longlong(b.flat.numel()), hdl.rank, hdl.world_size,
