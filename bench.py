@@ -156,8 +156,10 @@ def bwd_args(params, v, f, empty, zero3, zero1):
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), through NVML, from
-    the timing thread itself: one sample right before every timed step's L2 flush, i.e. while the
-    GPU is under the load of the region but outside the step's own CUDA events.  (A background
+    the timing thread itself: a sample right after a timed step has been enqueued (its kernels and
+    its exchange still running), outside the step's own CUDA events, on every rank at the same
+    steps (a delay on one rank only is measured by the others inside their allreduce) and on a
+    handful of steps only (the two NVML calls take ~0.1-1 ms of host time).  (A background
     poller — round 1 ran `nvidia-smi -lms`, an NVML thread was tried first this round — takes the
     driver's lock under a kernel launch every now and then: one 2.7-8 ms straggler step per run in
     SCALE_r01 and again with the NVML thread.)  Falls back to one nvidia-smi query after the region
@@ -167,7 +169,7 @@ class ClockSampler:
 
     def __init__(self, index, every=1):
         self.index, self.every, self.n = index, max(1, every), 0
-        self.sm, self.mx, self.reasons, self.nv, self.h = [], [], set(), None, None
+        self.sm, self.mx, self.reasons, self.nv, self.h, self.cost = [], [], set(), None, None, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -182,8 +184,10 @@ class ClockSampler:
         if self.nv is None or (self.n % self.every):
             return
         try:
+            t0 = time.perf_counter()
             self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
             r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            self.cost.append((time.perf_counter() - t0) * 1e3)
             for name, bit in self.REASONS:
                 if r & bit:
                     self.reasons.add(name)
@@ -208,7 +212,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": "nvml"}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
                 "sm_mhz_min": float(min(self.sm)), "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "source": "nvml, sampled by the timing thread right after enqueuing every timed step (its kernels still running)"}
+                "host_ms_per_sample": round(sorted(self.cost)[len(self.cost) // 2], 3) if self.cost else None,
+                "source": "nvml, sampled by the timing thread right after enqueuing a timed step (its kernels still "
+                          "running), on every rank, every K//6-th step"}
 
 
 def stage_bytes(stage, P, V, R, N, T, nviews=1):
@@ -306,7 +312,11 @@ class Timer:
         self.steps_ms = ms
         self.host_ms = host                    # host time spent inside step_fn (enqueue + its own waits)
         total = torch.tensor([sum(ms)], dtype=torch.float64, device=self.dev)
+        self.rank_totals_ms = [float(total.item())]
         if self.world > 1:
+            every = [torch.zeros_like(total) for _ in range(self.world)]
+            dist.all_gather(every, total)
+            self.rank_totals_ms = [float(t.item()) for t in every]
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
         return float(total.item()), out
 
@@ -457,7 +467,7 @@ def run_gpu(args, impl):
         return stats
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local, every=max(1, K // 64)) if (rank == 0 and not args.no_clocks) else None
+    sampler = ClockSampler(local, every=max(1, K // 6)) if not args.no_clocks else None   # every rank, same steps
     n0 = [0]
 
     def mark():               # launch counting starts after the warm-up (smem attribute calls etc.)
@@ -466,6 +476,7 @@ def run_gpu(args, impl):
     launches = (arm.capi.launch_count() - n0[0]) if impl == "ours" else None
     step_ms = list(timer.steps_ms)
     slowest = slowest_step(timer)
+    per_rank = [round(t / K, 4) for t in timer.rank_totals_ms]
     wall_ms = timer.wall_ms
     clocks = sampler.result() if sampler is not None else None
 
@@ -537,6 +548,7 @@ def run_gpu(args, impl):
         "fwd_bwd_ms_per_iter": round(total_ms / K, 4),
         "step_ms_min_med_max": min_med_max(step_ms),
         "slowest_step": slowest,
+        "ms_per_step_by_rank": per_rank,
         "wall_ms_total_incl_flush": round(wall_ms, 2),
         "render_mpix_s": round(mpix * K / (render_ms / 1e3), 3),
         "render_ms_per_step": round(render_ms / K, 4),
