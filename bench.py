@@ -176,6 +176,9 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            for _ in range(3):      # the FIRST call of each query takes 2-5 ms (seen as a straggler at the
+                pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)          # first sampled step
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)                # on every rank)
         except Exception:
             self.nv = None
 
@@ -313,10 +316,13 @@ class Timer:
         self.host_ms = host                    # host time spent inside step_fn (enqueue + its own waits)
         total = torch.tensor([sum(ms)], dtype=torch.float64, device=self.dev)
         self.rank_totals_ms = [float(total.item())]
+        self.rank_steps_ms = [ms]
         if self.world > 1:
-            every = [torch.zeros_like(total) for _ in range(self.world)]
-            dist.all_gather(every, total)
-            self.rank_totals_ms = [float(t.item()) for t in every]
+            mine = torch.tensor(ms, dtype=torch.float64, device=self.dev)
+            every = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine)
+            self.rank_steps_ms = [[float(x) for x in t.tolist()] for t in every]
+            self.rank_totals_ms = [sum(r) for r in self.rank_steps_ms]
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
         return float(total.item()), out
 
@@ -349,6 +355,9 @@ class Ours:
         # library's NVLS kernels is fastest on this very buffer (timed once, at construction)
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         b = self.parallel.GradBucket(params, scal, symmetric="auto" if multi else False)
+        forced = os.environ.get("GFT_BENCH_EXCHANGE")          # A/B runs: nccl | nvls | nvls_fused
+        if multi and forced in ("nccl", "nvls", "nvls_fused") and getattr(b, "_symm", None) is not None:
+            b.mode = forced
         return b, b.grad_out()
 
     def forward(self, key, params, views, specs=None):
@@ -477,6 +486,10 @@ def run_gpu(args, impl):
     step_ms = list(timer.steps_ms)
     slowest = slowest_step(timer)
     per_rank = [round(t / K, 4) for t in timer.rank_totals_ms]
+    per_rank_med = [min_med_max(r)[1] for r in timer.rank_steps_ms]
+    if rank == 0 and world > 1 and os.environ.get("GFT_BENCH_TRACE_RANKS"):
+        for i in range(K):
+            print("step", i, " ".join(f"{r[i]:.3f}" for r in timer.rank_steps_ms), file=sys.stderr)
     wall_ms = timer.wall_ms
     clocks = sampler.result() if sampler is not None else None
 
@@ -499,6 +512,8 @@ def run_gpu(args, impl):
                 share[name] = share.get(name, 0.0) + ms / stage_steps
             print(json.dumps({"resident_only": True, "impl": impl, "ms_per_step": round(total_ms / K, 4),
                               "step_ms_min_med_max": min_med_max(step_ms),
+                              "ms_per_step_by_rank": per_rank, "median_step_ms_by_rank": per_rank_med,
+                              "exchange": getattr(bucket, "mode", None) if world > 1 else None,
                               "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                               "gpu_launches": launches}), flush=True)
         if world > 1:
@@ -549,6 +564,7 @@ def run_gpu(args, impl):
         "step_ms_min_med_max": min_med_max(step_ms),
         "slowest_step": slowest,
         "ms_per_step_by_rank": per_rank,
+        "median_step_ms_by_rank": per_rank_med,
         "wall_ms_total_incl_flush": round(wall_ms, 2),
         "render_mpix_s": round(mpix * K / (render_ms / 1e3), 3),
         "render_ms_per_step": round(render_ms / K, 4),
@@ -628,9 +644,18 @@ def run_gpu(args, impl):
 def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     """Host buffers in, host buffers out.  Ours: the public batched autograd surface, the copies of
     neighbouring steps overlapping the kernels (upload stream / compute stream / download stream,
-    double-buffered device and host staging).  Reference: its stock path — sequential, default
-    stream (its kernels take no stream argument)."""
+    triple-buffered device and host staging).  Reference: its stock path — sequential, default
+    stream (its kernels take no stream argument).
+
+    At N > 1 ours runs the data-parallel step the way a host-resident (offloaded) optimizer would
+    drive it: the replicated parameters reach the GPUs ONCE — rank r uploads slice r of the flat
+    parameter buffer and an NVLink all-gather completes it on every GPU — and the summed gradients
+    leave ONCE — a reduce-scatter over NVLink, rank r downloads slice r.  Every rank still uploads
+    its own views' data and downloads its own images.  (The eight ranks of a box share its PCIe
+    switches: eight full copies of the same 109 MB each way took 16 ms per step, copies alone.)"""
     names = PARAM_NAMES
+    rank = dist.get_rank() if world > 1 else 0
+    sharded = impl == "ours" and world > 1
     host_params = {k: params[k].cpu().pin_memory() for k in names}
     host_views = []
     for v in views:
@@ -642,14 +667,39 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
         sum(t.numel() * 4 for t in (hv["viewmatrix"], hv["projmatrix"], hv["campos"])) +
         sum(g.numel() * 4 for g in hv["grads"].values()) for hv in host_views)
     NB = 3 if impl == "ours" else 1      # staging sets in flight: the host enqueues up to two steps ahead of the link
-    host_out_grads = [{k: torch.empty_like(host_params[k]).pin_memory() for k in names} for _ in range(NB)]
     host_imgs = [[torch.empty((11, v["H"], v["W"]), dtype=torch.float32).pin_memory() for v in views] for _ in range(NB)]
-    d2h_bytes = sum(t.numel() * 4 for t in host_out_grads[0].values()) + sum(t.numel() * 4 for t in host_imgs[0])
     npix_all = sum(v["W"] * v["H"] for v in views) * world
+    n_par = sum(host_params[k].numel() for k in names)
+    if sharded:
+        # flat parameter / gradient layout in PARAM_NAMES order, padded so that it splits evenly
+        n_pad = (n_par + 4 * world - 1) // (4 * world) * (4 * world)
+        shard = n_pad // world
+        host_flat = torch.zeros(n_pad, dtype=torch.float32).pin_memory()
+        o = 0
+        for k in names:
+            host_flat[o:o + host_params[k].numel()].copy_(host_params[k].reshape(-1))
+            o += host_params[k].numel()
+        host_in_shard = host_flat[rank * shard:(rank + 1) * shard]
+        host_out_shard = [torch.empty(shard, dtype=torch.float32).pin_memory() for _ in range(NB)]
+        g_up, g_down = dist.new_group(), dist.new_group()      # own communicators: no queueing behind each other
+        h2d_bytes += (shard - n_par) * 4
+        d2h_bytes = shard * 4 + sum(t.numel() * 4 for t in host_imgs[0])
+    else:
+        host_out_grads = [{k: torch.empty_like(host_params[k]).pin_memory() for k in names} for _ in range(NB)]
+        d2h_bytes = sum(t.numel() * 4 for t in host_out_grads[0].values()) + sum(t.numel() * 4 for t in host_imgs[0])
 
     # persistent device-side staging (what an application keeps): the H2D copies land in these
     def staging():
-        s = {"params": {k: torch.empty_like(params[k]) for k in names}, "bg": torch.empty_like(views[0]["bg"]), "views": []}
+        if sharded:
+            flat = torch.empty(n_pad, dtype=torch.float32, device=dev)
+            prm, o = {}, 0
+            for k in names:
+                prm[k] = flat[o:o + params[k].numel()].view(params[k].shape)
+                o += params[k].numel()
+            s = {"flat": flat, "params": prm}
+        else:
+            s = {"params": {k: torch.empty_like(params[k]) for k in names}}
+        s.update({"bg": torch.empty_like(views[0]["bg"]), "views": []})
         for v in views:
             dv = {k: torch.empty_like(v[k]) for k in ("viewmatrix", "projmatrix", "campos")}
             dv["grads"] = {k: torch.empty_like(g) for k, g in v["grads"].items()}
@@ -659,8 +709,13 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
 
     def upload(s):
         with torch.no_grad():
-            for k in names:
-                s["params"][k].copy_(host_params[k], non_blocking=True)
+            if sharded:
+                mine = s["flat"][rank * shard:(rank + 1) * shard]
+                mine.copy_(host_in_shard, non_blocking=True)
+                dist.all_gather_into_tensor(s["flat"], mine, group=g_up)      # in place, over NVLink
+            else:
+                for k in names:
+                    s["params"][k].copy_(host_params[k], non_blocking=True)
             s["bg"].copy_(host_bg, non_blocking=True)
             for hv, dv in zip(host_views, s["views"]):
                 for k in ("viewmatrix", "projmatrix", "campos"):
@@ -757,6 +812,10 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
         if pipelined:
             mark(comp, "Cf", i)
         torch.autograd.backward(tens, gr)
+        if sharded:
+            with torch.no_grad():
+                pad = [torch.zeros(n_pad - n_par, dtype=torch.float32, device=dev)] if n_pad > n_par else []
+                s["gflat"] = torch.cat([s["params"][k].grad.reshape(-1) for k in names] + pad)
         ev_comp[b].record(comp)
         tgt = down if pipelined else comp
         if pipelined:
@@ -771,10 +830,16 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
                 himg[10:11].copy_(o[2], non_blocking=True)
                 for t in (o[0], o[1], o[2]):
                     t.record_stream(tgt)
-            for k in names:
-                gk = s["params"][k].grad
-                host_out_grads[b][k].copy_(gk, non_blocking=True)
-                gk.record_stream(tgt)
+            if sharded:
+                gflat, gsh = s["gflat"], torch.empty(shard, dtype=torch.float32, device=dev)
+                dist.reduce_scatter_tensor(gsh, gflat, group=g_down)          # summed over the ranks, slice r stays here
+                host_out_shard[b].copy_(gsh, non_blocking=True)
+                gflat.record_stream(tgt)
+            else:
+                for k in names:
+                    gk = s["params"][k].grad
+                    host_out_grads[b][k].copy_(gk, non_blocking=True)
+                    gk.record_stream(tgt)
             ev_down[b].record(tgt)
             if pipelined:
                 mark(tgt, "D1", i)
@@ -798,8 +863,11 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
                 with torch.cuda.stream(down), torch.no_grad():
                     for d, himg in zip(dimgs, host_imgs[0]):
                         himg.copy_(d, non_blocking=True)
-                    for k in names:
-                        host_out_grads[0][k].copy_(stage[0]["params"][k].detach(), non_blocking=True)
+                    if sharded:
+                        host_out_shard[0].copy_(stage[0]["flat"][rank * shard:(rank + 1) * shard], non_blocking=True)
+                    else:
+                        for k in names:
+                            host_out_grads[0][k].copy_(stage[0]["params"][k].detach(), non_blocking=True)
         comp.wait_stream(up)
         comp.wait_stream(down)
         e1.record(comp)
@@ -857,12 +925,17 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
             "serial_ms_per_step": round(serial_ms, 4),
             "host_link_copies_only": dict(link, note="the same H2D / D2H copies of one step with no kernels between them: "
                                                      "each direction alone, then both concurrently (the floor of the pipelined step)"),
-            "l2": "every step's inputs arrive from the host (150 MB) and its results leave for it (136 MB): "
+            "l2": "every step's inputs arrive from the host or over NVLink (150 MB) and its results leave (136 MB): "
                   "the working set of a step exceeds the 126 MB L2; no extra flush in the pipelined region",
             "api": "gftorf_b200.rasterize_views(...) + torch.autograd.backward; H2D of step i+1 and D2H of step i-1 "
                    "overlap the kernels of step i (3 streams, triple-buffered pinned and device staging; the upload of step i+1 is "
                    "enqueued before the forward call of step i, which blocks the host while it learns the instance count); "
-                   "serial_ms_per_step = the same calls with upload -> compute -> download one after the other"}
+                   "serial_ms_per_step = the same calls with upload -> compute -> download one after the other"
+                   + ("; N > 1: data-parallel step with host I/O sharded over the ranks — rank r uploads slice r of the "
+                      "replicated parameters (NVLink all-gather completes them on every GPU) and downloads slice r of the "
+                      "summed gradients (NVLink reduce-scatter), plus its own views' inputs and images; the byte counts are "
+                      "per rank" if sharded else ""),
+            "sharded_host_io": bool(sharded)}
 
 
 # --------------------------------------------------------------------------------------------
