@@ -885,6 +885,20 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
     Ks = max(5, K // 4)
     serial_ms, _ = timer.run(step_serial, Ks, 3)
     serial_ms /= Ks
+    shard_check = None
+    if sharded:
+        # the sharded transfers carry what the full copies carried: every GPU holds the whole
+        # parameter set after the all-gather, and slice r of the reduce-scatter is the sum over the
+        # ranks (all ranks render the same scene here: N x the local gradient)
+        torch.cuda.synchronize(dev)
+        s0 = stage[0]
+        ok_p = bool(torch.equal(s0["flat"][:n_par], torch.cat([params[k].reshape(-1) for k in names])))
+        want = world * s0["gflat"][rank * shard:(rank + 1) * shard].double().cpu()
+        got = host_out_shard[0].double()
+        err = float((got - want).norm() / max(float(want.norm()), 1e-30))
+        shard_check = {"params_identical_after_all_gather": ok_p, "grad_slice_rel_err_vs_N_x_local": round(err, 8)}
+        if not ok_p or err > 1e-3:
+            raise RuntimeError(f"sharded host I/O check failed: {shard_check}")
 
     # pipelined: whole region timed with one event pair on the compute stream, every copy inside
     for e in ev_comp + ev_down:
@@ -935,7 +949,7 @@ def e2e_bench(arm, impl, params, views, dev, timer, K, W, world):
                       "replicated parameters (NVLink all-gather completes them on every GPU) and downloads slice r of the "
                       "summed gradients (NVLink reduce-scatter), plus its own views' inputs and images; the byte counts are "
                       "per rank" if sharded else ""),
-            "sharded_host_io": bool(sharded)}
+            "sharded_host_io": bool(sharded), "sharded_host_io_check": shard_check}
 
 
 # --------------------------------------------------------------------------------------------
