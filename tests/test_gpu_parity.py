@@ -1102,7 +1102,13 @@ def test_view_batch_equals_the_reference_calls_view_by_view(shape):
         # |dL/drot| ~ 1e-2 |dL/dscale|), so its noise floor sits at float rounding of THOSE terms;
         # the scalar offsets are single sums over all Gaussians in arbitrary atomic order
         tol = {"rotations": 3e-4, "phase_offset": 1e-3, "dc_offset": 1e-3}.get(name, harness.GRAD_REL_L2)
-        assert err <= tol * max(float(expect.norm()), 1e-3 * scale), (name, err)
+        bound = tol * max(float(expect.norm()), 1e-3 * scale)
+        if name == "rotations":
+            # ... so the floor is stated against those terms: 1e-5 of |dL/dscale| — float32 rounding
+            # (6e-8) through the ~100 operations of the covariance chain and atomic sums in
+            # arbitrary order; observed 2e-6 ... 5e-6 of |dL/dscale| from run to run
+            bound = max(bound, 1e-5 * scale)
+        assert err <= bound, (name, err, bound)
     assert harness.rel_l2(out["shs_p"][0], rbs[0][7][0] + rbs[1][7][0]) <= harness.GRAD_REL_L2
     for i in range(2):
         assert harness.rel_l2(out["means2D"][i], rbs[i][0]) <= harness.GRAD_REL_L2
