@@ -1039,7 +1039,7 @@ def c5_block(arm, impl, dev, timer, rank, world, sizes):
     return out
 
 
-def c3_iter_block(impl, dev, flush, iters=12, densify_every=6):
+def c3_iter_block(impl, dev, flush, iters=18, densify_every=6):
     """BASELINE configs[2]: a FULL training iteration incl. densification as one timed unit
     (train.py:165-279,441-474): assemble the rasterizer inputs from the raw parameters -> colour +
     ToF view -> losses (l1 + SSIM on colour, weighted L2 on a quad) -> backward -> Adam; every
@@ -1154,6 +1154,7 @@ def c3_iter_block(impl, dev, flush, iters=12, densify_every=6):
             "ms_per_iter_mean_incl_densify": round(float(np.mean(times[warm:])), 3),
             "ms_per_plain_iter": round(float(np.median(plain)), 3),
             "ms_per_densify_iter": round(float(np.median(dens)), 3) if dens else None,
+            "ms_per_densify_iter_each": [round(float(t), 3) for t in dens],   # the first pays one-time costs (lazy module loads, generator set-up)
             "gaussians_start_end": [sizes[0], sizes[-1]], "iters": iters}
 
 
