@@ -155,3 +155,32 @@ def test_c_abi_rejects_bad_view_batches_without_a_gpu():
     assert lib.gft_set_option(b"no_such_option", 1) < 0
     old = lib.gft_set_option(b"sort_cap", 2048)
     assert lib.gft_set_option(b"sort_cap", old) == 2048
+
+
+def test_sh_row_staging_piece_map_covers_every_piece_once_without_bank_conflicts():
+    """Mirror of `stage_piece<ROW>` (gftorf_b200/csrc/common.cuh): in iteration `it` lane l moves the
+    16-byte piece at (row r, first column c).  Over all iterations every piece of the 32 x ROW chunk is
+    moved exactly once; within one warp instruction the global addresses fill whole 32-byte sectors
+    and each of the four scalar shared-memory accesses (row stride ROW + 1) hits 32 distinct banks."""
+    def piece(row, it, lane):
+        if row == 32 or it < 8:
+            return 4 * it + (lane & 3), 4 * (lane >> 2)
+        return (lane & 16) + 4 * (it - 8) + (lane & 3), 32 + 4 * ((lane >> 2) & 3)
+
+    for row in (48, 32):
+        seen = set()
+        for it in range(row // 4):
+            pieces = [piece(row, it, lane) for lane in range(32)]
+            for r, c in pieces:
+                assert 0 <= r < 32 and 0 <= c <= row - 4 and c % 4 == 0
+                assert (r, c) not in seen
+                seen.add((r, c))
+            for j in range(4):                                     # the four scalar accesses of a piece
+                banks = {(r * (row + 1) + c + j) % 32 for r, c in pieces}
+                assert len(banks) == 32, (row, it, j)
+            sectors = {}
+            for r, c in pieces:                                    # 32-byte sectors of global memory
+                sectors.setdefault((r * row + c) * 4 // 32, 0)
+                sectors[(r * row + c) * 4 // 32] += 16
+            assert all(v == 32 for v in sectors.values()), (row, it)
+        assert len(seen) == 32 * row // 4
