@@ -38,17 +38,61 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;                       // one 16-byte load / store per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
+// ranges[t] = (starts[t*S], starts[(t+1)*S]), with (0,0) for empty tiles — the reference's memset
+// + identifyTileRanges never touch those (rasterizer_impl.cu:118-140,341) — and the launch order of
+// the blend kernels.  Run by ONE block (the scan block that finishes last): T <= 16 views x 8160
+// tiles.  `starts` was written by other blocks: read through the L2.
+__device__ __forceinline__ void tile_ranges_and_order(const uint32_t* starts, int T, int S,
+                                                      uint2* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                      uint32_t* s_bk) {
+  const uint32_t tid = threadIdx.x;
+  // Launch order of the blend kernels: longest tile lists first.  A blend block's time is
+  // proportional to its tile's list length, the lists differ by 2-4x, and a grid is only ~5 blocks
+  // per resident slot deep, so in index order a long tile that starts late leaves most SMs idle at
+  // the end of the kernel.  128 buckets on a quarter-octave scale; the order inside a bucket is
+  // whatever the atomics give (it only decides which SM runs a tile, never a result).
+  auto bucket = [](uint32_t len) -> uint32_t {
+    if (len < 4u) return len;
+    const uint32_t e = 31u - __clz(len);
+    return min(127u, e * 4u + ((len >> (e - 2u)) & 3u));
+  };
+  if (tid < 128) s_bk[tid] = 0u;
+  __syncthreads();
+  for (int t = tid; t < T; t += SCAN_THREADS) {
+    const uint32_t x = __ldcg(starts + (size_t)t * S), y = __ldcg(starts + (size_t)(t + 1) * S);
+    ranges[t] = y > x ? make_uint2(x, y) : make_uint2(0u, 0u);
+    atomicAdd(&s_bk[bucket(y - x)], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int b = 127; b >= 0; --b) {
+      const uint32_t c = s_bk[b];
+      s_bk[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += SCAN_THREADS) {
+    const uint32_t x = __ldcg(starts + (size_t)t * S), y = __ldcg(starts + (size_t)(t + 1) * S);
+    order[atomicAdd(&s_bk[bucket(y - x)], 1u)] = (uint32_t)t;
+  }
+}
+
 // Exclusive scan of the n = T_total * S sub-bin counters into starts[0..n] (clamped to `capacity`),
 // R = starts[n] unclamped into hdr[1].  Single pass over ceil(n / 4096) blocks, chained with the
 // decoupled look-back; a block's place in the chain is its ticket (hdr[0]), not blockIdx, so the
 // look-back never waits for a block that has not started.  state[b] = flag << 32 | value with
 // flag 1 = block aggregate, 2 = inclusive prefix (one 64-bit word: relaxed accesses suffice).
+// The block that FINISHES last (counter hdr[2]) turns the starts into `ranges` and the blend
+// launch order — the work of a second kernel without its launch.
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_starts_kernel(const uint32_t* __restrict__ counts, int n, uint32_t capacity,
-                   uint32_t* __restrict__ starts, uint32_t* __restrict__ hdr,
-                   unsigned long long* __restrict__ state, uint32_t* __restrict__ host_R) {
+                   uint32_t* starts, uint32_t* __restrict__ hdr,
+                   unsigned long long* __restrict__ state, uint32_t* __restrict__ host_R,
+                   int T, int S, uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-  __shared__ uint32_t s_bid, s_prefix;
+  __shared__ uint32_t s_bid, s_prefix, s_last, s_bk[128];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_bid = atomicAdd(hdr, 1u);
   __syncthreads();
@@ -125,47 +169,13 @@ scan_starts_kernel(const uint32_t* __restrict__ counts, int n, uint32_t capacity
     // plus an event, with no copy-engine transfer behind whatever bulk copies other streams queued
     if (host_R) { *reinterpret_cast<volatile uint32_t*>(host_R) = R; __threadfence_system(); }
   }
-}
-
-// ranges[t] = (starts[t*S], starts[(t+1)*S]), with (0,0) for empty tiles — the reference's memset
-// + identifyTileRanges never touch those (rasterizer_impl.cu:118-140,341) — and the launch order of
-// the blend kernels.  One block: T <= 16 views x 8160 tiles.
-__global__ void __launch_bounds__(SCAN_THREADS)
-tile_ranges_kernel(const uint32_t* __restrict__ starts, int T, int S, uint2* __restrict__ ranges,
-                   uint32_t* __restrict__ order) {
-  __shared__ uint32_t s_bk[128];
-  const uint32_t tid = threadIdx.x;
-  // Launch order of the blend kernels: longest tile lists first.  A blend block's time is
-  // proportional to its tile's list length, the lists differ by 2-4x, and a grid is only ~5 blocks
-  // per resident slot deep, so in index order a long tile that starts late leaves most SMs idle at
-  // the end of the kernel.  128 buckets on a quarter-octave scale; the order inside a bucket is
-  // whatever the atomics give (it only decides which SM runs a tile, never a result).
-  auto bucket = [](uint32_t len) -> uint32_t {
-    if (len < 4u) return len;
-    const uint32_t e = 31u - __clz(len);
-    return min(127u, e * 4u + ((len >> (e - 2u)) & 3u));
-  };
-  if (tid < 128) s_bk[tid] = 0u;
+  __threadfence();                         // this block's starts are visible before it counts as done
   __syncthreads();
-  for (int t = tid; t < T; t += SCAN_THREADS) {
-    const uint32_t x = __ldg(starts + (size_t)t * S), y = __ldg(starts + (size_t)(t + 1) * S);
-    ranges[t] = y > x ? make_uint2(x, y) : make_uint2(0u, 0u);
-    atomicAdd(&s_bk[bucket(y - x)], 1u);
-  }
+  if (tid == 0) s_last = atomicAdd(hdr + 2, 1u) == gridDim.x - 1u ? 1u : 0u;
   __syncthreads();
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (int b = 127; b >= 0; --b) {
-      const uint32_t c = s_bk[b];
-      s_bk[b] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  for (int t = tid; t < T; t += SCAN_THREADS) {
-    const uint32_t x = __ldg(starts + (size_t)t * S), y = __ldg(starts + (size_t)(t + 1) * S);
-    order[atomicAdd(&s_bk[bucket(y - x)], 1u)] = (uint32_t)t;
-  }
+  if (!s_last) return;
+  __threadfence();
+  tile_ranges_and_order(starts, T, S, ranges, order, s_bk);
 }
 
 // grid: (ceil(P/256), nviews).  Same tile enumeration as the counting in the preprocess kernel.
@@ -454,9 +464,9 @@ void launch_tile_scan(const uint32_t* tile_counts, int T_total, int sub_bins, ui
                       unsigned long long* scan_state, uint32_t* host_R, cudaStream_t stream) {
   const int n = T_total * sub_bins;
   scan_starts_kernel<<<(n + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, stream>>>(tile_counts, n, capacity, starts,
-                                                                                  hdr, scan_state, host_R);
-  tile_ranges_kernel<<<1, SCAN_THREADS, 0, stream>>>(starts, T_total, sub_bins, ranges, order);
-  note_launches(2);
+                                                                                  hdr, scan_state, host_R, T_total, sub_bins, ranges,
+                                                                                  order);
+  note_launches(1);
 }
 
 void launch_scatter_entries(const PreprocessParams& pp, const uint32_t* starts, uint32_t* cursors,
