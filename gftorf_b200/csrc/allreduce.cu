@@ -102,10 +102,107 @@ nvls_allreduce_fused_kernel(float4* __restrict__ mc, long long begin, long long 
   peer_barrier(pads, word0, rank, world);
 }
 
+// ---- the same exchange with plain peer-to-peer accesses (no multicast) ---------------------------
+// Rank r sums slice r: its own values plus one 16-byte load from every peer's symmetric buffer,
+// and stores the sum into every buffer.  Per GPU and direction the links carry 2 (N-1)/N S bytes
+// against (1 + 1/N) S through the switch-side reduction: fewer at N = 2 (S against 1.5 S), more
+// from N = 4 on — the autotuner decides.  Every element is summed by exactly one rank (own value
+// first, then the peers in rank order) and broadcast, so all ranks end with identical bits.
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer(float4* p, float4 v) {
+  asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+constexpr int P2P_MAX_WORLD = 8;
+struct PeerBufs { float4* buf[P2P_MAX_WORLD]; };
+
+template <int AR_UNROLL>
+__global__ void __launch_bounds__(512)
+p2p_allreduce_fused_kernel(const __grid_constant__ PeerBufs bufs, long long begin, long long end,
+                           uint32_t* const* __restrict__ pads, uint32_t word0, int rank, int world) {
+  peer_barrier(pads, word0, rank, world);
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < end; i += AR_UNROLL * stride) {
+    float4 v[AR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) {
+      const long long j = i + u * stride;
+      if (j < end) v[u] = ld_peer(bufs.buf[rank] + j);
+    }
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) continue;
+#pragma unroll
+      for (int u = 0; u < AR_UNROLL; ++u) {
+        const long long j = i + u * stride;
+        if (j < end) {
+          const float4 w = ld_peer(bufs.buf[p] + j);
+          v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
+        }
+      }
+    }
+    for (int p = 0; p < world; ++p) {
+#pragma unroll
+      for (int u = 0; u < AR_UNROLL; ++u) {
+        const long long j = i + u * stride;
+        if (j < end) st_peer(bufs.buf[p] + j, v[u]);
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  peer_barrier(pads, word0, rank, world);
+}
+
 }  // namespace
 }  // namespace gft
 
 extern "C" {
+
+int gft_p2p_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset, long long n_floats, int rank,
+                            int world, void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
+                            gft_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!buffer_ptrs_host || !signal_pads_dev) return gft::set_error(-1, "gft_p2p_allreduce_fused: null pointer");
+  if (world <= 0 || world > gft::P2P_MAX_WORLD || rank < 0 || rank >= world)
+    return gft::set_error(-1, "gft_p2p_allreduce_fused: bad rank / world (at most 8 ranks)");
+  if (n_floats < 0 || (n_floats & 3) || (byte_offset & 15))
+    return gft::set_error(-1, "gft_p2p_allreduce_fused: length must be a multiple of 4 floats, offset of 16 bytes");
+  gft::PeerBufs pb;
+  for (int p = 0; p < gft::P2P_MAX_WORLD; ++p) {
+    char* base = p < world ? static_cast<char*>(buffer_ptrs_host[p]) : nullptr;
+    if (p < world && (!base || (reinterpret_cast<uintptr_t>(base) & 15)))
+      return gft::set_error(-1, "gft_p2p_allreduce_fused: peer buffer pointers must be non-null and 16-byte aligned");
+    pb.buf[p] = base ? reinterpret_cast<float4*>(base + byte_offset) : nullptr;
+  }
+  const long long total = n_floats >> 2;
+  const long long per = (total + world - 1) / world;
+  const long long begin = per * rank, end = begin + per < total ? begin + per : total;
+  const int word0 = pad_words / 2;
+  int max_blocks = (pad_words - word0) / world;
+  if (max_blocks < 1) return gft::set_error(-1, "gft_p2p_allreduce_fused: signal pad too small");
+  // EVERY rank must launch the same number of blocks (block b pairs with block b of its peers)
+  long long want = blocks > 0 ? blocks : (long long)gft::sm_count();
+  const long long need = (per + 512 - 1) / 512;
+  if (want > need) want = need > 0 ? need : 1;
+  if (want > max_blocks) want = max_blocks;
+  uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads_dev);
+  const long long e = end > begin ? end : begin;
+  if (unroll == 4) gft::p2p_allreduce_fused_kernel<4><<<(int)want, 512, 0, stream>>>(pb, begin, e, pads, (uint32_t)word0, rank, world);
+  else if (unroll == 1) gft::p2p_allreduce_fused_kernel<1><<<(int)want, 512, 0, stream>>>(pb, begin, e, pads, (uint32_t)word0, rank, world);
+  else gft::p2p_allreduce_fused_kernel<2><<<(int)want, 512, 0, stream>>>(pb, begin, e, pads, (uint32_t)word0, rank, world);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(err));
+  gft::note_launches(1);
+  return 0;
+}
 
 int gft_nvls_allreduce_fused(float* multicast_ptr, long long n_floats, int rank, int world,
                              void* const* signal_pads_dev, int pad_words, int blocks, int unroll,

@@ -127,6 +127,7 @@ class GradBucket:
         self.sizes = sizes
         self._symm = None
         self.fused_shape = (64, 2)   # (blocks, unroll) of the one-kernel NVLS allreduce: best of the sweep at 4 and 8 GPUs
+        self.p2p_shape = (148, 2)    # (blocks, unroll) of the one-kernel peer-to-peer allreduce
         self.mode = "nccl"
         self.tuning = None
         if symmetric:
@@ -169,11 +170,17 @@ class GradBucket:
         keep = self.flat.clone()
         res = {}
         shapes = {"nvls_fused": (64, 2), "nvls_fused_148": (148, 2), "nvls_fused_u4": (64, 4)}
-        for key in ("nccl", "nvls", "nvls_fused", "nvls_fused_148", "nvls_fused_u4"):
-            mode = "nvls_fused" if key in shapes else key
+        p2p_shapes = {"p2p_fused": (148, 2), "p2p_fused_64": (64, 2), "p2p_fused_296u4": (296, 4)}
+        keys = ["nccl", "nvls", "nvls_fused", "nvls_fused_148", "nvls_fused_u4"]
+        if self._symm.world_size <= 4:        # the peer-to-peer exchange moves more bytes than the switch from N = 4 on
+            keys += list(p2p_shapes)
+        for key in keys:
+            mode = "nvls_fused" if key in shapes else ("p2p_fused" if key in p2p_shapes else key)
             self.mode = mode
             if key in shapes:
                 self.fused_shape = shapes[key]
+            if key in p2p_shapes:
+                self.p2p_shape = p2p_shapes[key]
             try:
                 for _ in range(3):
                     self.allreduce(group)
@@ -191,8 +198,9 @@ class GradBucket:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             res[key] = float(t)
         best = min(res, key=res.get)
-        self.mode = "nvls_fused" if best in shapes else best
+        self.mode = "nvls_fused" if best in shapes else ("p2p_fused" if best in p2p_shapes else best)
         self.fused_shape = shapes.get(best, (64, 2))
+        self.p2p_shape = p2p_shapes.get(best, (148, 2))
         self.tuning = {k: round(v, 4) for k, v in res.items()}
         self.flat.copy_(keep)
 
@@ -233,7 +241,18 @@ class GradBucket:
             lib = train_ops._lib()
             mc = int(hdl.multicast_ptr) + int(self.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])
             stream = C.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
-            if self.mode == "nvls_fused":
+            if self.mode == "p2p_fused":
+                # ONE kernel, plain peer-to-peer accesses: this rank sums its slice from every rank's
+                # buffer and stores the sum into every buffer (fewer bytes than the multicast path at N = 2)
+                ptrs = (C.c_void_p * hdl.world_size)(*[int(p) for p in hdl.buffer_ptrs])
+                with torch.cuda.device(self.flat.device):
+                    rc = lib.gft_p2p_allreduce_fused(ptrs, C.c_longlong(int(self.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])),
+                                                     C.c_longlong(self.flat.numel()), hdl.rank, hdl.world_size,
+                                                     C.c_void_p(int(hdl.signal_pad_ptrs_dev)),
+                                                     int(hdl.signal_pad_size) // 4, int(self.p2p_shape[0]),
+                                                     int(self.p2p_shape[1]), stream)
+                train_ops._check(rc, "gft_p2p_allreduce_fused")
+            elif self.mode == "nvls_fused":
                 # ONE kernel: barrier over the signal pads, multimem.ld_reduce + multimem.st on this
                 # rank's slice, barrier
                 with torch.cuda.device(self.flat.device):

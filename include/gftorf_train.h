@@ -233,6 +233,16 @@ int gft_nvls_allreduce_fused(float* multicast_ptr, long long n_floats, int rank,
                              void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
                              gft_stream_t stream);
 
+/* The same exchange with plain peer-to-peer accesses instead of the multicast object: rank r sums
+ * slice r from every rank's symmetric buffer and stores the sum into every buffer (barriers as
+ * above).  Moves 2(N-1)/N bucket sizes per GPU and direction against (1 + 1/N) through the switch:
+ * the better choice at N = 2.  `buffer_ptrs_host`: HOST array of `world` device pointers to the
+ * ranks' symmetric buffers (torch: SymmetricMemory.buffer_ptrs), `byte_offset` the bucket's offset
+ * inside them (a multiple of 16).  world <= 8; `unroll` 1, 2 or 4.  Collective. */
+int gft_p2p_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset, long long n_floats, int rank,
+                            int world, void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
+                            gft_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,7 +133,8 @@ def test_train_header_symbols_are_exported():
     names = sorted(set(re.findall(r"\b(gft_[a-z0-9_]+)\s*\(", src)))
     assert names == ["gft_adam_step", "gft_assemble_backward", "gft_assemble_forward", "gft_densify_apply",
                      "gft_densify_plan", "gft_densify_workspace_bytes", "gft_fused_loss",
-                     "gft_fused_loss_scratch_bytes", "gft_nvls_allreduce_fused", "gft_nvls_allreduce_sum"]
+                     "gft_fused_loss_scratch_bytes", "gft_nvls_allreduce_fused", "gft_nvls_allreduce_sum",
+                     "gft_p2p_allreduce_fused"]
     from gftorf_b200 import _capi
     lib = C.CDLL(_capi.LIB_PATH)
     for n in names:

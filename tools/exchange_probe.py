@@ -46,7 +46,7 @@ res = {"P": P, "world": world, "MB": b.nbytes() / 1e6}
 x = torch.randn(b.flat.numel(), device=dev, generator=torch.Generator(dev).manual_seed(rank + 1))
 ref = x.clone(); dist.all_reduce(ref)
 if b._symm is not None:
-    for mode in ("nvls", "nvls_fused"):
+    for mode in ("nvls", "nvls_fused") + (("p2p_fused",) if world <= 8 else ()):
         b.mode = mode
         b.flat.copy_(x)
         b.allreduce()
@@ -59,6 +59,22 @@ if b._symm is not None:
     hdl = b._symm
     lib = train_ops._lib()
     mc = int(hdl.multicast_ptr) + int(b.flat.data_ptr() - hdl.buffer_ptrs[hdl.rank])
+    if world <= 8:
+        b.mode = "p2p_fused"
+        for shape in ((32, 2), (64, 2), (148, 1), (148, 2), (148, 4), (296, 2), (296, 4), (592, 2)):
+            b.p2p_shape = shape
+            b.flat.copy_(x)
+            b.allreduce()
+            torch.cuda.synchronize()
+            assert float((b.flat - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), shape
+            # all ranks must hold identical bits
+            chk = b.flat.double().sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert float(lo) == float(hi), shape
+            t = timeit(lambda: b.allreduce(), iters=20)
+            res[f"p2p_b{shape[0]}_u{shape[1]}"] = t
+            say(f"p2p blocks={shape[0]} unroll={shape[1]}: {t:.4f} ms")
     for blocks in (16, 32, 48, 64, 96, 148, 296):
         for unroll in (2, 4, 8):
             def f():
