@@ -161,10 +161,99 @@ p2p_allreduce_fused_kernel(const __grid_constant__ PeerBufs bufs, long long begi
   peer_barrier(pads, word0, rank, world);
 }
 
+// ---- the peer-to-peer exchange with posted stores only ------------------------------------------
+// Remote LOADS are the slow half of the kernel above (530 GB/s per direction at N = 2 where the
+// links carry 900).  Here nothing is loaded over the links: (1) every rank pushes the slices it
+// does not own into region [rank] of the owner's symmetric scratch buffer, (2) barrier, (3) the
+// owner sums its own values and the N-1 regions of its scratch (local memory) and pushes the sum
+// into every rank's bucket, (4) barrier.  Same bytes per direction, 2 (N-1)/N bucket sizes.
+// Element j of a slice is handled by the same (block, thread) on every rank, so the per-block
+// barriers order exactly the data a block consumes.
+struct PushBufs { float4* buf[P2P_MAX_WORLD]; float4* scratch[P2P_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(512)
+push_allreduce_fused_kernel(const __grid_constant__ PushBufs b, long long per, long long total,
+                            uint32_t* const* __restrict__ pads, uint32_t word0, int rank, int world) {
+  peer_barrier(pads, word0, rank, world);            // every bucket is final, every scratch is free
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) continue;
+    const long long base = per * p;
+    const long long n_p = min(per, total - base);
+    float4* dst = b.scratch[p] + per * rank;
+    const float4* src = b.buf[rank] + base;
+    long long j = t0;
+    for (; j + stride < n_p; j += 2 * stride) {      // two independent 16-byte copies in flight
+      const float4 v0 = ld_peer(src + j), v1 = ld_peer(src + j + stride);
+      st_peer(dst + j, v0);
+      st_peer(dst + j + stride, v1);
+    }
+    if (j < n_p) st_peer(dst + j, ld_peer(src + j));
+  }
+  __threadfence_system();
+  __syncthreads();
+  peer_barrier(pads, word0, rank, world);            // all pushes have landed
+  __syncthreads();
+  {
+    const long long base = per * rank;
+    const long long n_r = min(per, total - base);
+    for (long long j = t0; j < n_r; j += stride) {
+      float4 acc = ld_peer(b.buf[rank] + base + j);
+      for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        const float4 w = ld_peer(b.scratch[rank] + per * q + j);
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+      }
+      for (int p = 0; p < world; ++p) st_peer(b.buf[p] + base + j, acc);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  peer_barrier(pads, word0, rank, world);            // every bucket holds every sum
+}
+
 }  // namespace
 }  // namespace gft
 
 extern "C" {
+
+int gft_push_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset, void* const* scratch_ptrs_host,
+                             long long n_floats, int rank, int world, void* const* signal_pads_dev, int pad_words,
+                             int blocks, gft_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!buffer_ptrs_host || !scratch_ptrs_host || !signal_pads_dev)
+    return gft::set_error(-1, "gft_push_allreduce_fused: null pointer");
+  if (world <= 0 || world > gft::P2P_MAX_WORLD || rank < 0 || rank >= world)
+    return gft::set_error(-1, "gft_push_allreduce_fused: bad rank / world (at most 8 ranks)");
+  if (n_floats < 0 || (n_floats & 3) || (byte_offset & 15))
+    return gft::set_error(-1, "gft_push_allreduce_fused: length must be a multiple of 4 floats, offset of 16 bytes");
+  gft::PushBufs pb;
+  for (int p = 0; p < gft::P2P_MAX_WORLD; ++p) {
+    char* bb = p < world ? static_cast<char*>(buffer_ptrs_host[p]) : nullptr;
+    char* sb = p < world ? static_cast<char*>(scratch_ptrs_host[p]) : nullptr;
+    if (p < world && (!bb || !sb || (reinterpret_cast<uintptr_t>(bb) & 15) || (reinterpret_cast<uintptr_t>(sb) & 15)))
+      return gft::set_error(-1, "gft_push_allreduce_fused: buffer pointers must be non-null and 16-byte aligned");
+    pb.buf[p] = bb ? reinterpret_cast<float4*>(bb + byte_offset) : nullptr;
+    pb.scratch[p] = reinterpret_cast<float4*>(sb);
+  }
+  const long long total = n_floats >> 2;
+  const long long per = (total + world - 1) / world;
+  const int word0 = pad_words / 2;
+  int max_blocks = (pad_words - word0) / world;
+  if (max_blocks < 1) return gft::set_error(-1, "gft_push_allreduce_fused: signal pad too small");
+  long long want = blocks > 0 ? blocks : (long long)gft::sm_count();
+  const long long need = (per + 512 - 1) / 512;
+  if (want > need) want = need > 0 ? need : 1;
+  if (want > max_blocks) want = max_blocks;
+  gft::push_allreduce_fused_kernel<<<(int)want, 512, 0, stream>>>(
+      pb, per, total, reinterpret_cast<uint32_t* const*>(signal_pads_dev), (uint32_t)word0, rank, world);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return gft::set_error(-2, cudaGetErrorString(err));
+  gft::note_launches(1);
+  return 0;
+}
 
 int gft_p2p_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset, long long n_floats, int rank,
                             int world, void* const* signal_pads_dev, int pad_words, int blocks, int unroll,

@@ -102,6 +102,9 @@ def _lib():
         lib.gft_p2p_allreduce_fused.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.gft_p2p_allreduce_fused.restype = C.c_int
+        lib.gft_push_allreduce_fused.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.gft_push_allreduce_fused.restype = C.c_int
         _declared = True
     return lib
 

@@ -243,6 +243,16 @@ int gft_p2p_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset
                             int world, void* const* signal_pads_dev, int pad_words, int blocks, int unroll,
                             gft_stream_t stream);
 
+/* The peer-to-peer exchange with posted stores only (remote loads are the slow half of the kernel
+ * above): every rank pushes the slices it does not own into region [rank] of the owner's scratch,
+ * barrier, the owner sums own values + its scratch regions and pushes the sums into every bucket,
+ * barrier.  `scratch_ptrs_host`: HOST array of `world` device pointers to a second symmetric
+ * buffer of at least world * ceil(n_floats / 4 / world) * 16 bytes per rank, used by nothing else
+ * while the call runs.  world <= 8.  Collective. */
+int gft_push_allreduce_fused(void* const* buffer_ptrs_host, long long byte_offset, void* const* scratch_ptrs_host,
+                             long long n_floats, int rank, int world, void* const* signal_pads_dev, int pad_words,
+                             int blocks, gft_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

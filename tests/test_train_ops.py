@@ -134,7 +134,7 @@ def test_train_header_symbols_are_exported():
     assert names == ["gft_adam_step", "gft_assemble_backward", "gft_assemble_forward", "gft_densify_apply",
                      "gft_densify_plan", "gft_densify_workspace_bytes", "gft_fused_loss",
                      "gft_fused_loss_scratch_bytes", "gft_nvls_allreduce_fused", "gft_nvls_allreduce_sum",
-                     "gft_p2p_allreduce_fused"]
+                     "gft_p2p_allreduce_fused", "gft_push_allreduce_fused"]
     from gftorf_b200 import _capi
     lib = C.CDLL(_capi.LIB_PATH)
     for n in names:

@@ -46,7 +46,7 @@ res = {"P": P, "world": world, "MB": b.nbytes() / 1e6}
 x = torch.randn(b.flat.numel(), device=dev, generator=torch.Generator(dev).manual_seed(rank + 1))
 ref = x.clone(); dist.all_reduce(ref)
 if b._symm is not None:
-    for mode in ("nvls", "nvls_fused") + (("p2p_fused",) if world <= 8 else ()):
+    for mode in ("nvls", "nvls_fused") + (("p2p_fused", "push_fused") if world <= 8 else ()):
         b.mode = mode
         b.flat.copy_(x)
         b.allreduce()
@@ -75,6 +75,21 @@ if b._symm is not None:
             t = timeit(lambda: b.allreduce(), iters=20)
             res[f"p2p_b{shape[0]}_u{shape[1]}"] = t
             say(f"p2p blocks={shape[0]} unroll={shape[1]}: {t:.4f} ms")
+    if world <= 8:
+        b.mode = "push_fused"
+        for nb in (32, 64, 148, 296, 592):
+            b.push_blocks = nb
+            b.flat.copy_(x)
+            b.allreduce()
+            torch.cuda.synchronize()
+            assert float((b.flat - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), nb
+            chk = b.flat.double().sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert float(lo) == float(hi), nb
+            t = timeit(lambda: b.allreduce(), iters=20)
+            res[f"push_b{nb}"] = t
+            say(f"push blocks={nb}: {t:.4f} ms")
     for blocks in (16, 32, 48, 64, 96, 148, 296):
         for unroll in (2, 4, 8):
             def f():
